@@ -1,0 +1,364 @@
+// k_ekf.cu — dense covariance algebra on the device-resident P.
+// Replaces StateHelper::EKFUpdate (ov_msckf/src/state/StateHelper.cpp:116-197), StateHelper::EKFPropagation (:36-114),
+// StateHelper::clone / augment_clone's time-offset term (:341-391, :604-615), StateHelper::marginalize (:271-339) and
+// get_marginal_covariance (:226-254).
+//
+// EKFUpdate on the device:   M = P[:,cols] H'   S = H M[cols,:] + R   S = L L'   Y = M L^-T   w = L^-1 res
+//                            P <- sym_U(P - Y Y')      dx = Y w
+// (K M' = M S^-1 M' = Y Y' and K res = Y w, so neither S^-1 nor K is formed; the reference forms both.)
+// P is row-major with a fixed leading dimension so clone() grows it in place.
+#include "chol.cuh"
+#include "ovb_internal.cuh"
+
+#define EK_T 32
+
+// C[x][y] = sum_j Aop(x,j) * Bop(j,y), 32x32 tile per CTA, 256 threads (4 outputs each), K tiles of 32.
+//  mode 0 (M = P[:,cols] H'):  Aop(a,j) = P[cs[j]*ldP + a]      Bop(j,i) = H[i*ldH + j]      C = M [N x r]
+//  mode 1 (S = H M[cols,:]+R): Aop(i,j) = H[i*ldH + j]          Bop(j,k) = M[cs[j]*ldM + k]  C = S [r x r], lower tiles only
+__global__ void __launch_bounds__(256) k_ekf_gemm(int mode, const double *__restrict__ P, int ldP, const double *__restrict__ H, int ldH,
+                                                  const double *__restrict__ Min, int ldM, const DevUpdateInfo *__restrict__ info, int X, int Y,
+                                                  int K, double *__restrict__ Cout, int ldC, double sigma2, const double *__restrict__ Rdiag) {
+  __shared__ double As[EK_T][EK_T + 1]; // [j][x]
+  __shared__ double Bs[EK_T][EK_T + 1]; // [j][y]
+  const int x0 = blockIdx.x * EK_T, y0 = blockIdx.y * EK_T;
+  if (mode == 1 && y0 > x0 + EK_T - 1)
+    return; // strictly upper tile of S
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5; // ty 0..7
+  double acc[4] = {0, 0, 0, 0};
+  const int *cs = info->col_state;
+  for (int j0 = 0; j0 < K; j0 += EK_T) {
+    // load tiles
+    for (int e = tid; e < EK_T * EK_T; e += 256) {
+      int jj = e >> 5, q = e & 31; // jj = k index in tile, q = x or y
+      int j = j0 + jj;
+      double av = 0.0, bv = 0.0;
+      if (j < K) {
+        if (mode == 0) {
+          int a = x0 + q;
+          if (a < X)
+            av = P[(size_t)cs[j] * ldP + a];
+        } else {
+          // Aop(i,j) = H[i][j]: transpose load (lanes over q=i → strided); small matrices, acceptable
+          int i = x0 + q;
+          if (i < X)
+            av = H[(size_t)i * ldH + j];
+        }
+        if (mode == 0) {
+          int i = y0 + q;
+          if (i < Y)
+            bv = H[(size_t)i * ldH + j];
+        } else {
+          int k = y0 + q;
+          if (k < Y)
+            bv = Min[(size_t)cs[j] * ldM + k];
+        }
+      }
+      As[jj][q] = av;
+      Bs[jj][q] = bv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int jj = 0; jj < EK_T; jj++) {
+      double b = Bs[jj][tx];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        acc[u] += As[jj][ty + 8 * u] * b;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    int x = x0 + ty + 8 * u, y = y0 + tx;
+    if (x < X && y < Y) {
+      double v = acc[u];
+      if (mode == 1 && x == y)
+        v += Rdiag ? Rdiag[x] : sigma2;
+      Cout[(size_t)x * ldC + y] = v;
+    }
+  }
+}
+
+// single CTA: S (r x r, lower) plus the residual as row r  ->  L and w = L^-1 res in row r. Works in shared memory when
+// it fits, else in place in global memory (L2).
+__global__ void __launch_bounds__(1024) k_ekf_chol(double *__restrict__ S, int ldS, int r, const double *__restrict__ res, double *__restrict__ w,
+                                                   DevUpdateInfo *__restrict__ info, int use_smem) {
+  extern __shared__ __align__(16) double chol_sm[];
+  __shared__ int flag;
+  const int tid = threadIdx.x;
+  if (tid == 0)
+    flag = 0;
+  for (int j = tid; j < r; j += 1024)
+    S[(size_t)r * ldS + j] = res[j];
+  __syncthreads();
+  double *W = S;
+  int ld = ldS;
+  if (use_smem) {
+    ld = r | 1;
+    W = chol_sm;
+    for (int e = tid; e < (r + 1) * r; e += 1024) {
+      int i = e / r, j = e % r;
+      if (j <= i)
+        W[i * ld + j] = S[(size_t)i * ldS + j];
+    }
+    __syncthreads();
+  }
+  chol_lower_block<1024>(W, ld, r, 1, &flag);
+  __syncthreads();
+  if (use_smem) {
+    for (int e = tid; e < (r + 1) * r; e += 1024) {
+      int i = e / r, j = e % r;
+      if (j <= i)
+        S[(size_t)i * ldS + j] = W[i * ld + j];
+    }
+  }
+  for (int j = tid; j < r; j += 1024)
+    w[j] = W[(size_t)r * ld + j];
+  if (tid == 0 && flag)
+    info->not_spd = 1;
+}
+
+// Y = M L^-T : each CTA owns 32 rows of M (independent triangular solves), blocked by 16 columns.
+__global__ void __launch_bounds__(256) k_ekf_trsm(const double *__restrict__ M, int ldM, const double *__restrict__ L, int ldL, int N, int r,
+                                                  double *__restrict__ Yout, int ldY) {
+  extern __shared__ __align__(16) double ysm[]; // [32][ldy]
+  const int ldy = r | 1;
+  const int a0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 32 * r; e += 256) {
+    int a = e / r, j = e % r;
+    ysm[a * ldy + j] = (a0 + a < N) ? M[(size_t)(a0 + a) * ldM + j] : 0.0;
+  }
+  __syncthreads();
+  for (int kb = 0; kb < r; kb += 16) {
+    int nbk = min(16, r - kb);
+    // y[a][kb+c] -= sum_{t<kb} y[a][t] L[kb+c][t]
+    for (int e = tid; e < 32 * nbk; e += 256) {
+      int c = e >> 5, a = e & 31; // lanes over rows a (y column access is conflict-free with odd ldy), warps over c
+      const double *Lr = L + (size_t)(kb + c) * ldL;
+      double acc = 0.0;
+      for (int t = 0; t < kb; t++)
+        acc += ysm[a * ldy + t] * Lr[t];
+      ysm[a * ldy + kb + c] -= acc;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int a = tid;
+      for (int c = 0; c < nbk; c++) {
+        const double *Lr = L + (size_t)(kb + c) * ldL;
+        double v = ysm[a * ldy + kb + c];
+        for (int t = 0; t < c; t++)
+          v -= ysm[a * ldy + kb + t] * Lr[kb + t];
+        ysm[a * ldy + kb + c] = v / Lr[kb + c];
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < 32 * r; e += 256) {
+    int a = e / r, j = e % r;
+    if (a0 + a < N)
+      Yout[(size_t)(a0 + a) * ldY + j] = ysm[a * ldy + j];
+  }
+}
+
+// P <- sym_U(P - Y Y'): upper tiles only, mirrored on write; negative-diagonal check; dx = Y w on the diagonal tiles' rows
+__global__ void __launch_bounds__(256) k_ekf_downdate(double *__restrict__ P, int ldP, const double *__restrict__ Yin, int ldY, int N, int r,
+                                                      const double *__restrict__ w, double *__restrict__ dx, DevUpdateInfo *__restrict__ info) {
+  __shared__ double As[EK_T][EK_T + 1]; // [k][a]
+  __shared__ double Bs[EK_T][EK_T + 1]; // [k][b]
+  const int a0 = blockIdx.x * EK_T, b0 = blockIdx.y * EK_T;
+  if (b0 < a0)
+    return;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  double acc[4] = {0, 0, 0, 0};
+  double dxa = 0.0; // dx partial for row a0 + tid (diagonal tiles, tid < 32)
+  for (int k0 = 0; k0 < r; k0 += EK_T) {
+    for (int e = tid; e < EK_T * EK_T; e += 256) {
+      int q = e >> 5, kk = e & 31; // lanes over k: coalesced rows of Y
+      int k = k0 + kk;
+      As[kk][q] = (k < r && a0 + q < N) ? Yin[(size_t)(a0 + q) * ldY + k] : 0.0;
+      Bs[kk][q] = (k < r && b0 + q < N) ? Yin[(size_t)(b0 + q) * ldY + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < EK_T; kk++) {
+      double b = Bs[kk][tx];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        acc[u] += As[kk][ty + 8 * u] * b;
+    }
+    if (a0 == b0 && tid < EK_T) {
+      for (int kk = 0; kk < EK_T; kk++)
+        if (k0 + kk < r)
+          dxa += As[kk][tid] * w[k0 + kk];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    int a = a0 + ty + 8 * u, b = b0 + tx;
+    if (a < N && b < N && b >= a) {
+      double v = P[(size_t)a * ldP + b] - acc[u];
+      P[(size_t)a * ldP + b] = v;
+      P[(size_t)b * ldP + a] = v;
+      if (a == b && v < 0.0)
+        atomicMin(&info->neg_diag_index, a);
+      if (!isfinite(v))
+        info->nonfinite = 1;
+    }
+  }
+  if (a0 == b0 && tid < EK_T && a0 + tid < N)
+    dx[a0 + tid] = dxa;
+}
+
+__global__ void k_ekf_prep(DevUpdateInfo *info) {
+  info->neg_diag_index = 0x7fffffff;
+  info->not_spd = 0;
+  info->nonfinite = 0;
+}
+
+// H: r x n (row-major, ldHm), r <= n <= N (callers compress first when r > n); column j of H is state column
+// d_info->col_state[j]. Everything is enqueued on the context stream; flags land in d_info.
+void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bool sizes_from_info, double sigma2, const double *Rdiag_dev) {
+  (void)sizes_from_info;
+  const int N = ctx->N;
+  const int ld = ctx->ldP;
+  double *P = ctx->P[ctx->cur];
+  k_ekf_prep<<<1, 1, 0, ctx->stream>>>(ctx->d_info);
+  if (r <= 0 || n <= 0)
+    return;
+  dim3 g0((N + EK_T - 1) / EK_T, (r + EK_T - 1) / EK_T);
+  k_ekf_gemm<<<g0, 256, 0, ctx->stream>>>(0, P, ld, H, ldHm, nullptr, 0, ctx->d_info, N, r, n, ctx->d_M, ld, 0.0, nullptr);
+  dim3 g1((r + EK_T - 1) / EK_T, (r + EK_T - 1) / EK_T);
+  k_ekf_gemm<<<g1, 256, 0, ctx->stream>>>(1, P, ld, H, ldHm, ctx->d_M, ld, ctx->d_info, r, r, n, ctx->d_S, ld, sigma2, Rdiag_dev);
+  size_t chol_bytes = sizeof(double) * (size_t)(r + 1) * (size_t)(r | 1);
+  int use_smem = chol_bytes <= 200 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_ekf_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_ekf_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  // the residual vector is column n of H's row (TSQR output) or a separate buffer: callers stage it in d_w
+  k_ekf_chol<<<1, 1024, use_smem ? chol_bytes : 0, ctx->stream>>>(ctx->d_S, ld, r, ctx->d_w, ctx->d_w, ctx->d_info, use_smem);
+  size_t trsm_bytes = sizeof(double) * 32 * (size_t)(r | 1);
+  k_ekf_trsm<<<(N + 31) / 32, 256, trsm_bytes, ctx->stream>>>(ctx->d_M, ld, ctx->d_S, ld, N, r, ctx->d_Y, ld);
+  dim3 g2((N + EK_T - 1) / EK_T, (N + EK_T - 1) / EK_T);
+  k_ekf_downdate<<<g2, 256, 0, ctx->stream>>>(P, ld, ctx->d_Y, ld, N, r, ctx->d_w, ctx->d_dx, ctx->d_info);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// covariance structure operations
+
+// StateHelper::clone: append a copy of the `size`-wide variable at old_off (StateHelper.cpp:371-373)
+__global__ void k_cov_clone(double *P, int ld, int N, int old_off, int size) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int N2 = N + size;
+  if (idx >= N2 * size)
+    return;
+  int i = idx / size, j = idx % size; // element (i, N+j) and its mirror (N+j, i)
+  double v;
+  if (i < N)
+    v = P[(size_t)i * ld + old_off + j];
+  else
+    v = P[(size_t)(old_off + (i - N)) * ld + old_off + j];
+  double vr = (i < N) ? P[(size_t)(old_off + j) * ld + i] : v;
+  P[(size_t)i * ld + N + j] = v;
+  if (i < N)
+    P[(size_t)(N + j) * ld + i] = vr;
+}
+// augment_clone time-offset term, step 1: P[:, N..N+size) += P[:, dt] dnc'   (StateHelper.cpp:611-612)
+__global__ void k_cov_dt_cols(double *P, int ld, int N2, int new_off, int size, int dt_off, const double *dnc) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N2 * size)
+    return;
+  int i = idx / size, j = idx % size;
+  P[(size_t)i * ld + new_off + j] += P[(size_t)i * ld + dt_off] * dnc[j];
+}
+// step 2: P[N..N+size, :] += dnc P[dt, :]   (StateHelper.cpp:613-614) — reads the row written by step 1
+__global__ void k_cov_dt_rows(double *P, int ld, int N2, int new_off, int size, int dt_off, const double *dnc) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N2 * size)
+    return;
+  int i = idx / N2, j = idx % N2;
+  P[(size_t)(new_off + i) * ld + j] += dnc[i] * P[(size_t)dt_off * ld + j];
+}
+
+void launch_cov_clone(ovb_ctx *ctx, int old_off, int size, const double *dnc_dt_dev, int dt_off) {
+  double *P = ctx->P[ctx->cur];
+  int N = ctx->N, N2 = N + size;
+  int tot = N2 * size;
+  k_cov_clone<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(P, ctx->ldP, N, old_off, size);
+  if (dnc_dt_dev) {
+    k_cov_dt_cols<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(P, ctx->ldP, N2, N, size, dt_off, dnc_dt_dev);
+    k_cov_dt_rows<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(P, ctx->ldP, N2, N, size, dt_off, dnc_dt_dev);
+  }
+}
+
+// StateHelper::marginalize (StateHelper.cpp:293-313): out of place into the other buffer; the x2-x1 block is the
+// transpose of the copied x1-x2 block exactly as the reference builds it.
+__global__ void k_cov_marg(const double *Pin, double *Pout, int ld, int N, int off, int size) {
+  int N2 = N - size;
+  int i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N2 || j >= N2)
+    return;
+  int si = i < off ? i : i + size, sj = j < off ? j : j + size;
+  double v = (i >= off && j < off) ? Pin[(size_t)sj * ld + si] : Pin[(size_t)si * ld + sj];
+  Pout[(size_t)i * ld + j] = v;
+}
+
+void launch_cov_marginalize(ovb_ctx *ctx, int off, int size) {
+  int N2 = ctx->N - size;
+  dim3 b(32, 8), g((N2 + 31) / 32, (N2 + 7) / 8);
+  k_cov_marg<<<g, b, 0, ctx->stream>>>(ctx->P[ctx->cur], ctx->P[ctx->cur ^ 1], ctx->ldP, ctx->N, off, size);
+}
+
+// EKFPropagation (StateHelper.cpp:80-100). old_idx[k] = covariance index of Phi's column k (q of them).
+//  C[a][j]   = sum_k P[a][old_idx[k]] Phi[j][k]                       (Cov_PhiT, N x p)  -> Cbuf
+//  PCP[i][j] = Qsym[i][j] + sum_k Phi[i][k] C[old_idx[k]][j]          (p x p)            -> Sbuf
+__global__ void k_prop_C(const double *P, int ld, int N, int p, int q, const int *old_idx, const double *Phi, double *Cbuf, int ldC) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * p)
+    return;
+  int a = idx / p, j = idx % p;
+  double acc = 0.0;
+  for (int k = 0; k < q; k++)
+    acc += P[(size_t)a * ld + old_idx[k]] * Phi[(size_t)j * q + k];
+  Cbuf[(size_t)a * ldC + j] = acc;
+}
+__global__ void k_prop_PCP(const double *Cbuf, int ldC, int p, int q, const int *old_idx, const double *Phi, const double *Q, double *Sbuf,
+                           int ldS) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p * p)
+    return;
+  int i = idx / p, j = idx % p;
+  double acc = (i <= j) ? Q[(size_t)i * p + j] : Q[(size_t)j * p + i];
+  for (int k = 0; k < q; k++)
+    acc += Phi[(size_t)i * q + k] * Cbuf[(size_t)old_idx[k] * ldC + j];
+  Sbuf[(size_t)i * ldS + j] = acc;
+}
+__global__ void k_prop_write(double *P, int ld, int N, int new_off, int p, const double *Cbuf, int ldC, const double *Sbuf, int ldS,
+                             DevUpdateInfo *info) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * p)
+    return;
+  int a = idx / p, j = idx % p;
+  if (a >= new_off && a < new_off + p) {
+    double v = Sbuf[(size_t)(a - new_off) * ldS + j];
+    P[(size_t)a * ld + new_off + j] = v;
+    if (a - new_off == j && v < 0.0)
+      atomicMin(&info->neg_diag_index, a);
+  } else {
+    double v = Cbuf[(size_t)a * ldC + j];
+    P[(size_t)a * ld + new_off + j] = v;
+    P[(size_t)(new_off + j) * ld + a] = v;
+  }
+}
+
+void launch_cov_propagate(ovb_ctx *ctx, int new_off, int p, int q, const int *old_idx_dev, const double *Phi_dev, const double *Q_dev) {
+  double *P = ctx->P[ctx->cur];
+  int N = ctx->N, ld = ctx->ldP;
+  k_ekf_prep<<<1, 1, 0, ctx->stream>>>(ctx->d_info);
+  k_prop_C<<<(N * p + 255) / 256, 256, 0, ctx->stream>>>(P, ld, N, p, q, old_idx_dev, Phi_dev, ctx->d_M, ld);
+  k_prop_PCP<<<(p * p + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_M, ld, p, q, old_idx_dev, Phi_dev, Q_dev, ctx->d_S, ld);
+  k_prop_write<<<(N * p + 255) / 256, 256, 0, ctx->stream>>>(P, ld, N, new_off, p, ctx->d_M, ld, ctx->d_S, ld, ctx->d_info);
+}

@@ -1,0 +1,451 @@
+// k_tsqr.cu — measurement compression as a communication-avoiding blocked Householder QR (TSQR/CAQR), plus the
+// stacked-column bookkeeping of UpdaterMSCKF::update.
+// Replaces UpdaterHelper::measurement_compress_inplace (ov_msckf/src/update/UpdaterHelper.cpp:456-487: a Givens sweep
+// of 3mn² flops with stride-m accesses) and the first-seen column map of UpdaterMSCKF.cpp:237-245.
+//
+// Layout: the stacked system [H | r] is row-major in HBM/L2 (m x (n+1), leading dimension ldA). For each column panel
+// (NB = 16 wide) the active rows are cut into chunks of CR = 256 rows; a CTA owns (chunk, column tile group):
+//   1. panel factorisation in registers: one row per thread, Householder by column with ONE 16-wide block reduction
+//      per column (p_j = a_k·a_j gives the column norm, all v'a_j and the reflector Gram row at once),
+//   2. compact-WY application to the chunk's trailing columns as two shared-memory GEMMs (Y = V'A, A -= V Z),
+//   3. the chunk's 16 x 16 R goes to a small workspace; the next level repeats 1-2 on the stacked R factors
+//      (rows addressed in place through an index map), until one chunk is left.
+// Chunks never exchange data inside a level (no grid-wide sync, no atomics: bitwise reproducible); Q is never formed.
+// The reference's Givens R has diag >= 0; rows of R (and z) are sign-flipped at the end to match.
+#include "ovb_internal.cuh"
+#include <math.h>
+
+#define QR_NB OVB_NB
+#define QR_CR OVB_CR
+#define QR_CT 32
+#define QR_THREADS QR_CR
+#define QR_WARPS (QR_THREADS / 32)
+#define QR_KG 4 // k-groups in the Y = V'A product
+
+struct QrSmem {
+  double Vs[QR_CR][QR_NB];            // reflectors (unit lower trapezoid)
+  double At[QR_CR][QR_CT];            // trailing tile
+  double Yp[QR_KG][QR_NB][QR_CT];     // partial V'A
+  double Zs[QR_NB][QR_CT];            // (T' V'A)
+  double wred[2][QR_WARPS][QR_NB];    // per-warp partial sums, double buffered
+  double fin[2][QR_NB];               // block totals
+  double rowk[2][QR_NB];              // pivot row broadcast
+  double G[QR_NB][QR_NB];             // strict lower: v_k'v_i
+  double tau[QR_NB];
+  int rowidx[QR_CR];
+};
+
+// sum of 16 per-lane values over the warp with the halving butterfly: 16 double shuffles instead of 80.
+// On return lane L holds in `out` the warp total of value index j(L) = 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of L).
+__device__ __forceinline__ double warp_reduce16(const double x[QR_NB], int lane) {
+  double y8[8], y4[4], y2[2], y1;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double send = h16 ? x[i] : x[i + 8];
+    double keep = h16 ? x[i + 8] : x[i];
+    y8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double send = h8 ? y8[i] : y8[i + 4];
+    double keep = h8 ? y8[i + 4] : y8[i];
+    y4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    double send = h4 ? y4[i] : y4[i + 2];
+    double keep = h4 ? y4[i + 2] : y4[i];
+    y2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    double send = h2 ? y2[0] : y2[1];
+    double keep = h2 ? y2[1] : y2[0];
+    y1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
+  return y1;
+}
+__device__ __forceinline__ int reduce16_index(int lane) {
+  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+
+// One (panel, level) step. grid = (chunks, column-tile groups).
+__global__ void __launch_bounds__(QR_THREADS)
+    k_tsqr_level(double *__restrict__ A, int ldA, int nt, int c0, int nbp, int level, int len, const double *__restrict__ Win,
+                 double *__restrict__ Wout, double *__restrict__ Rout, int ldR, int is_last) {
+  extern __shared__ __align__(16) unsigned char qr_smem_raw[];
+  QrSmem &sm = *reinterpret_cast<QrSmem *>(qr_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int chunk = blockIdx.x;
+  const int rows_i = min(QR_CR, len - chunk * QR_CR);
+  // ---- row map of this level back to rows of A
+  {
+    int g = chunk * QR_CR + tid;
+    for (int l = level; l >= 1; l--)
+      g = (g / nbp) * QR_CR + (g % nbp);
+    sm.rowidx[tid] = c0 + g;
+  }
+  // ---- load the panel row
+  double a[QR_NB];
+#pragma unroll
+  for (int j = 0; j < QR_NB; j++)
+    a[j] = 0.0;
+  if (tid < rows_i) {
+    if (level == 0) {
+      const double *src = A + (size_t)(c0 + chunk * QR_CR + tid) * ldA + c0;
+#pragma unroll
+      for (int j = 0; j < QR_NB; j++)
+        if (j < nbp)
+          a[j] = src[j];
+    } else {
+      const double *src = Win + (size_t)(chunk * QR_CR + tid) * QR_NB;
+#pragma unroll
+      for (int j = 0; j < QR_NB; j++)
+        if (j < nbp)
+          a[j] = src[j];
+    }
+  }
+  // ---- Householder by column
+#pragma unroll
+  for (int k = 0; k < QR_NB; k++) {
+    if (k >= nbp)
+      break;
+    const int buf = k & 1;
+    const bool below = (tid > k && tid < rows_i);
+    double p[QR_NB];
+    const double ak = a[k];
+#pragma unroll
+    for (int j = 0; j < QR_NB; j++)
+      p[j] = below ? ak * a[j] : 0.0;
+    double tot = warp_reduce16(p, lane);
+    if ((lane & 1) == 0)
+      sm.wred[buf][wid][reduce16_index(lane)] = tot;
+    if (tid == k) {
+#pragma unroll
+      for (int j = 0; j < QR_NB; j++)
+        sm.rowk[buf][j] = a[j];
+    }
+    __syncthreads();
+    if (tid < QR_NB) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < QR_WARPS; w++)
+        s += sm.wred[buf][w][tid];
+      sm.fin[buf][tid] = s;
+    }
+    __syncthreads();
+    const double alpha = sm.rowk[buf][k];
+    const double sigma = sm.fin[buf][k];
+    double beta, scale, tk;
+    if (sigma == 0.0) {
+      tk = 0.0;
+      beta = alpha;
+      scale = 0.0;
+    } else {
+      beta = sqrt(alpha * alpha + sigma);
+      if (alpha >= 0.0)
+        beta = -beta;
+      tk = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    const double vr = below ? ak * scale : (tid == k ? 1.0 : 0.0);
+#pragma unroll
+    for (int j = 0; j < QR_NB; j++) {
+      if (j > k && j < nbp) {
+        double wj = sm.rowk[buf][j] + sm.fin[buf][j] * scale;
+        if (tid >= k && tid < rows_i)
+          a[j] -= tk * wj * vr;
+      }
+    }
+    if (below)
+      a[k] = vr;
+    else if (tid == k)
+      a[k] = beta;
+    if (tid == 0) {
+      sm.tau[k] = tk;
+#pragma unroll
+      for (int i = 0; i < QR_NB; i++)
+        if (i < k)
+          sm.G[k][i] = sm.rowk[buf][i] + sm.fin[buf][i] * scale; // v_k'v_i
+    }
+  }
+  // ---- publish V, emit this chunk's R
+#pragma unroll
+  for (int j = 0; j < QR_NB; j++) {
+    double v = 0.0;
+    if (j < nbp && tid < rows_i)
+      v = (j < tid) ? a[j] : (j == tid ? 1.0 : 0.0);
+    sm.Vs[tid][j] = v;
+  }
+  if (blockIdx.y == 0 && tid < nbp) {
+    // rows beyond the chunk's height do not exist: the next level reads only min(nbp, rows_i) rows per chunk
+    if (tid < rows_i) {
+      if (is_last) {
+        double *dst = Rout + (size_t)(c0 + tid) * ldR + c0;
+#pragma unroll
+        for (int j = 0; j < QR_NB; j++)
+          if (j < nbp)
+            dst[j] = (j >= tid) ? a[j] : 0.0;
+      } else {
+        double *dst = Wout + (size_t)(chunk * nbp + tid) * QR_NB;
+#pragma unroll
+        for (int j = 0; j < QR_NB; j++)
+          dst[j] = (j >= tid && j < nbp) ? a[j] : 0.0;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- apply Q' to the trailing column tiles owned by this CTA
+  const int tc0 = c0 + nbp;
+  const int ntrail = nt - tc0;
+  const int ntiles = (ntrail + QR_CT - 1) / QR_CT;
+  for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+    const int col0 = tc0 + tile * QR_CT;
+    const int ncol = min(QR_CT, nt - col0);
+    // load tile (warp per row, lanes over columns: coalesced 256 B rows)
+    for (int r = wid; r < QR_CR; r += QR_WARPS) {
+      double v = 0.0;
+      if (r < rows_i && lane < ncol)
+        v = A[(size_t)sm.rowidx[r] * ldA + col0 + lane];
+      sm.At[r][lane] = v;
+    }
+    __syncthreads();
+    // Y = V'At : thread = (kgroup, 4 V-columns, 2 tile columns), 64 rows each
+    {
+      const int kg = tid >> 6, within = tid & 63, ib = within >> 4, cb = within & 15;
+      double acc[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        acc[i][0] = acc[i][1] = 0.0;
+      const int r0 = kg * (QR_CR / QR_KG);
+#pragma unroll 4
+      for (int r = r0; r < r0 + QR_CR / QR_KG; r++) {
+        const double2 v01 = *reinterpret_cast<const double2 *>(&sm.Vs[r][4 * ib]);
+        const double2 v23 = *reinterpret_cast<const double2 *>(&sm.Vs[r][4 * ib + 2]);
+        const double2 at = *reinterpret_cast<const double2 *>(&sm.At[r][2 * cb]);
+        acc[0][0] += v01.x * at.x;
+        acc[0][1] += v01.x * at.y;
+        acc[1][0] += v01.y * at.x;
+        acc[1][1] += v01.y * at.y;
+        acc[2][0] += v23.x * at.x;
+        acc[2][1] += v23.x * at.y;
+        acc[3][0] += v23.y * at.x;
+        acc[3][1] += v23.y * at.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        sm.Yp[kg][4 * ib + i][2 * cb] = acc[i][0];
+        sm.Yp[kg][4 * ib + i][2 * cb + 1] = acc[i][1];
+      }
+    }
+    __syncthreads();
+    // Z: sequential reflector coupling per column, z_k = tau_k (y_k - sum_{i<k} G[k][i] z_i)
+    if (tid < QR_CT) {
+      double z[QR_NB];
+#pragma unroll
+      for (int k = 0; k < QR_NB; k++) {
+        double y = 0.0;
+        if (k < nbp) {
+#pragma unroll
+          for (int g = 0; g < QR_KG; g++)
+            y += sm.Yp[g][k][tid];
+#pragma unroll
+          for (int i = 0; i < QR_NB; i++)
+            if (i < k)
+              y -= sm.G[k][i] * z[i];
+          y *= sm.tau[k];
+        }
+        z[k] = y;
+        sm.Zs[k][tid] = y;
+      }
+    }
+    __syncthreads();
+    // At -= V Z : lanes over columns (Z column in registers), warps over rows; then store back
+    {
+      double z[QR_NB];
+#pragma unroll
+      for (int k = 0; k < QR_NB; k++)
+        z[k] = sm.Zs[k][lane];
+      for (int r = wid; r < rows_i; r += QR_WARPS) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < QR_NB; k += 2) {
+          const double2 v = *reinterpret_cast<const double2 *>(&sm.Vs[r][k]);
+          acc += v.x * z[k];
+          acc += v.y * z[k + 1];
+        }
+        if (lane < ncol)
+          A[(size_t)sm.rowidx[r] * ldA + col0 + lane] = sm.At[r][lane] - acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// copy the trailing parts of the finished R rows out of A, zero the strict lower part, normalise diag >= 0
+__global__ void k_tsqr_assemble(const double *__restrict__ A, int ldA, int m, int n, double *__restrict__ Rout, int ldR) {
+  int i = blockIdx.x; // row of R
+  if (i >= n)
+    return;
+  int pend = min(n, (i / QR_NB + 1) * QR_NB); // first column right of this row's panel
+  for (int j = threadIdx.x; j <= n; j += blockDim.x) {
+    if (j < i)
+      Rout[(size_t)i * ldR + j] = 0.0;
+    else if (j >= pend)
+      Rout[(size_t)i * ldR + j] = (i < m) ? A[(size_t)i * ldA + j] : 0.0;
+    else if (i >= m)
+      Rout[(size_t)i * ldR + j] = 0.0;
+  }
+  __syncthreads();
+  double d = Rout[(size_t)i * ldR + i];
+  __syncthreads(); // everyone has read the diagonal before anyone flips it
+  if (d < 0.0) {
+    for (int j = threadIdx.x; j <= n; j += blockDim.x)
+      Rout[(size_t)i * ldR + j] = -Rout[(size_t)i * ldR + j];
+  }
+}
+
+void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_tsqr_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QrSmem));
+    attr_set = true;
+  }
+  const int nt = n + 1;
+  // panel blocks of rows that never get factored (m < n) must read as zero
+  cudaMemsetAsync(Rout, 0, sizeof(double) * (size_t)n * ldR, ctx->stream);
+  for (int c0 = 0; c0 < n; c0 += QR_NB) {
+    int nbp = n - c0 < QR_NB ? n - c0 : QR_NB;
+    int len = m - c0;
+    if (len <= 0)
+      break;
+    int level = 0;
+    const int ntiles = (nt - (c0 + nbp) + QR_CT - 1) / QR_CT;
+    while (true) {
+      int chunks = (len + QR_CR - 1) / QR_CR;
+      int last = (chunks == 1);
+      // few chunks: spread the trailing tiles over more CTAs; many chunks: one CTA walks all tiles (no redundant panels)
+      int gy = 1;
+      if (chunks < 2 * ctx->sm_count) {
+        gy = (2 * ctx->sm_count + chunks - 1) / chunks;
+        if (gy > ntiles)
+          gy = ntiles;
+        if (gy < 1)
+          gy = 1;
+      }
+      dim3 grid(chunks, gy);
+      k_tsqr_level<<<grid, QR_THREADS, sizeof(QrSmem), ctx->stream>>>(A, ldA, nt, c0, nbp, level, len, level > 0 ? ctx->d_W[(level - 1) & 1] : nullptr,
+                                                                       ctx->d_W[level & 1], Rout, ldR, last);
+      if (last)
+        break;
+      int rows_last = len - (chunks - 1) * QR_CR;
+      len = (chunks - 1) * nbp + (rows_last < nbp ? rows_last : nbp);
+      level++;
+    }
+  }
+  k_tsqr_assemble<<<n, 128, 0, ctx->stream>>>(A, ldA, m, n, Rout, ldR);
+}
+
+// =====================================================================================================================
+// stacked-column bookkeeping: which variables the accepted features touch, in which order (UpdaterMSCKF.cpp:237-245)
+extern unsigned char *ovb_feat_order_ptr(ovb_ctx *ctx);
+
+__global__ void k_column_map(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, const DevFeat *__restrict__ feats, int n_feats,
+                             const unsigned char *__restrict__ feat_order, DevUpdateInfo *__restrict__ info) {
+  __shared__ unsigned int key[OVB_MAX_VARS];
+  __shared__ int n_used_feats, rows_stacked;
+  __shared__ int order[OVB_MAX_VARS];
+  __shared__ int n_order;
+  const int tid = threadIdx.x;
+  if (tid < OVB_MAX_VARS)
+    key[tid] = 0xffffffffu;
+  if (tid == 0) {
+    n_used_feats = 0;
+    rows_stacked = 0;
+    n_order = 0;
+  }
+  __syncthreads();
+  for (int f = tid; f < n_feats; f += blockDim.x) {
+    if (feats[f].status != OVB_FEAT_OK)
+      continue;
+    atomicAdd(&n_used_feats, 1);
+    atomicAdd(&rows_stacked, 2 * (feats[f].m1 - feats[f].m0) - 3);
+    const unsigned char *ord = feat_order + (size_t)f * (OVB_MAX_VARS + 1);
+    int no = ord[0];
+    for (int q = 0; q < no; q++)
+      atomicMin(&key[ord[1 + q]], ((unsigned int)f << 7) | (unsigned int)q);
+  }
+  __syncthreads();
+  const int n_slots = fr->n_slots;
+  const bool first_seen = (dop->o.col_order == OVB_COLS_REFERENCE_FIRST_SEEN);
+  if (tid < n_slots) {
+    // rank among used slots: first-seen order = ascending key; canonical = ascending slot id
+    int rank = 0, nused = 0;
+    for (int s = 0; s < n_slots; s++) {
+      bool used = key[s] != 0xffffffffu;
+      nused += used ? 1 : 0;
+      if (!used)
+        continue;
+      if (first_seen ? (key[s] < key[tid]) : (s < tid))
+        rank++;
+    }
+    if (!first_seen)
+      order[tid] = tid; // canonical layout: stacked column q IS canonical column q (unused variables stay as zero columns)
+    else if (key[tid] != 0xffffffffu)
+      order[rank] = tid;
+    else {
+      // unused slots go last, in slot order (their columns are all zero)
+      int r2 = 0;
+      for (int s = 0; s < tid; s++)
+        if (key[s] == 0xffffffffu)
+          r2++;
+      order[nused + r2] = tid;
+    }
+    if (tid == 0)
+      n_order = nused;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int col = 0, used_cols = 0;
+    for (int q = 0; q < n_slots; q++) {
+      int s = order[q];
+      info->order_slot[q] = s;
+      for (int k = 0; k < fr->slot_size[s]; k++) {
+        info->col_state[col] = fr->slot_off[s] + k;
+        info->col_canon[col] = fr->slot_col[s] + k;
+        col++;
+      }
+      if (key[s] != 0xffffffffu)
+        used_cols += fr->slot_size[s];
+    }
+    info->n_order = n_order;
+    info->n_used = used_cols;
+    info->n_feats_used = n_used_feats;
+    info->rows_stacked = rows_stacked;
+    info->neg_diag_index = -1;
+    info->not_spd = 0;
+    info->nonfinite = 0;
+  }
+}
+
+void launch_column_map(ovb_ctx *ctx, int n_feats, BlobView bv) {
+  k_column_map<<<1, 256, 0, ctx->stream>>>(ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, ovb_feat_order_ptr(ctx), ctx->d_info);
+}
+
+// B[i][q] = Rin[i][col_canon[q]] for q < n_all, B[i][n_all] = Rin[i][n_all] (residual)
+__global__ void k_gather_cols(const double *__restrict__ Rin, int ldRin, int n_all, const DevUpdateInfo *__restrict__ info, double *__restrict__ B,
+                              int ldB) {
+  int i = blockIdx.x;
+  for (int q = threadIdx.x; q <= n_all; q += blockDim.x) {
+    int src = (q < n_all) ? info->col_canon[q] : n_all;
+    B[(size_t)i * ldB + q] = Rin[(size_t)i * ldRin + src];
+  }
+}
+
+void launch_reorder_R(ovb_ctx *ctx, const double *Rin, int n_all, int ldRin, double *Rout, int ldRout) {
+  // permuted copy into the (now free) staging matrix, then the same TSQR re-triangularises it
+  int ldB = ldRin;
+  k_gather_cols<<<n_all, 128, 0, ctx->stream>>>(Rin, ldRin, n_all, ctx->d_info, ctx->d_Hs, ldB);
+  launch_tsqr(ctx, ctx->d_Hs, n_all, n_all, ldB, Rout, ldRout);
+}

@@ -1,0 +1,861 @@
+// ovb_api.cu — the C ABI of include/ovb200.h: context, host-side marshalling into one pinned arena, stream orchestration.
+// No arithmetic of the path happens on the host: it packs the inputs, launches the kernels of k_*.cu and copies results back.
+#include "ovb_internal.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+static const double g_chi2_table[OVB_CHI2_TABLE_LEN] = {
+#include "chi2_table.inc"
+};
+
+unsigned char *ovb_feat_order_ptr(ovb_ctx *ctx) { return ctx->d_feat_order; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+static ovb_status ensure_stage(ovb_ctx *ctx, size_t doubles);
+
+int ovb_abi_version(void) { return OVB_ABI_VERSION; }
+
+double ovb_chi2_quantile95(int dof) {
+  if (dof < 1)
+    return 0.0;
+  if (dof >= OVB_CHI2_TABLE_LEN)
+    dof = OVB_CHI2_TABLE_LEN - 1;
+  return g_chi2_table[dof];
+}
+
+void ovb_opts_default(ovb_opts *o) {
+  memset(o, 0, sizeof(*o));
+  o->triangulate_1d = 0;
+  o->refine_features = 1;
+  o->max_runs = 5;
+  o->init_lamda = 1e-3;
+  o->max_lamda = 1e10;
+  o->min_dx = 1e-6;
+  o->min_dcost = 1e-6;
+  o->lam_mult = 10;
+  o->min_dist = 0.10;
+  o->max_dist = 60;
+  o->max_baseline = 40;
+  o->max_cond_number = 10000;
+  o->sigma_pix = 1;
+  o->chi2_multipler = 5;
+  o->do_fej = 1;
+  o->feat_rep = OVB_REP_GLOBAL_3D;
+  o->do_calib_camera_pose = 0;
+  o->do_calib_camera_intrinsics = 0;
+  o->col_order = OVB_COLS_CANONICAL;
+}
+
+const char *ovb_last_error(const ovb_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
+  if (!cfg || !out)
+    return OVB_ERR_ARG;
+  *out = nullptr;
+  ovb_ctx *ctx = new (std::nothrow) ovb_ctx();
+  if (!ctx)
+    return OVB_ERR_CAPACITY;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->cfg = *cfg;
+  if (ctx->cfg.max_state < 32)
+    ctx->cfg.max_state = 32;
+  if (ctx->cfg.max_feats < 1)
+    ctx->cfg.max_feats = 1;
+  if (ctx->cfg.max_meas < 2)
+    ctx->cfg.max_meas = 2;
+  ctx->device = cfg->device;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) {
+    delete ctx;
+    return OVB_ERR_CUDA; // no CUDA device: there is no CPU fallback
+  }
+#define CK(call)                                                                                                      \
+  do {                                                                                                                \
+    cudaError_t e_ = (call);                                                                                          \
+    if (e_ != cudaSuccess) {                                                                                          \
+      fprintf(stderr, "ovb_create: %s failed: %s\n", #call, cudaGetErrorString(e_));                                  \
+      ovb_destroy(ctx);                                                                                               \
+      return OVB_ERR_CUDA;                                                                                            \
+    }                                                                                                                 \
+  } while (0)
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++)
+    CK(cudaEventCreate(&ctx->ev[i]));
+  const int ms = ctx->cfg.max_state;
+  ctx->ldP = ms;
+  ctx->N = 0;
+  ctx->cur = 0;
+  CK(cudaMalloc(&ctx->P[0], sizeof(double) * (size_t)ms * ms));
+  CK(cudaMalloc(&ctx->P[1], sizeof(double) * (size_t)ms * ms));
+  CK(cudaMemset(ctx->P[0], 0, sizeof(double) * (size_t)ms * ms));
+  CK(cudaMemset(ctx->P[1], 0, sizeof(double) * (size_t)ms * ms));
+  // input arena
+  ctx->off_opts = align_up(sizeof(DevFrame), 256);
+  ctx->off_feat = ctx->off_opts + align_up(sizeof(DevOpts), 256);
+  ctx->off_blob = ctx->off_feat + align_up(sizeof(DevFeat) * (size_t)ctx->cfg.max_feats, 256);
+  ctx->blob_cap = align_up((size_t)ctx->cfg.max_meas * (1 + 2 + 8 + 8) + (size_t)ctx->cfg.max_feats * OVB_MAX_CAMS + 64, 256);
+  ctx->arena_bytes = ctx->off_blob + ctx->blob_cap;
+  CK(cudaMalloc(&ctx->d_arena, ctx->arena_bytes));
+  CK(cudaMallocHost(&ctx->h_arena, ctx->arena_bytes));
+  ctx->d_frame = (DevFrame *)ctx->d_arena;
+  ctx->d_opts = (DevOpts *)(ctx->d_arena + ctx->off_opts);
+  ctx->d_feat = (DevFeat *)(ctx->d_arena + ctx->off_feat);
+  ctx->d_blob = ctx->d_arena + ctx->off_blob;
+  ctx->h_frame = (DevFrame *)ctx->h_arena;
+  ctx->h_opts = (DevOpts *)(ctx->h_arena + ctx->off_opts);
+  ctx->h_feat = (DevFeat *)(ctx->h_arena + ctx->off_feat);
+  ctx->h_blob = ctx->h_arena + ctx->off_blob;
+  CK(cudaMalloc(&ctx->d_cc, sizeof(DevCamPoses)));
+  CK(cudaMalloc(&ctx->d_feat_order, (size_t)ctx->cfg.max_feats * (OVB_MAX_VARS + 1)));
+  CK(cudaMalloc(&ctx->d_info, sizeof(DevUpdateInfo)));
+  CK(cudaMallocHost(&ctx->h_info, sizeof(DevUpdateInfo)));
+  CK(cudaMallocHost(&ctx->h_dx, sizeof(double) * (size_t)ms));
+  CK(cudaMalloc(&ctx->d_chi2_table, sizeof(g_chi2_table)));
+  CK(cudaMemcpy(ctx->d_chi2_table, g_chi2_table, sizeof(g_chi2_table), cudaMemcpyHostToDevice));
+  // stacked staging matrix
+  ctx->max_rows = ctx->cfg.max_rows > 0 ? ctx->cfg.max_rows : 2 * ctx->cfg.max_meas;
+  if (ctx->max_rows < 2 * ctx->cfg.max_meas)
+    ctx->max_rows = 2 * ctx->cfg.max_meas;
+  int ldcap = std::min(OVB_MAX_COLS, ms) + 8;
+  ctx->Hs_cap = (size_t)ctx->max_rows * ldcap;
+  CK(cudaMalloc(&ctx->d_Hs, sizeof(double) * ctx->Hs_cap));
+  ctx->h_stage = nullptr; // pinned dense staging is grown on demand (ensure_stage)
+  ctx->stage_cap = 0;
+  ctx->W_cap = ((size_t)ctx->max_rows / OVB_CR + 2) * OVB_NB * OVB_NB + 4096;
+  CK(cudaMalloc(&ctx->d_W[0], sizeof(double) * ctx->W_cap));
+  CK(cudaMalloc(&ctx->d_W[1], sizeof(double) * ctx->W_cap));
+  size_t rsz = (size_t)(ms + 8) * (ms + 8);
+  CK(cudaMalloc(&ctx->d_R, sizeof(double) * rsz));
+  CK(cudaMalloc(&ctx->d_R2, sizeof(double) * rsz));
+  CK(cudaMalloc(&ctx->d_M, sizeof(double) * (size_t)ms * ms));
+  CK(cudaMalloc(&ctx->d_S, sizeof(double) * (size_t)(ms + 1) * ms));
+  CK(cudaMalloc(&ctx->d_Y, sizeof(double) * (size_t)ms * ms));
+  CK(cudaMalloc(&ctx->d_w, sizeof(double) * (size_t)ms * 4));
+  CK(cudaMalloc(&ctx->d_dx, sizeof(double) * (size_t)ms));
+  ctx->scratch_per_cta = (size_t)(2 * OVB_MAX_MEAS_PER_FEAT + 1) * (2 * OVB_MAX_MEAS_PER_FEAT + 1);
+  ctx->scratch_ctas = 2 * ctx->sm_count;
+  CK(cudaMalloc(&ctx->d_scratch, sizeof(double) * ctx->scratch_per_cta * ctx->scratch_ctas));
+  ctx->dump_cap = (size_t)ctx->max_rows * (OVB_MAX_COLS + 4);
+  ctx->d_dump = nullptr; // allocated on first use by ovb_feature_jacobians(stage 0)
+#undef CK
+  *out = ctx;
+  return OVB_OK;
+}
+
+void ovb_destroy(ovb_ctx *ctx) {
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream)
+    cudaStreamSynchronize(ctx->stream);
+  void *dev[] = {ctx->P[0],   ctx->P[1], ctx->d_arena, ctx->d_cc, ctx->d_feat_order, ctx->d_info, ctx->d_chi2_table, ctx->d_Hs, ctx->d_W[0],
+                 ctx->d_W[1], ctx->d_R,  ctx->d_R2,    ctx->d_M,  ctx->d_S,          ctx->d_Y,    ctx->d_w,          ctx->d_dx, ctx->d_scratch,
+                 ctx->d_dump};
+  for (void *p : dev)
+    if (p)
+      cudaFree(p);
+  void *host[] = {ctx->h_arena, ctx->h_info, ctx->h_dx, ctx->h_stage};
+  for (void *p : host)
+    if (p)
+      cudaFreeHost(p);
+  for (int i = 0; i < 8; i++)
+    if (ctx->ev[i])
+      cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------------ covariance residency
+int ovb_cov_dim(const ovb_ctx *ctx) { return ctx ? ctx->N : 0; }
+
+ovb_status ovb_cov_set(ovb_ctx *ctx, const double *P, int N) {
+  if (!ctx || !P || N < 1)
+    return OVB_ERR_ARG;
+  if (N > ctx->cfg.max_state) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_cov_set: N=%d exceeds max_state=%d", N, ctx->cfg.max_state);
+    return OVB_ERR_CAPACITY;
+  }
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  OVB_CUDA_CHECK(ctx, cudaMemcpy2DAsync(ctx->P[ctx->cur], sizeof(double) * ctx->ldP, P, sizeof(double) * N, sizeof(double) * N, N,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->N = N;
+  return OVB_OK;
+}
+
+ovb_status ovb_cov_get(ovb_ctx *ctx, double *P, int N) {
+  if (!ctx || !P || N != ctx->N)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  OVB_CUDA_CHECK(ctx, cudaMemcpy2DAsync(P, sizeof(double) * N, ctx->P[ctx->cur], sizeof(double) * ctx->ldP, sizeof(double) * N, N,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return OVB_OK;
+}
+
+ovb_status ovb_cov_get_marginal(ovb_ctx *ctx, const int *off, const int *sz, int nvar, double *out) {
+  if (!ctx || !off || !sz || !out || nvar < 1)
+    return OVB_ERR_ARG;
+  int n = 0;
+  for (int i = 0; i < nvar; i++) {
+    if (off[i] < 0 || sz[i] < 1 || off[i] + sz[i] > ctx->N)
+      return OVB_ERR_ARG;
+    n += sz[i];
+  }
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  // block copies (small): one strided copy per (i,k) block
+  int ii = 0;
+  for (int i = 0; i < nvar; i++) {
+    int kk = 0;
+    for (int k = 0; k < nvar; k++) {
+      OVB_CUDA_CHECK(ctx, cudaMemcpy2DAsync(out + (size_t)ii * n + kk, sizeof(double) * n,
+                                            ctx->P[ctx->cur] + (size_t)off[i] * ctx->ldP + off[k], sizeof(double) * ctx->ldP,
+                                            sizeof(double) * sz[k], sz[i], cudaMemcpyDeviceToHost, ctx->stream));
+      kk += sz[k];
+    }
+    ii += sz[i];
+  }
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return OVB_OK;
+}
+
+ovb_status ovb_cov_clone(ovb_ctx *ctx, int old_off, int size, const double *dnc_dt, int dt_off) {
+  if (!ctx || size < 1 || old_off < 0 || old_off + size > ctx->N)
+    return OVB_ERR_ARG;
+  if (ctx->N + size > ctx->cfg.max_state) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_cov_clone: N+size=%d exceeds max_state=%d", ctx->N + size, ctx->cfg.max_state);
+    return OVB_ERR_CAPACITY;
+  }
+  if (dnc_dt && (dt_off < 0 || dt_off >= ctx->N || size > 64))
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const double *dnc_dev = nullptr;
+  if (dnc_dt) {
+    memcpy(ctx->h_dx, dnc_dt, sizeof(double) * size);
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_w, ctx->h_dx, sizeof(double) * size, cudaMemcpyHostToDevice, ctx->stream));
+    dnc_dev = ctx->d_w;
+  }
+  launch_cov_clone(ctx, old_off, size, dnc_dev, dt_off);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->N += size;
+  return OVB_OK;
+}
+
+ovb_status ovb_cov_marginalize(ovb_ctx *ctx, int off, int size) {
+  if (!ctx || size < 1 || off < 0 || off + size > ctx->N)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  launch_cov_marginalize(ctx, off, size);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->cur ^= 1;
+  ctx->N -= size;
+  return OVB_OK;
+}
+
+ovb_status ovb_cov_propagate(ovb_ctx *ctx, int new_off, int p, const int *old_off, const int *old_sz, int nold, const double *Phi,
+                             const double *Q) {
+  if (!ctx || !old_off || !old_sz || !Phi || !Q || p < 1 || nold < 1 || new_off < 0 || new_off + p > ctx->N)
+    return OVB_ERR_ARG; // the reference exits on empty variable lists (StateHelper.cpp:41-44)
+  int q = 0;
+  for (int i = 0; i < nold; i++) {
+    if (old_off[i] < 0 || old_sz[i] < 1 || old_off[i] + old_sz[i] > ctx->N)
+      return OVB_ERR_ARG;
+    q += old_sz[i];
+  }
+  if (q > ctx->cfg.max_state || p > ctx->cfg.max_state || (size_t)p * q + (size_t)p * p > ctx->Hs_cap)
+    return OVB_ERR_CAPACITY;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  // stage: [Phi p*q][Q p*p] doubles, then q ints
+  {
+    ovb_status es = ensure_stage(ctx, (size_t)p * q + (size_t)p * p + (size_t)q + 16);
+    if (es != OVB_OK)
+      return es;
+  }
+  double *hs = ctx->h_stage;
+  memcpy(hs, Phi, sizeof(double) * (size_t)p * q);
+  memcpy(hs + (size_t)p * q, Q, sizeof(double) * (size_t)p * p);
+  int *hidx = (int *)(hs + (size_t)p * q + (size_t)p * p);
+  int c = 0;
+  for (int i = 0; i < nold; i++)
+    for (int k = 0; k < old_sz[i]; k++)
+      hidx[c++] = old_off[i] + k;
+  size_t bytes = sizeof(double) * ((size_t)p * q + (size_t)p * p) + sizeof(int) * q;
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_Hs, hs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const double *Phi_dev = ctx->d_Hs;
+  const double *Q_dev = ctx->d_Hs + (size_t)p * q;
+  const int *idx_dev = (const int *)(ctx->d_Hs + (size_t)p * q + (size_t)p * p);
+  launch_cov_propagate(ctx, new_off, p, q, idx_dev, Phi_dev, Q_dev);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_info->neg_diag_index != 0x7fffffff) {
+    snprintf(ctx->err, sizeof(ctx->err), "EKFPropagation: diagonal at %d is negative", ctx->h_info->neg_diag_index);
+    return OVB_ERR_NEG_DIAG;
+  }
+  return OVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ marshalling
+struct Packed {
+  int n_feats, n_meas, max_M, m_total, ldH, n_all;
+  BlobView bv;
+};
+
+static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_batch *fb, const ovb_opts *op, const ovb_feat_out *given,
+                              Packed *pk) {
+  if (!fr || !fb || !op)
+    return OVB_ERR_ARG;
+  if (fr->n_clones < 1 || fr->n_clones > OVB_MAX_CLONES || fr->n_cams < 1 || fr->n_cams > OVB_MAX_CAMS) {
+    snprintf(ctx->err, sizeof(ctx->err), "frame: n_clones=%d (max %d) n_cams=%d (max %d)", fr->n_clones, OVB_MAX_CLONES, fr->n_cams, OVB_MAX_CAMS);
+    return OVB_ERR_CAPACITY;
+  }
+  if (fb->n_feats < 0 || fb->n_feats > ctx->cfg.max_feats || fb->n_meas < 0 || fb->n_meas > ctx->cfg.max_meas) {
+    snprintf(ctx->err, sizeof(ctx->err), "batch: n_feats=%d (max %d) n_meas=%d (max %d)", fb->n_feats, ctx->cfg.max_feats, fb->n_meas,
+             ctx->cfg.max_meas);
+    return OVB_ERR_CAPACITY;
+  }
+  DevFrame *hf = ctx->h_frame;
+  memset(hf, 0, sizeof(*hf));
+  hf->n_clones = fr->n_clones;
+  hf->n_cams = fr->n_cams;
+  memcpy(hf->clone_R, fr->clone_R, sizeof(double) * 9 * fr->n_clones);
+  memcpy(hf->clone_p, fr->clone_p, sizeof(double) * 3 * fr->n_clones);
+  memcpy(hf->clone_R_fej, fr->clone_R_fej ? fr->clone_R_fej : fr->clone_R, sizeof(double) * 9 * fr->n_clones);
+  memcpy(hf->clone_p_fej, fr->clone_p_fej ? fr->clone_p_fej : fr->clone_p, sizeof(double) * 3 * fr->n_clones);
+  memcpy(hf->cam_R, fr->cam_R, sizeof(double) * 9 * fr->n_cams);
+  memcpy(hf->cam_p, fr->cam_p, sizeof(double) * 3 * fr->n_cams);
+  memcpy(hf->cam_intr, fr->cam_intr, sizeof(double) * 8 * fr->n_cams);
+  for (int k = 0; k < fr->n_cams; k++)
+    hf->cam_model[k] = fr->cam_model ? fr->cam_model[k] : OVB_CAM_RADTAN;
+  // ---- slots in ascending covariance offset
+  struct SlotRec {
+    int off, size, kind, idx;
+  }; // kind 0 clone, 1 ext, 2 intr
+  std::vector<SlotRec> slots;
+  for (int k = 0; k < fr->n_cams; k++) {
+    hf->cam_ext_slot[k] = hf->cam_intr_slot[k] = -1;
+    if (op->do_calib_camera_pose) {
+      if (!fr->cam_ext_off || fr->cam_ext_off[k] < 0) {
+        snprintf(ctx->err, sizeof(ctx->err), "do_calib_camera_pose set but cam_ext_off[%d] < 0", k);
+        return OVB_ERR_ARG;
+      }
+      slots.push_back({fr->cam_ext_off[k], 6, 1, k});
+    }
+    if (op->do_calib_camera_intrinsics) {
+      if (!fr->cam_intr_off || fr->cam_intr_off[k] < 0) {
+        snprintf(ctx->err, sizeof(ctx->err), "do_calib_camera_intrinsics set but cam_intr_off[%d] < 0", k);
+        return OVB_ERR_ARG;
+      }
+      slots.push_back({fr->cam_intr_off[k], 8, 2, k});
+    }
+  }
+  for (int c = 0; c < fr->n_clones; c++)
+    slots.push_back({fr->clone_off[c], 6, 0, c});
+  std::sort(slots.begin(), slots.end(), [](const SlotRec &a, const SlotRec &b) { return a.off < b.off; });
+  if ((int)slots.size() > OVB_MAX_VARS)
+    return OVB_ERR_CAPACITY;
+  int col = 0;
+  for (size_t s = 0; s < slots.size(); s++) {
+    if (slots[s].off < 0 || slots[s].off + slots[s].size > ctx->N) {
+      snprintf(ctx->err, sizeof(ctx->err), "variable offset %d(+%d) outside the covariance (N=%d)", slots[s].off, slots[s].size, ctx->N);
+      return OVB_ERR_ARG;
+    }
+    if (s > 0 && slots[s].off < slots[s - 1].off + slots[s - 1].size) {
+      snprintf(ctx->err, sizeof(ctx->err), "overlapping state variables at offset %d", slots[s].off);
+      return OVB_ERR_ARG;
+    }
+    hf->slot_off[s] = slots[s].off;
+    hf->slot_size[s] = slots[s].size;
+    hf->slot_col[s] = col;
+    col += slots[s].size;
+    if (slots[s].kind == 0)
+      hf->clone_slot[slots[s].idx] = (int)s;
+    else if (slots[s].kind == 1)
+      hf->cam_ext_slot[slots[s].idx] = (int)s;
+    else
+      hf->cam_intr_slot[slots[s].idx] = (int)s;
+  }
+  hf->n_slots = (int)slots.size();
+  hf->n_all = col;
+  if (col > OVB_MAX_COLS || col + 1 > std::min(OVB_MAX_COLS, ctx->cfg.max_state) + 8)
+    return OVB_ERR_CAPACITY;
+  // ---- options
+  DevOpts *ho = ctx->h_opts;
+  ho->o = *op;
+  ho->sigma_pix_sq = std::pow(op->sigma_pix, 2);
+  ho->rep = op->feat_rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE ? OVB_REP_ANCHORED_MSCKF_INVERSE_DEPTH : op->feat_rep;
+  if (ho->rep < 0 || ho->rep > OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE)
+    return OVB_ERR_ARG;
+  // ---- blob: [cam u8 M][pad2][clone u16 M][pad4][uv f32 2M][uvn f32 2M][keys u8]
+  const int F = fb->n_feats, M = fb->n_meas;
+  size_t o_cam = 0;
+  size_t o_clone = align_up(o_cam + (size_t)M, 16);
+  size_t o_uv = align_up(o_clone + 2 * (size_t)M, 16);
+  size_t o_uvn = align_up(o_uv + 8 * (size_t)M, 16);
+  size_t o_keys = align_up(o_uvn + 8 * (size_t)M, 16);
+  unsigned char *hb = ctx->h_blob;
+  if (M > 0) {
+    memcpy(hb + o_cam, fb->cam, (size_t)M);
+    memcpy(hb + o_clone, fb->clone, 2 * (size_t)M);
+    memcpy(hb + o_uv, fb->uv, 8 * (size_t)M);
+    memcpy(hb + o_uvn, fb->uvn, 8 * (size_t)M);
+  }
+  unsigned char *hkeys = hb + o_keys;
+  size_t nkeys = 0;
+  int row = 0, maxM = 0;
+  for (int f = 0; f < F; f++) {
+    DevFeat &d = ctx->h_feat[f];
+    d.m0 = fb->meas_off[f];
+    d.m1 = fb->meas_off[f + 1];
+    if (d.m0 < 0 || d.m1 < d.m0 || d.m1 > M)
+      return OVB_ERR_ARG;
+    int Mf = d.m1 - d.m0;
+    if (Mf > OVB_MAX_MEAS_PER_FEAT) {
+      snprintf(ctx->err, sizeof(ctx->err), "feature %d has %d measurements (max %d)", f, Mf, OVB_MAX_MEAS_PER_FEAT);
+      return OVB_ERR_CAPACITY;
+    }
+    maxM = std::max(maxM, Mf);
+    d.row0 = row;
+    row += Mf >= 2 ? 2 * Mf - 3 : 0;
+    d.key0 = (int)nkeys;
+    if (fb->cam_keys_off && fb->cam_keys) {
+      for (int k = fb->cam_keys_off[f]; k < fb->cam_keys_off[f + 1]; k++) {
+        if (fb->cam_keys[k] >= fr->n_cams)
+          return OVB_ERR_ARG;
+        hkeys[nkeys++] = fb->cam_keys[k];
+      }
+    } else {
+      int last = -1;
+      for (int i = d.m0; i < d.m1; i++)
+        if ((int)fb->cam[i] != last) {
+          last = fb->cam[i];
+          hkeys[nkeys++] = (unsigned char)last;
+        }
+    }
+    d.key1 = (int)nkeys;
+    if (o_keys + nkeys + OVB_MAX_CAMS > ctx->blob_cap)
+      return OVB_ERR_CAPACITY;
+    for (int i = d.m0; i < d.m1; i++)
+      if (fb->cam[i] >= fr->n_cams || fb->clone[i] >= fr->n_clones)
+        return OVB_ERR_ARG;
+    d.status = OVB_FEAT_OK;
+    d.anchor_cam = d.anchor_clone = -1;
+    d.chi2 = NAN;
+    for (int k = 0; k < 3; k++)
+      d.p_FinA[k] = d.p_FinG[k] = NAN;
+    if (given) {
+      d.status = given->status ? given->status[f] : OVB_FEAT_OK;
+      d.anchor_cam = given->anchor_cam ? given->anchor_cam[f] : -1;
+      d.anchor_clone = given->anchor_clone ? given->anchor_clone[f] : -1;
+      for (int k = 0; k < 3; k++) {
+        d.p_FinA[k] = given->p_FinA ? given->p_FinA[3 * f + k] : NAN;
+        d.p_FinG[k] = given->p_FinG ? given->p_FinG[3 * f + k] : NAN;
+      }
+    }
+  }
+  pk->n_feats = F;
+  pk->n_meas = M;
+  pk->max_M = maxM;
+  pk->m_total = row;
+  pk->n_all = col;
+  pk->ldH = (int)align_up((size_t)col + 1, 4);
+  if ((size_t)std::max(row, col) * pk->ldH > ctx->Hs_cap || row > ctx->max_rows) {
+    snprintf(ctx->err, sizeof(ctx->err), "stacked system %d x %d exceeds the reserved staging matrix", row, pk->ldH);
+    return OVB_ERR_CAPACITY;
+  }
+  pk->bv.cam = ctx->d_blob + o_cam;
+  pk->bv.clone = (const uint16_t *)(ctx->d_blob + o_clone);
+  pk->bv.uv = (const float *)(ctx->d_blob + o_uv);
+  pk->bv.uvn = (const float *)(ctx->d_blob + o_uvn);
+  pk->bv.keys = ctx->d_blob + o_keys;
+  size_t used = ctx->off_blob + o_keys + nkeys;
+  cudaError_t e = cudaMemcpyAsync(ctx->d_arena, ctx->h_arena, used, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    snprintf(ctx->err, sizeof(ctx->err), "H2D arena copy: %s", cudaGetErrorString(e));
+    return OVB_ERR_CUDA;
+  }
+  return OVB_OK;
+}
+
+static void unpack_feats(ovb_ctx *ctx, int F, ovb_feat_out *out) {
+  if (!out)
+    return;
+  for (int f = 0; f < F; f++) {
+    const DevFeat &d = ctx->h_feat[f];
+    if (out->status)
+      out->status[f] = d.status;
+    if (out->anchor_cam)
+      out->anchor_cam[f] = d.anchor_cam;
+    if (out->anchor_clone)
+      out->anchor_clone[f] = d.anchor_clone;
+    if (out->chi2)
+      out->chi2[f] = d.chi2;
+    for (int k = 0; k < 3; k++) {
+      if (out->p_FinA)
+        out->p_FinA[3 * f + k] = d.p_FinA[k];
+      if (out->p_FinG)
+        out->p_FinG[3 * f + k] = d.p_FinG[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ hot path
+ovb_status ovb_triangulate(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, ovb_feat_out *out) {
+  if (!ctx || !out)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  Packed pk;
+  int saveN = ctx->N;
+  if (ctx->N == 0)
+    ctx->N = ctx->cfg.max_state; // offsets are not dereferenced by this stage
+  ovb_status st = pack_inputs(ctx, frame, feats, opts, nullptr, &pk);
+  ctx->N = saveN;
+  if (st != OVB_OK)
+    return st;
+  launch_cam_poses(ctx);
+  launch_triangulate(ctx, pk.n_feats, pk.bv);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)pk.n_feats, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  unpack_feats(ctx, pk.n_feats, out);
+  return OVB_OK;
+}
+
+ovb_status ovb_feature_jacobians(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, ovb_feat_out *out,
+                                 int stage, double *Hf_out, double *Hx_out, double *res_out, int32_t *row_off_out, int32_t *ncols_out,
+                                 int32_t *col_index_out, int ld_out) {
+  if (!ctx || !out || !row_off_out || !ncols_out || !col_index_out)
+    return OVB_ERR_ARG;
+  if (ctx->N < 1) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_feature_jacobians: no covariance loaded (ovb_cov_set)");
+    return OVB_ERR_ARG;
+  }
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  Packed pk;
+  ovb_status st = pack_inputs(ctx, frame, feats, opts, out, &pk);
+  if (st != OVB_OK)
+    return st;
+  const int F = pk.n_feats, n_all = pk.n_all;
+  if (ld_out < n_all)
+    return OVB_ERR_ARG;
+  *ncols_out = n_all;
+  for (int s = 0, c = 0; s < ctx->h_frame->n_slots; s++)
+    for (int k = 0; k < ctx->h_frame->slot_size[s]; k++)
+      col_index_out[c++] = ctx->h_frame->slot_off[s] + k;
+  launch_cam_poses(ctx);
+  if (stage == 0) {
+    int rows = 2 * pk.n_meas;
+    size_t need = (size_t)rows * (OVB_MAX_COLS + 4);
+    if (!ctx->d_dump || need > ctx->dump_cap) {
+      if (ctx->d_dump)
+        cudaFree(ctx->d_dump);
+      ctx->dump_cap = need;
+      OVB_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_dump, sizeof(double) * ctx->dump_cap));
+    }
+    OVB_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_dump, 0, sizeof(double) * need, ctx->stream));
+    launch_feature_system(ctx, F, pk.bv, pk.ldH, 1, pk.max_M);
+    OVB_CUDA_CHECK(ctx, cudaGetLastError());
+    std::vector<double> host(need);
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(host.data(), ctx->d_dump, sizeof(double) * need, cudaMemcpyDeviceToHost, ctx->stream));
+    OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    int dump_rows = (int)(ctx->dump_cap / (size_t)(OVB_MAX_COLS + 4));
+    const double *dHf = host.data(), *dres = host.data() + (size_t)dump_rows * 3, *dHx = host.data() + (size_t)dump_rows * 4;
+    for (int f = 0; f <= F; f++)
+      row_off_out[f] = 2 * feats->meas_off[f];
+    for (int i = 0; i < rows; i++) {
+      if (Hf_out)
+        for (int k = 0; k < 3; k++)
+          Hf_out[(size_t)i * 3 + k] = dHf[(size_t)i * 3 + k];
+      if (res_out)
+        res_out[i] = dres[i];
+      if (Hx_out)
+        for (int j = 0; j < n_all; j++)
+          Hx_out[(size_t)i * ld_out + j] = dHx[(size_t)i * OVB_MAX_COLS + j];
+    }
+    return OVB_OK;
+  }
+  launch_feature_system(ctx, F, pk.bv, pk.ldH, 0, pk.max_M);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  std::vector<double> host((size_t)pk.m_total * pk.ldH);
+  if (pk.m_total > 0)
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(host.data(), ctx->d_Hs, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  unpack_feats(ctx, F, out);
+  for (int f = 0; f < F; f++)
+    row_off_out[f] = ctx->h_feat[f].row0;
+  row_off_out[F] = pk.m_total;
+  for (int i = 0; i < pk.m_total; i++) {
+    if (res_out)
+      res_out[i] = host[(size_t)i * pk.ldH + n_all];
+    if (Hx_out)
+      for (int j = 0; j < n_all; j++)
+        Hx_out[(size_t)i * ld_out + j] = host[(size_t)i * pk.ldH + j];
+  }
+  return OVB_OK;
+}
+
+// copy column n (the residual z) of the n x (n+1) R into d_w so the Cholesky kernel can append it
+__global__ void k_take_z(const double *R, int ldR, int n, double *w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    w[i] = R[(size_t)i * ldR + n];
+}
+// col_state for the canonical layout (used by ovb_compress-less paths): info->col_state[j] = slot_off + k
+__global__ void k_fill_zero_dx(double *dx, int N) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N)
+    dx[i] = 0.0;
+}
+
+ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, ovb_feat_out *out,
+                            double *dx, ovb_stats *stats) {
+  if (!ctx || !dx)
+    return OVB_ERR_ARG;
+  if (ctx->N < 1) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_msckf_update: no covariance loaded (ovb_cov_set)");
+    return OVB_ERR_ARG;
+  }
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const int N = ctx->N;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->neg_diag_index = -1;
+  }
+  for (int i = 0; i < N; i++)
+    dx[i] = 0.0;
+  if (!feats || feats->n_feats <= 0) // UpdaterMSCKF.cpp:61-62
+    return OVB_OK;
+  cudaEventRecord(ctx->ev[0], ctx->stream);
+  Packed pk;
+  ovb_status st = pack_inputs(ctx, frame, feats, opts, nullptr, &pk);
+  if (st != OVB_OK)
+    return st;
+  const int F = pk.n_feats, n_all = pk.n_all;
+  launch_cam_poses(ctx);
+  launch_triangulate(ctx, F, pk.bv);
+  cudaEventRecord(ctx->ev[1], ctx->stream);
+  launch_feature_system(ctx, F, pk.bv, pk.ldH, 0, pk.max_M);
+  cudaEventRecord(ctx->ev[2], ctx->stream);
+  launch_column_map(ctx, F, pk.bv);
+  cudaEventRecord(ctx->ev[3], ctx->stream);
+  const int ldR = pk.ldH;
+  const double *Rfinal = ctx->d_R;
+  if (pk.m_total > 0) {
+    launch_tsqr(ctx, ctx->d_Hs, pk.m_total, n_all, pk.ldH, ctx->d_R, ldR);
+    if (opts->col_order == OVB_COLS_REFERENCE_FIRST_SEEN) {
+      launch_reorder_R(ctx, ctx->d_R, n_all, ldR, ctx->d_R2, ldR);
+      Rfinal = ctx->d_R2;
+    }
+  }
+  cudaEventRecord(ctx->ev[4], ctx->stream);
+  const int r = std::min(pk.m_total, n_all);
+  if (r > 0) {
+    k_take_z<<<(r + 127) / 128, 128, 0, ctx->stream>>>(Rfinal, ldR, r, ctx->d_w);
+    // canonical mode: stacked column q is canonical column q; the column map kernel fills col_state for both modes,
+    // but for canonical order it lists used slots first — rebuild the identity map in that case
+    launch_ekf_update(ctx, Rfinal, ldR, r, n_all, false, ctx->h_opts->sigma_pix_sq, nullptr);
+  } else {
+    k_fill_zero_dx<<<(N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_dx, N);
+  }
+  cudaEventRecord(ctx->ev[5], ctx->stream);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  cudaEventRecord(ctx->ev[6], ctx->stream);
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  unpack_feats(ctx, F, out);
+  for (int i = 0; i < N; i++)
+    dx[i] = ctx->h_dx[i];
+  for (int s = 0; s < 5; s++)
+    cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
+  cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[0], ctx->ev[6]);
+  const DevUpdateInfo *inf = ctx->h_info;
+  if (stats) {
+    stats->n_feats_in = F;
+    stats->n_feats_used = inf->n_feats_used;
+    stats->rows_stacked = inf->rows_stacked;
+    stats->cols_stacked = inf->n_used;
+    stats->rows_update = std::min(inf->rows_stacked, inf->n_used);
+    stats->neg_diag_index = (r > 0 && inf->neg_diag_index != 0x7fffffff) ? inf->neg_diag_index : -1;
+    stats->ms_total = ctx->stage_ms[5];
+  }
+  if (r > 0) {
+    if (inf->not_spd) {
+      snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: innovation covariance not positive definite");
+      return OVB_ERR_NOT_SPD;
+    }
+    if (inf->nonfinite) {
+      snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: non-finite covariance entry");
+      return OVB_ERR_NONFINITE;
+    }
+    if (inf->neg_diag_index != 0x7fffffff) {
+      snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: diagonal at %d is negative", inf->neg_diag_index);
+      return OVB_ERR_NEG_DIAG;
+    }
+  }
+  return OVB_OK;
+}
+
+ovb_status ovb_last_stage_ms(const ovb_ctx *ctx, float ms[6]) {
+  if (!ctx || !ms)
+    return OVB_ERR_ARG;
+  for (int i = 0; i < 6; i++)
+    ms[i] = ctx->stage_ms[i];
+  return OVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ staged dense entry points
+// rows scaled by 1/sqrt(Rdiag): whitening turns R = diag(Rdiag) into the identity so that compression applies
+__global__ void k_whiten_rows(double *A, int ld, int m, int ncols) {
+  int i = blockIdx.x;
+  double s = 1.0 / sqrt(A[(size_t)i * ld + ncols]); // the row's noise variance rides in column ncols
+  __syncthreads();
+  for (int j = threadIdx.x; j < ncols; j += blockDim.x)
+    A[(size_t)i * ld + j] *= s;
+}
+
+// pinned staging buffer, grown on demand (dense H uploads are a test/microbench path, not the per-frame path)
+static ovb_status ensure_stage(ovb_ctx *ctx, size_t doubles) {
+  if (doubles <= ctx->stage_cap && ctx->h_stage)
+    return OVB_OK;
+  if (ctx->h_stage)
+    cudaFreeHost(ctx->h_stage);
+  ctx->h_stage = nullptr;
+  ctx->stage_cap = 0;
+  OVB_CUDA_CHECK(ctx, cudaMallocHost(&ctx->h_stage, sizeof(double) * doubles));
+  ctx->stage_cap = doubles;
+  return OVB_OK;
+}
+
+// [H | res | extra] rows into the device staging matrix; column n = res, column n+1 = extra (or 0)
+static ovb_status stage_dense(ovb_ctx *ctx, const double *H, int m, int n, const double *res, const double *extra, int *ld_out) {
+  int ld = (int)align_up((size_t)n + 2, 4);
+  if ((size_t)std::max(m, n) * ld > ctx->Hs_cap) {
+    snprintf(ctx->err, sizeof(ctx->err), "dense system %d x %d exceeds the reserved staging matrix (max_rows/max_state)", m, n);
+    return OVB_ERR_CAPACITY;
+  }
+  ovb_status st = ensure_stage(ctx, (size_t)std::max(m, n) * ld);
+  if (st != OVB_OK)
+    return st;
+  double *hs = ctx->h_stage;
+  for (int i = 0; i < m; i++) {
+    memcpy(hs + (size_t)i * ld, H + (size_t)i * n, sizeof(double) * n);
+    hs[(size_t)i * ld + n] = res[i];
+    for (int j = n + 1; j < ld; j++)
+      hs[(size_t)i * ld + j] = 0.0;
+    if (extra)
+      hs[(size_t)i * ld + n + 1] = extra[i];
+  }
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_Hs, hs, sizeof(double) * (size_t)m * ld, cudaMemcpyHostToDevice, ctx->stream));
+  *ld_out = ld;
+  return OVB_OK;
+}
+
+ovb_status ovb_compress(ovb_ctx *ctx, const double *H, int m, int n, const double *res, double *R_out, double *z_out) {
+  if (!ctx || !H || !res || !R_out || !z_out || m < 1 || n < 1)
+    return OVB_ERR_ARG;
+  if (n + 8 > ctx->cfg.max_state + 8)
+    return OVB_ERR_CAPACITY;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  int ld;
+  ovb_status st = stage_dense(ctx, H, m, n, res, nullptr, &ld);
+  if (st != OVB_OK)
+    return st;
+  launch_tsqr(ctx, ctx->d_Hs, m, n, ld, ctx->d_R, ld);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  double *hs = ctx->h_stage;
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(hs, ctx->d_R, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < n; j++)
+      R_out[(size_t)i * n + j] = hs[(size_t)i * ld + j];
+    z_out[i] = hs[(size_t)i * ld + n];
+  }
+  return OVB_OK;
+}
+
+ovb_status ovb_ekf_update(ovb_ctx *ctx, const int *off, const int *sz, int nvar, const double *H, int r, const double *res, double sigma2,
+                          const double *Rdiag, double *dx) {
+  if (!ctx || !off || !sz || !H || !res || !dx || nvar < 1 || r < 1)
+    return OVB_ERR_ARG;
+  if (ctx->N < 1)
+    return OVB_ERR_ARG;
+  const int N = ctx->N;
+  int n = 0;
+  for (int i = 0; i < nvar; i++) {
+    if (off[i] < 0 || sz[i] < 1 || off[i] + sz[i] > N)
+      return OVB_ERR_ARG;
+    n += sz[i];
+  }
+  if (n > OVB_MAX_COLS || n > ctx->cfg.max_state)
+    return OVB_ERR_CAPACITY;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (Rdiag)
+    for (int i = 0; i < r; i++)
+      if (!(Rdiag[i] > 0.0))
+        return OVB_ERR_ARG;
+  int ld;
+  ovb_status st = stage_dense(ctx, H, r, n, res, Rdiag, &ld);
+  if (st != OVB_OK)
+    return st;
+  DevUpdateInfo *hi = ctx->h_info;
+  memset(hi, 0, sizeof(*hi));
+  int c = 0;
+  for (int i = 0; i < nvar; i++)
+    for (int k = 0; k < sz[i]; k++)
+      hi->col_state[c++] = off[i] + k;
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_info, hi, sizeof(DevUpdateInfo), cudaMemcpyHostToDevice, ctx->stream));
+  const double *Hdev = ctx->d_Hs;
+  int rr = r;
+  double s2 = sigma2;
+  if (Rdiag) {
+    // whiten each row by 1/sqrt(R_ii) so that R = I; then compression is admissible (UpdaterSLAM.cpp:444 uses diagonal R)
+    k_whiten_rows<<<r, 128, 0, ctx->stream>>>(ctx->d_Hs, ld, r, n + 1);
+    s2 = 1.0;
+  }
+  if (r > n) {
+    // more rows than columns: compress first (identical update, UpdaterMSCKF.cpp:275 does the same before EKFUpdate)
+    launch_tsqr(ctx, ctx->d_Hs, r, n, ld, ctx->d_R, ld);
+    Hdev = ctx->d_R;
+    rr = n;
+  }
+  k_take_z<<<(rr + 127) / 128, 128, 0, ctx->stream>>>(Hdev, ld, rr, ctx->d_w);
+  // k_take_z reads column n: for the uncompressed case that is the staged residual column
+  launch_ekf_update(ctx, Hdev, ld, rr, n, false, s2, nullptr);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < N; i++)
+    dx[i] = ctx->h_dx[i];
+  if (ctx->h_info->not_spd) {
+    snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: innovation covariance not positive definite");
+    return OVB_ERR_NOT_SPD;
+  }
+  if (ctx->h_info->nonfinite)
+    return OVB_ERR_NONFINITE;
+  if (ctx->h_info->neg_diag_index != 0x7fffffff) {
+    snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: diagonal at %d is negative", ctx->h_info->neg_diag_index);
+    return OVB_ERR_NEG_DIAG;
+  }
+  return OVB_OK;
+}
+
+} // extern "C"

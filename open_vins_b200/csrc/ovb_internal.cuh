@@ -1,0 +1,158 @@
+// ovb_internal.cuh — context, device-side views and launch declarations shared by the .cu files of libovb200.so.
+#pragma once
+#include "../../include/ovb200.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define OVB_MAX_MEAS_PER_FEAT 128 // K*C of config 4 is 124 (SURVEY.md §8 sizes table)
+#define OVB_MAX_COLS 400          // 6*OVB_MAX_CLONES + 14*OVB_MAX_CAMS
+#define OVB_NB 16                 // TSQR panel width
+#define OVB_CR 256                // TSQR rows per chunk
+
+// ---- device-resident copy of the slice of State the path reads (uploaded once per update call)
+struct DevFrame {
+  int n_clones, n_cams;
+  int n_slots;        // variables a feature can touch (clones + calibrated extrinsics/intrinsics)
+  int n_all;          // canonical column count = sum of slot sizes
+  double clone_R[OVB_MAX_CLONES][9];
+  double clone_p[OVB_MAX_CLONES][3];
+  double clone_R_fej[OVB_MAX_CLONES][9];
+  double clone_p_fej[OVB_MAX_CLONES][3];
+  double cam_R[OVB_MAX_CAMS][9];
+  double cam_p[OVB_MAX_CAMS][3];
+  double cam_intr[OVB_MAX_CAMS][8];
+  int cam_model[OVB_MAX_CAMS];
+  // slots in canonical (ascending covariance offset) order
+  int slot_off[OVB_MAX_VARS];  // covariance offset
+  int slot_size[OVB_MAX_VARS]; // 6 or 8
+  int slot_col[OVB_MAX_VARS];  // first canonical column
+  int clone_slot[OVB_MAX_CLONES];
+  int cam_ext_slot[OVB_MAX_CAMS];  // -1 when not calibrated
+  int cam_intr_slot[OVB_MAX_CAMS]; // -1 when not calibrated
+};
+
+// camera-at-clone poses (update/UpdaterMSCKF.cpp:98-115), filled on the device by k_cam_poses
+struct DevCamPoses {
+  double cc_R[OVB_MAX_CAMS][OVB_MAX_CLONES][9]; // R_GtoCi
+  double cc_p[OVB_MAX_CAMS][OVB_MAX_CLONES][3]; // p_CiinG
+};
+
+struct DevOpts {
+  ovb_opts o;
+  double sigma_pix_sq;
+  int rep; // effective MSCKF representation (SINGLE remapped, UpdaterMSCKF.cpp:180-183)
+};
+
+// per-feature device record (inputs derived on the host while packing + outputs)
+struct DevFeat {
+  int m0, m1;        // measurement range
+  int row0;          // first row in the stacked staging matrix (prefix sum of max(2M-3,0))
+  int key0, key1;    // camera-key range
+  int status;        // ovb_feat_status
+  int anchor_cam, anchor_clone;
+  double p_FinA[3], p_FinG[3];
+  double chi2;
+};
+
+// written by the column-map kernel; read by TSQR re-order, EKF and the host (D2H with the outputs)
+struct DevUpdateInfo {
+  int n_used;                   // columns of the stacked H in the requested order (ct_jacob)
+  int n_feats_used;             // accepted features
+  int rows_stacked;             // Σ (2M-3) over accepted features
+  int n_order;                  // variables in Hx_order_big
+  int order_slot[OVB_MAX_VARS]; // slot id of each variable in stacked order
+  int col_state[OVB_MAX_COLS];  // covariance index of each stacked column (order applied)
+  int col_canon[OVB_MAX_COLS];  // canonical column each stacked column comes from
+  int neg_diag_index;           // EKF: -1 or first negative diagonal
+  int not_spd;                  // EKF: Cholesky pivot failure flag
+  int nonfinite;
+};
+
+struct ovb_ctx {
+  ovb_config cfg;
+  int device;
+  cudaStream_t stream;
+  cudaEvent_t ev[8];
+  char err[256];
+  // covariance (double buffered for clone/marginalize), row-major with leading dimension ldP
+  int N, ldP;
+  double *P[2];
+  int cur;
+  // per-call device inputs
+  // one input arena (single H2D copy per call): [DevFrame][DevOpts][DevFeat x max_feats][blob]
+  unsigned char *d_arena, *h_arena;
+  size_t arena_bytes, off_opts, off_feat, off_blob;
+  DevFrame *d_frame;
+  DevOpts *d_opts;
+  DevFeat *d_feat;
+  unsigned char *d_blob; // packed SoA measurements
+  DevFrame *h_frame;
+  DevOpts *h_opts;
+  DevFeat *h_feat;
+  unsigned char *h_blob;
+  size_t blob_cap;
+  DevCamPoses *d_cc;
+  unsigned char *d_feat_order; // [max_feats][OVB_MAX_VARS+1] per-feature Hx_order (slot ids, first-seen)
+  DevUpdateInfo *d_info;
+  DevUpdateInfo *h_info;
+  double *h_dx;
+  double *h_stage; // pinned staging for dense H / Phi uploads (grown on demand)
+  size_t stage_cap;
+  // device work buffers
+  double *d_chi2_table;
+  double *d_Hs; // stacked staging matrix [max_rows][ldH]
+  size_t Hs_cap; // doubles
+  double *d_W[2]; // TSQR panel ping-pong workspaces
+  size_t W_cap;
+  double *d_R;   // TSQR output [OVB_MAX_COLS][ldR]
+  double *d_R2;  // re-ordered / re-triangularised R
+  double *d_M;   // EKF: P[:,cols] H'   [max_state][ldM]
+  double *d_S;   // EKF: innovation covariance / Cholesky factor
+  double *d_Y;   // EKF: M L^-T
+  double *d_w;   // EKF: L^-1 z
+  double *d_dx;
+  double *d_scratch; // per-CTA scratch for large features in the gate kernel
+  size_t scratch_per_cta;
+  int scratch_ctas;
+  double *d_dump; // debug dumps for ovb_feature_jacobians
+  size_t dump_cap;
+  int max_rows;
+  int sm_count;
+  float stage_ms[6];
+};
+
+#define OVB_CUDA_CHECK(ctx, call)                                                                                     \
+  do {                                                                                                                \
+    cudaError_t e_ = (call);                                                                                          \
+    if (e_ != cudaSuccess) {                                                                                          \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+      return OVB_ERR_CUDA;                                                                                            \
+    }                                                                                                                 \
+  } while (0)
+
+// packed measurement blob layout (device): [meas_off int32 (F+1)][cam u8 (M)][pad][clone u16 (M)][pad][uv f32 2M][uvn f32 2M][keys u8]
+struct BlobView {
+  const uint8_t *cam;
+  const uint16_t *clone;
+  const float *uv;
+  const float *uvn;
+  const uint8_t *keys;
+};
+
+// ---- launchers (each enqueues on ctx->stream; no host sync)
+void launch_cam_poses(ovb_ctx *ctx);
+void launch_triangulate(ovb_ctx *ctx, int n_feats, BlobView bv);
+// mode 0: normal (write post-nullspace rows to Hs, gate on chi²); mode 1: dump pre-nullspace dense rows to d_dump
+// mode 2: like 0 but features keep the status/p_FinG given (no triangulation ran) — used by ovb_feature_jacobians
+void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int mode, int max_M);
+void launch_column_map(ovb_ctx *ctx, int n_feats, BlobView bv);
+// TSQR of A [m x (n+1)] (last column = residual) in place; R (n x (n+1), diag>=0) to Rout with leading dimension ldR
+void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR);
+// gather columns of Rin in the order info->col_canon (n_used of them) into Hs scratch and re-triangularise into Rout
+void launch_reorder_R(ovb_ctx *ctx, const double *Rin, int n_all, int ldRin, double *Rout, int ldRout);
+// EKF update from an upper-trapezoidal / dense H [r x n] with column->state map in d_info (device-side sizes)
+void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r_max, int n_max, bool sizes_from_info, double sigma2,
+                       const double *Rdiag_dev);
+void launch_cov_clone(ovb_ctx *ctx, int old_off, int size, const double *dnc_dt_dev, int dt_off);
+void launch_cov_marginalize(ovb_ctx *ctx, int off, int size);
+void launch_cov_propagate(ovb_ctx *ctx, int new_off, int p, int q, const int *old_idx_dev, const double *Phi_dev, const double *Q_dev);
