@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""bench.py — MSCKF updates/s on the BASELINE.json config-2 workload (rpng_sim-like stereo, 20+1 clone poses, 400 MSCKF
+features, full online calibration: N = 194), one step = one UpdaterMSCKF::update over one feature batch.
+
+    python bench.py --gpus N --steps K --warmup W                # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU arithmetic (oracle port), rank 0
+
+Prints ONE JSON line (rank 0). `value` = updates/s with inputs resident in HBM (CUDA events on the engine's stream, L2
+flushed between steps); `e2e` = updates/s through the C-ABI call with host buffers (H2D/D2H inside the timed call).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n_feats=400, n_clones=21, n_cams=2, seed=2026, calib_ext=True, calib_intr=True, calib_imu=True, calib_dt=True)
+WORKLOAD_NAME = ("rpng_sim-like stereo, max_clones=20 (21 clone poses in the window), 400 MSCKF features/update, "
+                 "calib extrinsics+intrinsics+imu+dt on (N=194), radtan 752x480, sigma_px=1, chi2_mult=1, FEJ on, GLOBAL_3D")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            self.path = tempfile.NamedTemporaryFile(delete=False, suffix=".csv").name
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def cpu_baseline_updates(case, opts, seconds_budget=12.0, min_updates=3):
+    """The oracle (CPU restatement of the reference's Eigen arithmetic, single thread like the reference) on the same batch."""
+    from oracle import ovo_py
+    ovo_py.build()
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < min_updates or (time.perf_counter() - t_all) < seconds_budget:
+        t = time.perf_counter()
+        r = ovo_py.msckf_update(case.frame, case.feats, opts, case.P, dumps=False)
+        times.append(time.perf_counter() - t)
+        if len(times) >= 40:
+            break
+    return 1.0 / float(np.median(times)), len(times), r
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path. The reference cannot be built in this image
+    (Eigen/OpenCV/Boost absent), so this is the oracle port timed on the host, single thread like the reference."""
+    if rank != 0:
+        return
+    from open_vins_b200 import capi, sim
+    from oracle import ovo_py
+    ovo_py.build()
+    case = sim.make_update_case(**WORKLOAD)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1)
+    for _ in range(min(args.warmup, 2)):
+        ovo_py.msckf_update(case.frame, case.feats, opts, case.P, dumps=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = ovo_py.msckf_update(case.frame, case.feats, opts, case.P, dumps=False)
+    dt = time.perf_counter() - t0
+    ups = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "msckf_updates_per_sec", "value": ups, "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "feats_per_sec": ups * WORKLOAD["n_feats"],
+        "config": {"workload": WORKLOAD_NAME, "features_used": int(r["stats"].n_feats_used), "rows_stacked": int(r["stats"].rows_stacked),
+                   "cols_stacked": int(r["stats"].cols_stacked)},
+        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} full updates of the 400-feature batch, single thread (the reference update is single-threaded)"},
+        "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_s": {k: float(v) for k, v in zip(["triangulate", "create_system", "compress", "update"], r["times"])},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from open_vins_b200 import capi, sim
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    case = sim.make_update_case(**WORKLOAD)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, col_order=capi.COLS_CANONICAL)
+    F = case.feats.n_feats
+    if world > 1:
+        from open_vins_b200 import multigpu
+        return multigpu.bench_sharded(args, rank, local_rank, world, case, opts, WORKLOAD_NAME, ClockSampler, peaks)
+
+    eng = capi.Engine(max_state=256, max_feats=1024, max_meas=1024 * 48, device=local_rank)
+    eng.set_replay(True)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    # ---- e2e leg: the public C-ABI call with host buffers; P re-uploaded (untimed) so that every step is the same update
+    sampler = ClockSampler(local_rank)
+    for _ in range(W):
+        eng.cov_set(case.P)
+        st, out, dx, stats = eng.msckf_update(case.frame, case.feats, opts)
+    barrier()
+    sampler.start()
+    t_e2e = 0.0
+    for _ in range(K):
+        eng.cov_set(case.P)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        st, out, dx, stats = eng.msckf_update(case.frame, case.feats, opts)
+        t_e2e += time.perf_counter() - t
+    cnt = eng.last_counters()
+    stage_last = eng.last_stage_ms()
+    # ---- value leg: the same update replayed on device-resident inputs, L2 flushed between steps, CUDA events per step
+    barrier()
+    ms, stage_sum = eng.msckf_replay(W + K, flush_l2=True)
+    barrier()
+    clocks = sampler.stop()
+    ms = ms[W:]
+    t_dev = float(ms.sum()) * 1e-3
+    # stage sums include the warm-up steps; scale to per-step
+    stage_ms = stage_sum / float(W + K)
+    value = K / t_dev
+    # ---- roofline of the dominant kernel (TSQR level kernel)
+    m_rows, n_cols = int(stats.rows_stacked), int(stats.cols_stacked)
+    t_tsqr = stage_ms[3] * 1e-3
+    bytes_onepass = 8.0 * m_rows * (n_cols + 1) + 4.0 * n_cols * (n_cols + 1)
+    flops_qr = 2.0 * m_rows * n_cols**2 - (2.0 / 3.0) * n_cols**3 + 4.0 * m_rows * n_cols
+    hbm_peak, peak_src = peaks()
+    n_lvl = max(cnt["tsqr_level_launches"], 1)
+    roofline = {
+        "kernel": "k_tsqr_level (blocked Householder TSQR: panel factorisation + compact-WY trailing update)",
+        "bound": "hbm", "achieved": bytes_onepass / t_tsqr / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": bytes_onepass / t_tsqr / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "launches_per_step": n_lvl, "avg_launch_us": 1e6 * t_tsqr / n_lvl,
+        "algorithmic_bytes_per_launch": bytes_onepass / n_lvl,
+        "note": "whole-matrix QR is FP64-compute-bound (AI = n/4 flop/B); the HBM fraction is reported as the contract asks, the FP64 rate explains it",
+        "fp64": {"achieved_tflops": flops_qr / t_tsqr / 1e12, "nominal_peak_tflops": 37.0, "frac": flops_qr / t_tsqr / 1e12 / 37.0,
+                 "flops_per_step": flops_qr},
+    }
+    line = {
+        "metric": "msckf_updates_per_sec", "value": value, "unit": "updates/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "feats_per_sec": value * F,
+        "config": {"workload": WORKLOAD_NAME, "features_in": F, "features_used": int(stats.n_feats_used), "rows_stacked": m_rows,
+                   "cols_stacked": n_cols, "state_dim": int(case.layout.N), "l2": "flushed between steps (256 MiB memset)",
+                   "col_order": "canonical"},
+        "e2e": {"value": K / t_e2e, "unit": "updates/s", "ms_per_step": 1e3 * t_e2e / K, "h2d_bytes_per_step": cnt["h2d_bytes"],
+                "d2h_bytes_per_step": cnt["d2h_bytes"], "feats_per_sec": F * K / t_e2e,
+                "timing": "host clock around the synchronous C-ABI call (marshalling + H2D + kernels + D2H), summed over steps"},
+        "gpu_launches": cnt["launches"] * K,
+        "gpu_launches_per_step": cnt["launches"],
+        "stage_ms": {k: float(v) for k, v in zip(["triangulate", "feature_systems", "column_map", "compress_tsqr", "ekf_update"], stage_ms)},
+        "stage_ms_e2e_last": {k: float(v) for k, v in zip(["triangulate", "feature_systems", "column_map", "compress_tsqr", "ekf_update", "total"], stage_last)},
+        "roofline": roofline,
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        ups, n_upd, r = cpu_baseline_updates(case, opts)
+        assert np.array_equal(r["out"].status, out.status), "GPU and CPU gate decisions differ on the bench workload"
+        line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": 1, "kind": "port",
+                                "sample": f"{n_upd} full updates of the same 400-feature batch (median), single thread; cpu={os.cpu_count()} logical cores on the box",
+                                "stage_s": {k: float(v) for k, v in zip(["triangulate", "create_system", "compress", "update"], r["times"])}}
+        line["speedup_e2e_vs_cpu_port"] = (K / t_e2e) / ups
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -242,6 +242,17 @@ double ovb_chi2_quantile95(int dof);
  * [0] triangulate+GN  [1] jacobian+nullspace+gate  [2] column map  [3] TSQR  [4] EKF update  [5] total */
 ovb_status ovb_last_stage_ms(const ovb_ctx *ctx, float ms[6]);
 
+/* ---- measurement support: re-run the LAST ovb_msckf_update on its device-resident inputs ----
+ * ovb_set_replay(ctx,1) makes ovb_msckf_update keep a copy of the prior P; ovb_msckf_replay then restores that prior and
+ * re-enqueues the identical device pipeline `steps` times (optionally flushing L2 with a 256 MiB memset between steps),
+ * timing each step with CUDA events on the context stream. ms_per_step[steps]; stage_ms_sum[5] = summed stage times
+ * {triangulate, feature systems, column map, compression, EKF update}. This is bench.py's kernel-only `value` leg. */
+/* out[0] kernels launched by the last update pipeline, out[1] of which TSQR level kernels,
+ * out[2]/out[3] bytes copied host->device / device->host by the last ovb_msckf_update. */
+ovb_status ovb_last_counters(const ovb_ctx *ctx, int64_t out[4]);
+ovb_status ovb_set_replay(ovb_ctx *ctx, int enabled);
+ovb_status ovb_msckf_replay(ovb_ctx *ctx, int steps, int flush_l2, float *ms_per_step, float stage_ms_sum[5]);
+
 #ifdef __cplusplus
 }
 #endif

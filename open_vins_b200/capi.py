@@ -227,6 +227,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ovb_chi2_quantile95.argtypes = [C.c_int]
     lib.ovb_chi2_quantile95.restype = C.c_double
     lib.ovb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 6)]
+    lib.ovb_last_counters.argtypes = [vp, C.POINTER(C.c_int64 * 4)]
+    lib.ovb_set_replay.argtypes = [vp, C.c_int]
+    lib.ovb_msckf_replay.argtypes = [vp, C.c_int, C.c_int, c_float_p, C.POINTER(C.c_float * 5)]
     if path is None:
         _LIB = lib
     return lib
@@ -236,7 +239,7 @@ EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate",
     "ovb_msckf_update", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress",
-    "ovb_chi2_quantile95", "ovb_last_stage_ms",
+    "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
 ]
 
 
@@ -370,6 +373,21 @@ class Engine:
                                      _ptr(dx, c_double_p))
         self._check(st, allow=(OVB_ERR_NEG_DIAG,))
         return st, dx
+
+    def last_counters(self):
+        a = (C.c_int64 * 4)()
+        self._check(self.lib.ovb_last_counters(self.h, C.byref(a)))
+        return dict(launches=int(a[0]), tsqr_level_launches=int(a[1]), h2d_bytes=int(a[2]), d2h_bytes=int(a[3]))
+
+    def set_replay(self, enabled=True):
+        self._check(self.lib.ovb_set_replay(self.h, int(enabled)))
+
+    def msckf_replay(self, steps, flush_l2=True):
+        """Re-run the last msckf_update `steps` times on device-resident inputs. Returns (ms_per_step, stage_ms_sum)."""
+        ms = np.zeros(steps, dtype=np.float32)
+        st5 = (C.c_float * 5)()
+        self._check(self.lib.ovb_msckf_replay(self.h, steps, int(flush_l2), _ptr(ms, c_float_p), C.byref(st5)))
+        return ms, np.array([float(x) for x in st5])
 
     def last_stage_ms(self):
         a = (C.c_float * 6)()

@@ -798,7 +798,7 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
       grid = ctx->scratch_ctas;
     scratch = ctx->d_scratch;
   }
-  int dump_rows = (int)(ctx->dump_cap / (size_t)(OVB_MAX_COLS + 4));
+  int dump_rows = ctx->dump_rows; // rows of the current dump (set by ovb_feature_jacobians)
   k_feature_system<<<grid, FT_THREADS, smem, ctx->stream>>>(ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv, ctx->P[ctx->cur], ctx->ldP,
                                                             ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, scratch,
                                                             ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);

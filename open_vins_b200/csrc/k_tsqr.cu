@@ -337,6 +337,8 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
       dim3 grid(chunks, gy);
       k_tsqr_level<<<grid, QR_THREADS, sizeof(QrSmem), ctx->stream>>>(A, ldA, nt, c0, nbp, level, len, level > 0 ? ctx->d_W[(level - 1) & 1] : nullptr,
                                                                        ctx->d_W[level & 1], Rout, ldR, last);
+      ctx->n_launch++;
+      ctx->n_launch_tsqr_level++;
       if (last)
         break;
       int rows_last = len - (chunks - 1) * QR_CR;
@@ -345,6 +347,7 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
     }
   }
   k_tsqr_assemble<<<n, 128, 0, ctx->stream>>>(A, ldA, m, n, Rout, ldR);
+  ctx->n_launch++;
 }
 
 // =====================================================================================================================
@@ -447,5 +450,6 @@ void launch_reorder_R(ovb_ctx *ctx, const double *Rin, int n_all, int ldRin, dou
   // permuted copy into the (now free) staging matrix, then the same TSQR re-triangularises it
   int ldB = ldRin;
   k_gather_cols<<<n_all, 128, 0, ctx->stream>>>(Rin, ldRin, n_all, ctx->d_info, ctx->d_Hs, ldB);
+  ctx->n_launch++;
   launch_tsqr(ctx, ctx->d_Hs, n_all, n_all, ldB, Rout, ldRout);
 }

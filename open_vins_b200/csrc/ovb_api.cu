@@ -147,7 +147,7 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
   ctx->scratch_per_cta = (size_t)(2 * OVB_MAX_MEAS_PER_FEAT + 1) * (2 * OVB_MAX_MEAS_PER_FEAT + 1);
   ctx->scratch_ctas = 2 * ctx->sm_count;
   CK(cudaMalloc(&ctx->d_scratch, sizeof(double) * ctx->scratch_per_cta * ctx->scratch_ctas));
-  ctx->dump_cap = (size_t)ctx->max_rows * (OVB_MAX_COLS + 4);
+  ctx->dump_cap = 0;
   ctx->d_dump = nullptr; // allocated on first use by ovb_feature_jacobians(stage 0)
 #undef CK
   *out = ctx;
@@ -162,7 +162,7 @@ void ovb_destroy(ovb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
   void *dev[] = {ctx->P[0],   ctx->P[1], ctx->d_arena, ctx->d_cc, ctx->d_feat_order, ctx->d_info, ctx->d_chi2_table, ctx->d_Hs, ctx->d_W[0],
                  ctx->d_W[1], ctx->d_R,  ctx->d_R2,    ctx->d_M,  ctx->d_S,          ctx->d_Y,    ctx->d_w,          ctx->d_dx, ctx->d_scratch,
-                 ctx->d_dump};
+                 ctx->d_dump, ctx->P_snap, ctx->d_flush};
   for (void *p : dev)
     if (p)
       cudaFree(p);
@@ -484,6 +484,7 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
   pk->bv.uvn = (const float *)(ctx->d_blob + o_uvn);
   pk->bv.keys = ctx->d_blob + o_keys;
   size_t used = ctx->off_blob + o_keys + nkeys;
+  ctx->last_h2d_bytes = used;
   cudaError_t e = cudaMemcpyAsync(ctx->d_arena, ctx->h_arena, used, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) {
     snprintf(ctx->err, sizeof(ctx->err), "H2D arena copy: %s", cudaGetErrorString(e));
@@ -567,13 +568,14 @@ ovb_status ovb_feature_jacobians(ovb_ctx *ctx, const ovb_frame *frame, const ovb
       ctx->dump_cap = need;
       OVB_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_dump, sizeof(double) * ctx->dump_cap));
     }
+    ctx->dump_rows = rows;
     OVB_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_dump, 0, sizeof(double) * need, ctx->stream));
     launch_feature_system(ctx, F, pk.bv, pk.ldH, 1, pk.max_M);
     OVB_CUDA_CHECK(ctx, cudaGetLastError());
     std::vector<double> host(need);
     OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(host.data(), ctx->d_dump, sizeof(double) * need, cudaMemcpyDeviceToHost, ctx->stream));
     OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    int dump_rows = (int)(ctx->dump_cap / (size_t)(OVB_MAX_COLS + 4));
+    int dump_rows = rows;
     const double *dHf = host.data(), *dres = host.data() + (size_t)dump_rows * 3, *dHx = host.data() + (size_t)dump_rows * 4;
     for (int f = 0; f <= F; f++)
       row_off_out[f] = 2 * feats->meas_off[f];
@@ -611,16 +613,125 @@ ovb_status ovb_feature_jacobians(ovb_ctx *ctx, const ovb_frame *frame, const ovb
 }
 
 // copy column n (the residual z) of the n x (n+1) R into d_w so the Cholesky kernel can append it
-__global__ void k_take_z(const double *R, int ldR, int n, double *w) {
+__global__ void k_take_z(const double *R, int ldR, int rows, int col, double *w) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n)
-    w[i] = R[(size_t)i * ldR + n];
+  if (i < rows)
+    w[i] = R[(size_t)i * ldR + col];
 }
 // col_state for the canonical layout (used by ovb_compress-less paths): info->col_state[j] = slot_off + k
 __global__ void k_fill_zero_dx(double *dx, int N) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N)
     dx[i] = 0.0;
+}
+
+// The device pipeline of one update on inputs already in the arena: steps 2-6 of UpdaterMSCKF::update.
+// ev (optional): ev[1] after triangulation, ev[2] after the per-feature systems, ev[3] after the column map, ev[4] after
+// compression, ev[5] after the EKF update. Returns the row count handed to the EKF update.
+static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, int m_total, int n_all, int col_order, cudaEvent_t *ev) {
+  const int N = ctx->N;
+  ctx->n_launch = 0;
+  ctx->n_launch_tsqr_level = 0;
+  launch_cam_poses(ctx);
+  launch_triangulate(ctx, F, bv);
+  ctx->n_launch += 4; // cam poses, triangulate, feature systems, column map
+  if (ev)
+    cudaEventRecord(ev[1], ctx->stream);
+  launch_feature_system(ctx, F, bv, ldH, 0, max_M);
+  if (ev)
+    cudaEventRecord(ev[2], ctx->stream);
+  launch_column_map(ctx, F, bv);
+  if (ev)
+    cudaEventRecord(ev[3], ctx->stream);
+  const int ldR = ldH;
+  const double *Rfinal = ctx->d_R;
+  if (m_total > 0) {
+    launch_tsqr(ctx, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
+    if (col_order == OVB_COLS_REFERENCE_FIRST_SEEN) {
+      launch_reorder_R(ctx, ctx->d_R, n_all, ldR, ctx->d_R2, ldR);
+      Rfinal = ctx->d_R2;
+    }
+  }
+  if (ev)
+    cudaEventRecord(ev[4], ctx->stream);
+  const int r = std::min(m_total, n_all);
+  if (r > 0) {
+    k_take_z<<<(r + 127) / 128, 128, 0, ctx->stream>>>(Rfinal, ldR, r, n_all, ctx->d_w);
+    launch_ekf_update(ctx, Rfinal, ldR, r, n_all, false, ctx->h_opts->sigma_pix_sq, nullptr);
+    ctx->n_launch += 7; // take_z + prep, 2 gemm, chol, trsm, downdate
+  } else {
+    k_fill_zero_dx<<<(N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_dx, N);
+    ctx->n_launch += 1;
+  }
+  if (ev)
+    cudaEventRecord(ev[5], ctx->stream);
+  return r;
+}
+
+ovb_status ovb_last_counters(const ovb_ctx *ctx, int64_t out[4]) {
+  if (!ctx || !out)
+    return OVB_ERR_ARG;
+  out[0] = ctx->n_launch;            // kernels launched by the last update pipeline
+  out[1] = ctx->n_launch_tsqr_level; // of which k_tsqr_level
+  out[2] = (int64_t)ctx->last_h2d_bytes;
+  out[3] = (int64_t)ctx->last_d2h_bytes;
+  return OVB_OK;
+}
+
+ovb_status ovb_set_replay(ovb_ctx *ctx, int enabled) {
+  if (!ctx)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (enabled && !ctx->P_snap)
+    OVB_CUDA_CHECK(ctx, cudaMalloc(&ctx->P_snap, sizeof(double) * (size_t)ctx->ldP * ctx->ldP));
+  ctx->replay_enabled = enabled ? 1 : 0;
+  ctx->last_pk_valid = 0;
+  return OVB_OK;
+}
+
+ovb_status ovb_msckf_replay(ovb_ctx *ctx, int steps, int flush_l2, float *ms_per_step, float stage_ms_sum[5]) {
+  if (!ctx || steps < 1 || !ms_per_step)
+    return OVB_ERR_ARG;
+  if (!ctx->replay_enabled || !ctx->last_pk_valid) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_msckf_replay: call ovb_set_replay(ctx,1) and ovb_msckf_update first");
+    return OVB_ERR_ARG;
+  }
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const size_t flush_bytes = (size_t)256 << 20; // > 126 MB of L2
+  if (flush_l2 && !ctx->d_flush)
+    OVB_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_flush, flush_bytes));
+  std::vector<cudaEvent_t> evs((size_t)steps * 6);
+  for (auto &e : evs)
+    OVB_CUDA_CHECK(ctx, cudaEventCreate(&e));
+  const size_t Pbytes = sizeof(double) * (size_t)ctx->ldP * ctx->N;
+  for (int s = 0; s < steps; s++) {
+    if (flush_l2)
+      cudaMemsetAsync(ctx->d_flush, s & 0xff, flush_bytes, ctx->stream);
+    // restore the prior saved by the last ovb_msckf_update (outside the timed bracket: it is not part of an update)
+    cudaMemcpyAsync(ctx->P[ctx->cur], ctx->P_snap, Pbytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaEvent_t *ev = &evs[(size_t)s * 6];
+    cudaEventRecord(ev[0], ctx->stream);
+    enqueue_update(ctx, ctx->last_n_feats, ctx->last_bv, ctx->last_ldH, ctx->last_max_M, ctx->last_m_total, ctx->last_n_all, ctx->last_col_order,
+                   ev);
+  }
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stage_ms_sum)
+    for (int k = 0; k < 5; k++)
+      stage_ms_sum[k] = 0.f;
+  for (int s = 0; s < steps; s++) {
+    cudaEvent_t *ev = &evs[(size_t)s * 6];
+    cudaEventElapsedTime(&ms_per_step[s], ev[0], ev[5]);
+    if (stage_ms_sum)
+      for (int k = 0; k < 5; k++) {
+        float t;
+        cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+        stage_ms_sum[k] += t;
+      }
+  }
+  for (auto &e : evs)
+    cudaEventDestroy(e);
+  return OVB_OK;
 }
 
 ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, ovb_feat_out *out,
@@ -646,38 +757,26 @@ ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat
   ovb_status st = pack_inputs(ctx, frame, feats, opts, nullptr, &pk);
   if (st != OVB_OK)
     return st;
-  const int F = pk.n_feats, n_all = pk.n_all;
-  launch_cam_poses(ctx);
-  launch_triangulate(ctx, F, pk.bv);
-  cudaEventRecord(ctx->ev[1], ctx->stream);
-  launch_feature_system(ctx, F, pk.bv, pk.ldH, 0, pk.max_M);
-  cudaEventRecord(ctx->ev[2], ctx->stream);
-  launch_column_map(ctx, F, pk.bv);
-  cudaEventRecord(ctx->ev[3], ctx->stream);
-  const int ldR = pk.ldH;
-  const double *Rfinal = ctx->d_R;
-  if (pk.m_total > 0) {
-    launch_tsqr(ctx, ctx->d_Hs, pk.m_total, n_all, pk.ldH, ctx->d_R, ldR);
-    if (opts->col_order == OVB_COLS_REFERENCE_FIRST_SEEN) {
-      launch_reorder_R(ctx, ctx->d_R, n_all, ldR, ctx->d_R2, ldR);
-      Rfinal = ctx->d_R2;
-    }
+  const int F = pk.n_feats;
+  if (ctx->replay_enabled) {
+    // keep the prior so that ovb_msckf_replay can re-run this exact update on device-resident inputs
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->P_snap, ctx->P[ctx->cur], sizeof(double) * (size_t)ctx->ldP * N, cudaMemcpyDeviceToDevice,
+                                        ctx->stream));
+    ctx->last_pk_valid = 1;
+    ctx->last_n_feats = pk.n_feats;
+    ctx->last_max_M = pk.max_M;
+    ctx->last_m_total = pk.m_total;
+    ctx->last_ldH = pk.ldH;
+    ctx->last_n_all = pk.n_all;
+    ctx->last_bv = pk.bv;
+    ctx->last_col_order = opts->col_order;
   }
-  cudaEventRecord(ctx->ev[4], ctx->stream);
-  const int r = std::min(pk.m_total, n_all);
-  if (r > 0) {
-    k_take_z<<<(r + 127) / 128, 128, 0, ctx->stream>>>(Rfinal, ldR, r, ctx->d_w);
-    // canonical mode: stacked column q is canonical column q; the column map kernel fills col_state for both modes,
-    // but for canonical order it lists used slots first — rebuild the identity map in that case
-    launch_ekf_update(ctx, Rfinal, ldR, r, n_all, false, ctx->h_opts->sigma_pix_sq, nullptr);
-  } else {
-    k_fill_zero_dx<<<(N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_dx, N);
-  }
-  cudaEventRecord(ctx->ev[5], ctx->stream);
+  const int r = enqueue_update(ctx, pk.n_feats, pk.bv, pk.ldH, pk.max_M, pk.m_total, pk.n_all, opts->col_order, ctx->ev);
   OVB_CUDA_CHECK(ctx, cudaGetLastError());
   OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
   OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
   OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + sizeof(DevUpdateInfo) + sizeof(double) * (size_t)N;
   cudaEventRecord(ctx->ev[6], ctx->stream);
   OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   unpack_feats(ctx, F, out);
@@ -836,7 +935,7 @@ ovb_status ovb_ekf_update(ovb_ctx *ctx, const int *off, const int *sz, int nvar,
     Hdev = ctx->d_R;
     rr = n;
   }
-  k_take_z<<<(rr + 127) / 128, 128, 0, ctx->stream>>>(Hdev, ld, rr, ctx->d_w);
+  k_take_z<<<(rr + 127) / 128, 128, 0, ctx->stream>>>(Hdev, ld, rr, n, ctx->d_w);
   // k_take_z reads column n: for the uncompressed case that is the staged residual column
   launch_ekf_update(ctx, Hdev, ld, rr, n, false, s2, nullptr);
   OVB_CUDA_CHECK(ctx, cudaGetLastError());

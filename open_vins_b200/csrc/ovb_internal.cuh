@@ -68,6 +68,15 @@ struct DevUpdateInfo {
   int nonfinite;
 };
 
+// packed measurement blob layout (device): [meas_off int32 (F+1)][cam u8 (M)][pad][clone u16 (M)][pad][uv f32 2M][uvn f32 2M][keys u8]
+struct BlobView {
+  const uint8_t *cam;
+  const uint16_t *clone;
+  const float *uv;
+  const float *uvn;
+  const uint8_t *keys;
+};
+
 struct ovb_ctx {
   ovb_config cfg;
   int device;
@@ -116,9 +125,19 @@ struct ovb_ctx {
   int scratch_ctas;
   double *d_dump; // debug dumps for ovb_feature_jacobians
   size_t dump_cap;
+  int dump_rows;
   int max_rows;
   int sm_count;
   float stage_ms[6];
+  // replay of the last update on device-resident inputs (bench: `value` leg; see ovb_msckf_replay)
+  int replay_enabled, last_pk_valid;
+  int last_n_feats, last_max_M, last_m_total, last_ldH, last_n_all, last_col_order;
+  BlobView last_bv;
+  double *P_snap;
+  void *d_flush;
+  // bookkeeping for bench.py: kernels launched by the last update pipeline, bytes moved by the last ovb_msckf_update
+  int n_launch, n_launch_tsqr_level;
+  size_t last_h2d_bytes, last_d2h_bytes;
 };
 
 #define OVB_CUDA_CHECK(ctx, call)                                                                                     \
@@ -129,15 +148,6 @@ struct ovb_ctx {
       return OVB_ERR_CUDA;                                                                                            \
     }                                                                                                                 \
   } while (0)
-
-// packed measurement blob layout (device): [meas_off int32 (F+1)][cam u8 (M)][pad][clone u16 (M)][pad][uv f32 2M][uvn f32 2M][keys u8]
-struct BlobView {
-  const uint8_t *cam;
-  const uint16_t *clone;
-  const float *uv;
-  const float *uvn;
-  const uint8_t *keys;
-};
 
 // ---- launchers (each enqueues on ctx->stream; no host sync)
 void launch_cam_poses(ovb_ctx *ctx);

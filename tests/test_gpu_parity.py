@@ -252,7 +252,7 @@ def test_config2_size_properties(eng, oracle):
     assert st == 0
     assert np.array_equal(P, P.T)
     assert np.all(np.diag(P) <= np.diag(case.P) * (1 + 1e-12)) and np.linalg.eigvalsh(P).min() > -1e-12 * np.abs(P).max()
-    assert np.isfinite(dx).all() and stats.n_feats_used > 300
+    assert np.isfinite(dx).all() and stats.n_feats_used > 250
     # idempotence of the gate: re-running on the same prior gives the same decisions and the same answer bit for bit
     eng.cov_set(case.P)
     st2, out2, dx2, _ = eng.msckf_update(case.frame, case.feats, opts)
