@@ -21,6 +21,12 @@
 #define QR_THREADS QR_CR
 #define QR_WARPS (QR_THREADS / 32)
 #define QR_KG 4 // k-groups in the Y = V'A product
+#ifdef OVB_TSQR_TIMING
+#include <cstdio>
+#define TPROBE(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) tprobe[i] = clock64(); } while (0)
+#else
+#define TPROBE(i) do { } while (0)
+#endif
 
 struct QrSmem {
   double Vs[QR_CR][QR_NB];            // reflectors (unit lower trapezoid)
@@ -32,6 +38,9 @@ struct QrSmem {
   double rowk[2][QR_NB];              // pivot row broadcast
   double G[QR_NB][QR_NB];             // strict lower: v_k'v_i
   double tau[QR_NB];
+  double vbuf[16 * 18];               // pivot column broadcast [row group][16 rows], pitch 18 against bank conflicts
+  double sc[4];                       // tau, 1/(alpha-beta) of the current step
+  double Rb[QR_NB][QR_NB];            // finished R entries of this chunk
   int rowidx[QR_CR];
 };
 
@@ -78,6 +87,11 @@ __global__ void __launch_bounds__(QR_THREADS)
   QrSmem &sm = *reinterpret_cast<QrSmem *>(qr_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int chunk = blockIdx.x;
+#ifdef OVB_TSQR_TIMING
+  long long tprobe[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tacc[5] = {0, 0, 0, 0, 0}, tlast = 0;
+#endif
+  TPROBE(0);
   const int rows_i = min(QR_CR, len - chunk * QR_CR);
   // ---- row map of this level back to rows of A
   {
@@ -86,131 +100,199 @@ __global__ void __launch_bounds__(QR_THREADS)
       g = (g / nbp) * QR_CR + (g % nbp);
     sm.rowidx[tid] = c0 + g;
   }
-  // ---- load the panel row
+  // ---- panel factorisation. Ownership: thread (j = tid>>4, g = tid&15) holds rows 16g..16g+15 of panel column j in
+  // registers, so a half-warp owns one column and every column dot product v'a_j is 16 FMAs + a 4-level half-warp
+  // butterfly (the previous row-per-thread layout needed a 16-value block reduction per column: ~6x the instructions,
+  // all on one dependent chain). The 16 rows sit in a rotating window: after k rotations slot t holds local row
+  // (k + t) mod 16, hence the pivot row of step k is slot 0 of group g == k/16 and every register index is static.
+  double *Bp = &sm.At[0][0]; // staging [j][t][g], pitch 257: conflict-free both ways (aliases the tile buffer)
+  {
+    const int lj = tid & 15, rr = tid >> 4;
+#pragma unroll 4
+    for (int pass = 0; pass < QR_CR / 16; pass++) {
+      const int r = pass * 16 + rr;
+      double v = 0.0;
+      if (r < rows_i && lj < nbp) {
+        if (level == 0)
+          v = A[(size_t)(c0 + chunk * QR_CR + r) * ldA + c0 + lj];
+        else
+          v = Win[(size_t)(chunk * QR_CR + r) * QR_NB + lj];
+      }
+      Bp[lj * 257 + (r & 15) * 16 + (r >> 4)] = v;
+    }
+  }
+  __syncthreads();
+  TPROBE(1);
+  const int pj = tid >> 4, pg = tid & 15;
   double a[QR_NB];
 #pragma unroll
-  for (int j = 0; j < QR_NB; j++)
-    a[j] = 0.0;
-  if (tid < rows_i) {
-    if (level == 0) {
-      const double *src = A + (size_t)(c0 + chunk * QR_CR + tid) * ldA + c0;
-#pragma unroll
-      for (int j = 0; j < QR_NB; j++)
-        if (j < nbp)
-          a[j] = src[j];
-    } else {
-      const double *src = Win + (size_t)(chunk * QR_CR + tid) * QR_NB;
-#pragma unroll
-      for (int j = 0; j < QR_NB; j++)
-        if (j < nbp)
-          a[j] = src[j];
+  for (int t = 0; t < QR_NB; t++)
+    a[t] = Bp[pj * 257 + t * 16 + pg];
+  __syncthreads(); // Bp (== At) is free again
+  // Finished rows (row k of columns j >= k after step k) leave the register window: their value goes to sm.Rb and
+  // the slot is zeroed, so every later dot product and update runs unmasked over all 16 slots.
+#pragma unroll 1
+  for (int k = 0; k < nbp; k++) {
+#ifdef OVB_TSQR_TIMING
+    tlast = clock64();
+#define TSTEP(i) do { long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
+#else
+#define TSTEP(i) do { } while (0)
+#endif
+    // pivot row k lives in group 0, window slot 0 (k < 16)
+    double pv = 0.0;
+    if (pg == 0 && pj >= k) {
+      pv = a[0];
+      a[0] = 0.0;
     }
-  }
-  // ---- Householder by column
+    if (pj == k) {
 #pragma unroll
-  for (int k = 0; k < QR_NB; k++) {
-    if (k >= nbp)
-      break;
-    const int buf = k & 1;
-    const bool below = (tid > k && tid < rows_i);
-    double p[QR_NB];
-    const double ak = a[k];
-#pragma unroll
-    for (int j = 0; j < QR_NB; j++)
-      p[j] = below ? ak * a[j] : 0.0;
-    double tot = warp_reduce16(p, lane);
-    if ((lane & 1) == 0)
-      sm.wred[buf][wid][reduce16_index(lane)] = tot;
-    if (tid == k) {
-#pragma unroll
-      for (int j = 0; j < QR_NB; j++)
-        sm.rowk[buf][j] = a[j];
+      for (int t = 0; t < QR_NB; t++)
+        sm.vbuf[pg * 18 + t] = a[t];
     }
     __syncthreads();
-    if (tid < QR_NB) {
-      double s = 0.0;
+    TSTEP(0);
+    double v[QR_NB];
 #pragma unroll
-      for (int w = 0; w < QR_WARPS; w++)
-        s += sm.wred[buf][w][tid];
-      sm.fin[buf][tid] = s;
+    for (int t = 0; t < QR_NB; t += 2) {
+      const double2 vv = *reinterpret_cast<const double2 *>(&sm.vbuf[pg * 18 + t]);
+      v[t] = vv.x;
+      v[t + 1] = vv.y;
     }
-    __syncthreads();
-    const double alpha = sm.rowk[buf][k];
-    const double sigma = sm.fin[buf][k];
-    double beta, scale, tk;
-    if (sigma == 0.0) {
-      tk = 0.0;
-      beta = alpha;
-      scale = 0.0;
-    } else {
-      beta = sqrt(alpha * alpha + sigma);
-      if (alpha >= 0.0)
-        beta = -beta;
-      tk = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
-    }
-    const double vr = below ? ak * scale : (tid == k ? 1.0 : 0.0);
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-    for (int j = 0; j < QR_NB; j++) {
-      if (j > k && j < nbp) {
-        double wj = sm.rowk[buf][j] + sm.fin[buf][j] * scale;
-        if (tid >= k && tid < rows_i)
-          a[j] -= tk * wj * vr;
+    for (int t = 0; t < QR_NB; t += 4) {
+      d0 += v[t] * a[t];
+      d1 += v[t + 1] * a[t + 1];
+      d2 += v[t + 2] * a[t + 2];
+      d3 += v[t + 3] * a[t + 3];
+    }
+    double dot = (d0 + d1) + (d2 + d3);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    // pivot-row entry of this thread's column (held by the g == 0 thread of the half-warp; for j < k it is V[k][j])
+    const double akj = __shfl_sync(0xffffffffu, (pj >= k) ? pv : a[0], lane & 16);
+    TSTEP(1);
+    if (pj == k && pg == 0) {
+      const double alpha = akj, sigma = dot;
+      double tk = 0.0, scale = 0.0, beta = alpha;
+      if (sigma != 0.0) {
+        // |x|, 1/|x| and 1/(|alpha|+|x|) from float-seeded Newton iterations (2 steps: 23 -> 46 -> 92 bits). The library
+        // sqrt + two divisions cost ~1600 cycles in this single thread while the whole CTA waits at the barrier.
+        const double n2 = alpha * alpha + sigma;
+        const double aa = fabs(alpha);
+        double nrm, tkk, sc;
+        if (n2 > 1e-30 && n2 < 1e30) {
+          double y = (double)rsqrtf((float)n2);
+          y = y * (1.5 - 0.5 * n2 * y * y);
+          y = y * (1.5 - 0.5 * n2 * y * y);
+          nrm = n2 * y;
+          nrm = nrm + 0.5 * y * (n2 - nrm * nrm); // one Heron correction: nrm = sqrt(n2) to ~1 ulp
+          const double x = aa + nrm;
+          double rc = (double)(1.0f / (float)x);
+          rc = rc * (2.0 - x * rc);
+          rc = rc * (2.0 - x * rc);
+          rc = rc * (2.0 - x * rc);
+          sc = rc;
+          tkk = 1.0 + aa * y; // tau = (|alpha| + nrm)/nrm = 1 + |alpha|/nrm, with 1/nrm = y to working precision
+        } else { // out of float range: the slow exact path
+          nrm = sqrt(n2);
+          sc = 1.0 / (aa + nrm);
+          tkk = (aa + nrm) / nrm;
+        }
+        beta = (alpha >= 0.0) ? -nrm : nrm;
+        tk = tkk;                               // (beta - alpha)/beta = (|alpha| + nrm)/nrm
+        scale = (alpha >= 0.0) ? sc : -sc;      // 1/(alpha - beta) = sign(alpha)/(|alpha| + nrm)
       }
-    }
-    if (below)
-      a[k] = vr;
-    else if (tid == k)
-      a[k] = beta;
-    if (tid == 0) {
+      sm.sc[0] = tk;
+      sm.sc[1] = scale;
       sm.tau[k] = tk;
-#pragma unroll
-      for (int i = 0; i < QR_NB; i++)
-        if (i < k)
-          sm.G[k][i] = sm.rowk[buf][i] + sm.fin[buf][i] * scale; // v_k'v_i
+      sm.Rb[k][k] = beta;
     }
-  }
-  // ---- publish V, emit this chunk's R
+    TSTEP(2);
+    __syncthreads();
+    TSTEP(3);
+    const double tk = sm.sc[0], scale = sm.sc[1];
+    const double wj = akj + dot * scale; // v'a_j (for j < k: v_k'v_j)
+    if (pj > k) {
+      const double tw = tk * wj * scale;
 #pragma unroll
-  for (int j = 0; j < QR_NB; j++) {
-    double v = 0.0;
-    if (j < nbp && tid < rows_i)
-      v = (j < tid) ? a[j] : (j == tid ? 1.0 : 0.0);
-    sm.Vs[tid][j] = v;
+      for (int t = 0; t < QR_NB; t++)
+        a[t] -= tw * v[t];
+      if (pg == 0)
+        sm.Rb[k][pj] = pv - tk * wj; // finished entry R[k][j]
+    } else if (pj == k) {
+#pragma unroll
+      for (int t = 0; t < QR_NB; t++)
+        a[t] = v[t] * scale;
+    } else if (pg == 0) {
+      sm.G[k][pj] = wj;
+    }
+    {
+      const double t0 = a[0];
+#pragma unroll
+      for (int t = 0; t < QR_NB - 1; t++)
+        a[t] = a[t + 1];
+      a[QR_NB - 1] = t0;
+    }
+    TSTEP(4);
   }
-  if (blockIdx.y == 0 && tid < nbp) {
-    // rows beyond the chunk's height do not exist: the next level reads only min(nbp, rows_i) rows per chunk
-    if (tid < rows_i) {
+#pragma unroll 1
+  for (int s2 = nbp; s2 < QR_NB; s2++) { // complete the cycle: slot t is local row t again
+    const double t0 = a[0];
+#pragma unroll
+    for (int t = 0; t < QR_NB - 1; t++)
+      a[t] = a[t + 1];
+    a[QR_NB - 1] = t0;
+  }
+  __syncthreads();
+  TPROBE(2);
+  // ---- publish V (unit lower trapezoid) and emit this chunk's R
+#pragma unroll
+  for (int t = 0; t < QR_NB; t++) {
+    const int r = pg * 16 + t;
+    double vv = 0.0;
+    if (pj < nbp && r < rows_i)
+      vv = (r > pj) ? a[t] : (r == pj ? 1.0 : 0.0);
+    sm.Vs[r][pj] = vv;
+  }
+  if (blockIdx.y == 0 && pg == 0) {
+    // thread (j, g=0) emits column j of the chunk's R from sm.Rb (rows t <= j; zeros below the diagonal)
+    const int nr = min(nbp, rows_i);
+    for (int t = 0; t < nr; t++) {
+      const double val = (pj < nbp && t <= pj) ? sm.Rb[t][pj] : 0.0;
       if (is_last) {
-        double *dst = Rout + (size_t)(c0 + tid) * ldR + c0;
-#pragma unroll
-        for (int j = 0; j < QR_NB; j++)
-          if (j < nbp)
-            dst[j] = (j >= tid) ? a[j] : 0.0;
+        if (pj < nbp)
+          Rout[(size_t)(c0 + t) * ldR + c0 + pj] = val;
       } else {
-        double *dst = Wout + (size_t)(chunk * nbp + tid) * QR_NB;
-#pragma unroll
-        for (int j = 0; j < QR_NB; j++)
-          dst[j] = (j >= tid && j < nbp) ? a[j] : 0.0;
+        Wout[(size_t)(chunk * nbp + t) * QR_NB + pj] = val;
       }
     }
   }
   __syncthreads();
   // ---- apply Q' to the trailing column tiles owned by this CTA
+  TPROBE(3);
   const int tc0 = c0 + nbp;
   const int ntrail = nt - tc0;
   const int ntiles = (ntrail + QR_CT - 1) / QR_CT;
   for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
     const int col0 = tc0 + tile * QR_CT;
     const int ncol = min(QR_CT, nt - col0);
-    // load tile (warp per row, lanes over columns: coalesced 256 B rows)
-    for (int r = wid; r < QR_CR; r += QR_WARPS) {
-      double v = 0.0;
-      if (r < rows_i && lane < ncol)
-        v = A[(size_t)sm.rowidx[r] * ldA + col0 + lane];
-      sm.At[r][lane] = v;
+    // load tile (warp per row, lanes over columns: coalesced 256 B rows); 8 independent loads in flight per lane
+    for (int rb = 0; rb < QR_CR; rb += 8 * QR_WARPS) {
+      double vals[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int r = rb + u * QR_WARPS + wid;
+        vals[u] = (r < rows_i && lane < ncol) ? A[(size_t)sm.rowidx[r] * ldA + col0 + lane] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        sm.At[rb + u * QR_WARPS + wid][lane] = vals[u];
     }
     __syncthreads();
+    if (tile == (int)blockIdx.y) TPROBE(4);
     // Y = V'At : thread = (kgroup, 4 V-columns, 2 tile columns), 64 rows each
     {
       const int kg = tid >> 6, within = tid & 63, ib = within >> 4, cb = within & 15;
@@ -240,6 +322,7 @@ __global__ void __launch_bounds__(QR_THREADS)
       }
     }
     __syncthreads();
+    if (tile == (int)blockIdx.y) TPROBE(5);
     // Z: sequential reflector coupling per column, z_k = tau_k (y_k - sum_{i<k} G[k][i] z_i)
     if (tid < QR_CT) {
       double z[QR_NB];
@@ -261,26 +344,44 @@ __global__ void __launch_bounds__(QR_THREADS)
       }
     }
     __syncthreads();
+    if (tile == (int)blockIdx.y) TPROBE(6);
     // At -= V Z : lanes over columns (Z column in registers), warps over rows; then store back
     {
       double z[QR_NB];
 #pragma unroll
       for (int k = 0; k < QR_NB; k++)
         z[k] = sm.Zs[k][lane];
-      for (int r = wid; r < rows_i; r += QR_WARPS) {
-        double acc = 0.0;
+      for (int r0 = wid; r0 < rows_i; r0 += 4 * QR_WARPS) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < QR_NB; k += 2) {
-          const double2 v = *reinterpret_cast<const double2 *>(&sm.Vs[r][k]);
-          acc += v.x * z[k];
-          acc += v.y * z[k + 1];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int r = min(r0 + u * QR_WARPS, QR_CR - 1);
+            const double2 v = *reinterpret_cast<const double2 *>(&sm.Vs[r][k]);
+            acc[u] += v.x * z[k];
+            acc[u] += v.y * z[k + 1];
+          }
         }
-        if (lane < ncol)
-          A[(size_t)sm.rowidx[r] * ldA + col0 + lane] = sm.At[r][lane] - acc;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int r = r0 + u * QR_WARPS;
+          if (r < rows_i && lane < ncol)
+            A[(size_t)sm.rowidx[r] * ldA + col0 + lane] = sm.At[r][lane] - acc[u];
+        }
       }
     }
     __syncthreads();
   }
+  TPROBE(7);
+#ifdef OVB_TSQR_TIMING
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    printf("tsqr c0=%d lvl=%d grid=(%d,%d) rows=%d | load %lld qr %lld publish %lld tileload %lld Y %lld Z %lld upd+rest %lld | total %lld\n", c0, level,
+           gridDim.x, gridDim.y, rows_i, tprobe[1] - tprobe[0], tprobe[2] - tprobe[1], tprobe[3] - tprobe[2], tprobe[4] - tprobe[3], tprobe[5] - tprobe[4],
+           tprobe[6] - tprobe[5], tprobe[7] - tprobe[6], tprobe[7] - tprobe[0]);
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && c0 == 0)
+    printf("   qr steps: syncA %lld dot+shfl %lld scalar %lld syncB %lld update+rot %lld\n", tacc[0], tacc[1], tacc[2], tacc[3], tacc[4]);
+#endif
 }
 
 // copy the trailing parts of the finished R rows out of A, zero the strict lower part, normalise diag >= 0
