@@ -242,6 +242,19 @@ double ovb_chi2_quantile95(int dof);
  * [0] triangulate+GN  [1] jacobian+nullspace+gate  [2] column map  [3] TSQR  [4] EKF update  [5] total */
 ovb_status ovb_last_stage_ms(const ovb_ctx *ctx, float ms[6]);
 
+/* ---- multi-GPU: features sharded across ranks, one all-gather of the compressed [R | z] blocks ----
+ * The reference is single-process; these replace nothing in it. One context per rank/GPU, each holding a replica of P.
+ *  ovb_set_stream           adopt an external CUDA stream (e.g. the stream NCCL collectives are issued on).
+ *  ovb_msckf_shard_compress steps 2-5 of UpdaterMSCKF::update on THIS rank's feature shard; the shard's compressed system
+ *                           [R_g | z_g] (n_cols x (n_cols+1), row-major, leading dimension *ld) is written to the DEVICE
+ *                           buffer R_dev. Asynchronous on the context stream. Column order is canonical.
+ *  ovb_msckf_shard_finish   stacked_dev = the n_blocks all-gathered blocks, stacked by rank (DEVICE pointer, overwritten):
+ *                           compress the stack, EKFUpdate on this rank's P, return dx and the shard's per-feature results. */
+ovb_status ovb_set_stream(ovb_ctx *ctx, void *cuda_stream);
+ovb_status ovb_msckf_shard_compress(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, double *R_dev,
+                                    int R_cap_doubles, int *n_cols, int *ld);
+ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_blocks, ovb_feat_out *out, double *dx, ovb_stats *stats);
+
 /* ---- measurement support: re-run the LAST ovb_msckf_update on its device-resident inputs ----
  * ovb_set_replay(ctx,1) makes ovb_msckf_update keep a copy of the prior P; ovb_msckf_replay then restores that prior and
  * re-enqueues the identical device pipeline `steps` times (optionally flushing L2 with a 256 MiB memset between steps),

@@ -228,6 +228,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ovb_chi2_quantile95.restype = C.c_double
     lib.ovb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 6)]
     lib.ovb_last_counters.argtypes = [vp, C.POINTER(C.c_int64 * 4)]
+    lib.ovb_set_stream.argtypes = [vp, C.c_void_p]
+    lib.ovb_msckf_shard_compress.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts), C.c_void_p,
+                                             C.c_int, c_int_p, c_int_p]
+    lib.ovb_msckf_shard_finish.argtypes = [vp, C.c_void_p, C.c_int, C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
     lib.ovb_set_replay.argtypes = [vp, C.c_int]
     lib.ovb_msckf_replay.argtypes = [vp, C.c_int, C.c_int, c_float_p, C.POINTER(C.c_float * 5)]
     if path is None:
@@ -240,6 +244,7 @@ EXPORTED_SYMBOLS = [
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate",
     "ovb_msckf_update", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress",
     "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
+    "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_finish",
 ]
 
 
@@ -373,6 +378,29 @@ class Engine:
                                      _ptr(dx, c_double_p))
         self._check(st, allow=(OVB_ERR_NEG_DIAG,))
         return st, dx
+
+    # ---- multi-GPU staged calls (device pointers are raw ints, e.g. torch.Tensor.data_ptr())
+    def set_stream(self, cuda_stream_handle: int):
+        self._check(self.lib.ovb_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def shard_compress(self, frame: FrameArrays, feats: FeatArrays, opts: ovb_opts, R_dev_ptr: int, R_cap_doubles: int):
+        n = np.zeros(1, dtype=np.int32)
+        ld = np.zeros(1, dtype=np.int32)
+        fs, bs = frame.struct(), feats.struct()
+        self._keep = (frame, feats, fs, bs)  # the call is asynchronous: keep the host arrays alive until shard_finish
+        self._check(self.lib.ovb_msckf_shard_compress(self.h, C.byref(fs), C.byref(bs), C.byref(opts), C.c_void_p(R_dev_ptr),
+                                                      int(R_cap_doubles), _ptr(n, c_int_p), _ptr(ld, c_int_p)))
+        return int(n[0]), int(ld[0])
+
+    def shard_finish(self, stacked_dev_ptr: int, n_blocks: int, n_feats: int):
+        out = FeatOut(n_feats)
+        dx = np.zeros(self.cov_dim())
+        stats = ovb_stats()
+        os_ = out.struct()
+        st = self.lib.ovb_msckf_shard_finish(self.h, C.c_void_p(stacked_dev_ptr), int(n_blocks), C.byref(os_), _ptr(dx, c_double_p),
+                                             C.byref(stats))
+        self._check(st, allow=(OVB_ERR_NEG_DIAG,))
+        return st, out, dx, stats
 
     def last_counters(self):
         a = (C.c_int64 * 4)()

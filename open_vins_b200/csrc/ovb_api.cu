@@ -91,6 +91,7 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
   CK(cudaGetDeviceProperties(&prop, ctx->device));
   ctx->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = 1;
   for (int i = 0; i < 8; i++)
     CK(cudaEventCreate(&ctx->ev[i]));
   const int ms = ctx->cfg.max_state;
@@ -173,7 +174,7 @@ void ovb_destroy(ovb_ctx *ctx) {
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i])
       cudaEventDestroy(ctx->ev[i]);
-  if (ctx->stream)
+  if (ctx->stream && ctx->own_stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -817,6 +818,113 @@ ovb_status ovb_last_stage_ms(const ovb_ctx *ctx, float ms[6]) {
     return OVB_ERR_ARG;
   for (int i = 0; i < 6; i++)
     ms[i] = ctx->stage_ms[i];
+  return OVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU (features sharded)
+// stages A (triangulate, Jacobian, nullspace, gate) and the local compression run on this rank's feature
+// shard; the ranks exchange their compressed [R_g | z_g] blocks with ONE all-gather (done by the caller, e.g. NCCL through
+// torch.distributed on the stream adopted with ovb_set_stream); every rank then compresses the stack and performs the
+// identical EKF update on its replica of P (bitwise identical kernels on identical inputs keep the replicas in sync).
+ovb_status ovb_set_stream(ovb_ctx *ctx, void *cuda_stream) {
+  if (!ctx)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cuda_stream) {
+    if (ctx->own_stream && ctx->stream)
+      cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = 0;
+  }
+  return OVB_OK;
+}
+
+ovb_status ovb_msckf_shard_compress(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, double *R_dev,
+                                    int R_cap_doubles, int *n_cols, int *ld) {
+  if (!ctx || !frame || !feats || !opts || !R_dev || !n_cols || !ld || ctx->N < 1)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  cudaEventRecord(ctx->ev[0], ctx->stream);
+  Packed pk;
+  ovb_opts o2 = *opts;
+  o2.col_order = OVB_COLS_CANONICAL; // the column order must be fixed before sharding
+  ovb_status st = pack_inputs(ctx, frame, feats, &o2, nullptr, &pk);
+  if (st != OVB_OK)
+    return st;
+  *n_cols = pk.n_all;
+  *ld = pk.ldH;
+  if ((size_t)pk.n_all * pk.ldH > (size_t)R_cap_doubles)
+    return OVB_ERR_CAPACITY;
+  ctx->last_n_feats = pk.n_feats;
+  ctx->last_n_all = pk.n_all;
+  ctx->last_ldH = pk.ldH;
+  ctx->n_launch = 0;
+  ctx->n_launch_tsqr_level = 0;
+  launch_cam_poses(ctx);
+  launch_triangulate(ctx, pk.n_feats, pk.bv);
+  launch_feature_system(ctx, pk.n_feats, pk.bv, pk.ldH, 0, pk.max_M);
+  launch_column_map(ctx, pk.n_feats, pk.bv);
+  ctx->n_launch += 4;
+  if (pk.m_total > 0)
+    launch_tsqr(ctx, ctx->d_Hs, pk.m_total, pk.n_all, pk.ldH, R_dev, pk.ldH);
+  else
+    OVB_CUDA_CHECK(ctx, cudaMemsetAsync(R_dev, 0, sizeof(double) * (size_t)pk.n_all * pk.ldH, ctx->stream));
+  cudaEventRecord(ctx->ev[4], ctx->stream);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  return OVB_OK;
+}
+
+ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_blocks, ovb_feat_out *out, double *dx, ovb_stats *stats) {
+  if (!ctx || !stacked_dev || n_blocks < 1 || !dx || ctx->N < 1)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const int N = ctx->N, n_all = ctx->last_n_all, ld = ctx->last_ldH, F = ctx->last_n_feats;
+  const double *Rfinal = stacked_dev;
+  if (n_blocks > 1) {
+    launch_tsqr(ctx, stacked_dev, n_blocks * n_all, n_all, ld, ctx->d_R, ld);
+    Rfinal = ctx->d_R;
+  }
+  k_take_z<<<(n_all + 127) / 128, 128, 0, ctx->stream>>>(Rfinal, ld, n_all, n_all, ctx->d_w);
+  launch_ekf_update(ctx, Rfinal, ld, n_all, n_all, false, ctx->h_opts->sigma_pix_sq, nullptr);
+  ctx->n_launch += 7;
+  cudaEventRecord(ctx->ev[5], ctx->stream);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + sizeof(DevUpdateInfo) + sizeof(double) * (size_t)N;
+  cudaEventRecord(ctx->ev[6], ctx->stream);
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  unpack_feats(ctx, F, out);
+  for (int i = 0; i < N; i++)
+    dx[i] = ctx->h_dx[i];
+  cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[0], ctx->ev[6]);
+  cudaEventElapsedTime(&ctx->stage_ms[3], ctx->ev[0], ctx->ev[4]);
+  cudaEventElapsedTime(&ctx->stage_ms[4], ctx->ev[4], ctx->ev[5]);
+  const DevUpdateInfo *inf = ctx->h_info;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_feats_in = F;
+    int used = 0, rows = 0;
+    for (int f = 0; f < F; f++)
+      if (ctx->h_feat[f].status == OVB_FEAT_OK) {
+        used++;
+        rows += 2 * (ctx->h_feat[f].m1 - ctx->h_feat[f].m0) - 3;
+      }
+    stats->n_feats_used = used; // this rank's shard
+    stats->rows_stacked = rows;
+    stats->cols_stacked = n_all;
+    stats->rows_update = n_all;
+    stats->neg_diag_index = inf->neg_diag_index != 0x7fffffff ? inf->neg_diag_index : -1;
+    stats->ms_total = ctx->stage_ms[5];
+  }
+  if (inf->not_spd)
+    return OVB_ERR_NOT_SPD;
+  if (inf->nonfinite)
+    return OVB_ERR_NONFINITE;
+  if (inf->neg_diag_index != 0x7fffffff)
+    return OVB_ERR_NEG_DIAG;
   return OVB_OK;
 }
 

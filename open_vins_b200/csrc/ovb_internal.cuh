@@ -81,6 +81,7 @@ struct ovb_ctx {
   ovb_config cfg;
   int device;
   cudaStream_t stream;
+  int own_stream;
   cudaEvent_t ev[8];
   char err[256];
   // covariance (double buffered for clone/marginalize), row-major with leading dimension ldP

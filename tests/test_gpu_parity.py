@@ -261,3 +261,43 @@ def test_config2_size_properties(eng, oracle):
     assert np.array_equal(out.status, ref["out"].status)
     assert np.linalg.norm(P - ref["P"]) <= 1e-9 * np.linalg.norm(ref["P"])
     assert np.linalg.norm(dx - ref["dx"]) <= 1e-9 * np.linalg.norm(ref["dx"])
+
+
+def test_sharded_update_matches_single(oracle):
+    """The N>1 data path on one GPU: two engine contexts stand in for two ranks; their compressed blocks are stacked
+    (what the all-gather produces) and each finishes the update. Result = the single-context update = the oracle."""
+    import torch
+    from open_vins_b200 import multigpu
+    case = sim.make_update_case(n_feats=120, n_clones=21, n_cams=2, seed=3, calib_ext=True, calib_intr=True, calib_imu=True, calib_dt=True)
+    opts = _opts(case, col_order=capi.COLS_CANONICAL)
+    ref = oracle.msckf_update(case.frame, case.feats, opts, case.P, dumps=False)
+    world = 2
+    dev = torch.device("cuda", 0)
+    engs = [capi.Engine(max_state=256, max_feats=512, max_meas=512 * 48) for _ in range(world)]
+    parts = multigpu.partition_features(case.feats.meas_off, world)
+    blocks, shards = [], []
+    cap = 512 * 520
+    for r, e in enumerate(engs):
+        e.cov_set(case.P)
+        shard = case.feats.subset(np.arange(*parts[r]))
+        shards.append(shard)
+        buf = torch.zeros(cap, dtype=torch.float64, device=dev)
+        n, ld = e.shard_compress(case.frame, shard, opts, buf.data_ptr(), cap)
+        torch.cuda.synchronize()
+        blocks.append(buf[: n * ld].clone())
+    status = []
+    for r, e in enumerate(engs):
+        stacked = torch.cat(blocks).contiguous()
+        st, out, dx, stats = e.shard_finish(stacked.data_ptr(), world, shards[r].n_feats)
+        assert st == 0
+        status.append(out.status)
+        P = e.cov_get()
+        assert np.linalg.norm(P - ref["P"]) <= 1e-9 * np.linalg.norm(ref["P"])
+        assert np.linalg.norm(dx - ref["dx"]) <= 1e-9 * np.linalg.norm(ref["dx"])
+        if r == 0:
+            P0, dx0 = P, dx
+        else:
+            assert np.array_equal(P, P0) and np.array_equal(dx, dx0)  # replicas stay bitwise identical
+    assert np.array_equal(np.concatenate(status), ref["out"].status)
+    for e in engs:
+        e.close()
