@@ -22,6 +22,7 @@ UNITS = [
     ("k_triangulate.cu", ["-fmad=false"]),
     ("k_feature.cu", ["-fmad=false"]),
     ("k_tsqr.cu", []),
+    ("k_gram.cu", []),
     ("k_ekf.cu", []),
     ("ovb_api.cu", []),
 ]

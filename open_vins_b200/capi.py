@@ -28,6 +28,7 @@ OVB_OK, OVB_ERR_NEG_DIAG, OVB_ERR_NONFINITE, OVB_ERR_CAPACITY, OVB_ERR_CUDA, OVB
  REP_ANCHORED_MSCKF_INVERSE_DEPTH, REP_ANCHORED_INVERSE_DEPTH_SINGLE) = range(6)
 CAM_RADTAN, CAM_EQUI = 0, 1
 COLS_REFERENCE_FIRST_SEEN, COLS_CANONICAL = 0, 1
+COMPRESS_HOUSEHOLDER_TSQR, COMPRESS_NORMAL_EQUATIONS = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)
@@ -49,7 +50,7 @@ class ovb_opts(C.Structure):
         ("max_cond_number", C.c_double),
         ("sigma_pix", C.c_double), ("chi2_multipler", C.c_double),
         ("do_fej", C.c_int), ("feat_rep", C.c_int), ("do_calib_camera_pose", C.c_int),
-        ("do_calib_camera_intrinsics", C.c_int), ("col_order", C.c_int),
+        ("do_calib_camera_intrinsics", C.c_int), ("col_order", C.c_int), ("compress", C.c_int),
     ]
 
 
@@ -59,7 +60,8 @@ def default_opts(**kw) -> ovb_opts:
     o = ovb_opts(triangulate_1d=0, refine_features=1, max_runs=5, init_lamda=1e-3, max_lamda=1e10, min_dx=1e-6,
                  min_dcost=1e-6, lam_mult=10.0, min_dist=0.10, max_dist=60.0, max_baseline=40.0,
                  max_cond_number=10000.0, sigma_pix=1.0, chi2_multipler=1.0, do_fej=1, feat_rep=REP_GLOBAL_3D,
-                 do_calib_camera_pose=0, do_calib_camera_intrinsics=0, col_order=COLS_REFERENCE_FIRST_SEEN)
+                 do_calib_camera_pose=0, do_calib_camera_intrinsics=0, col_order=COLS_REFERENCE_FIRST_SEEN,
+                 compress=COMPRESS_HOUSEHOLDER_TSQR)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise AttributeError(k)
@@ -224,6 +226,7 @@ def load_library(path: str | None = None) -> C.CDLL:
                                           C.POINTER(ovb_feat_out), C.c_int, c_double_p, c_double_p, c_double_p,
                                           c_int_p, c_int_p, c_int_p, C.c_int]
     lib.ovb_compress.argtypes = [vp, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
+    lib.ovb_compress_gram.argtypes = [vp, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
     lib.ovb_chi2_quantile95.argtypes = [C.c_int]
     lib.ovb_chi2_quantile95.restype = C.c_double
     lib.ovb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 6)]
@@ -242,7 +245,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate",
-    "ovb_msckf_update", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress",
+    "ovb_msckf_update", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram",
     "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
     "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_finish",
 ]
@@ -356,14 +359,14 @@ class Engine:
         n = int(ncols[0])
         return Hf, np.ascontiguousarray(Hx[:, :n]), res, row_off, col_index[:n].copy()
 
-    def compress(self, H, res):
+    def compress(self, H, res, mode=COMPRESS_HOUSEHOLDER_TSQR):
         H = np.ascontiguousarray(H, dtype=np.float64)
         res = np.ascontiguousarray(res, dtype=np.float64)
         m, n = H.shape
         R = np.zeros((n, n))
         z = np.zeros(n)
-        self._check(self.lib.ovb_compress(self.h, _ptr(H, c_double_p), m, n, _ptr(res, c_double_p),
-                                          _ptr(R, c_double_p), _ptr(z, c_double_p)))
+        fn = self.lib.ovb_compress if mode == COMPRESS_HOUSEHOLDER_TSQR else self.lib.ovb_compress_gram
+        self._check(fn(self.h, _ptr(H, c_double_p), m, n, _ptr(res, c_double_p), _ptr(R, c_double_p), _ptr(z, c_double_p)))
         return R, z
 
     def ekf_update(self, off, sz, H, res, sigma2=1.0, Rdiag=None):

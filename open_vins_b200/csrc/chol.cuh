@@ -1,42 +1,84 @@
-// chol.cuh — CTA-cooperative blocked Cholesky used by the chi² gate (k_feature.cu) and the EKF update (k_ekf.cu).
+// chol.cuh — CTA-cooperative blocked Cholesky used by the chi² gate (k_feature.cu), the EKF update (k_ekf.cu) and the
+// normal-equations compression (k_gram.cu).
 #pragma once
 #include <math.h>
 
-// ---- blocked in-place Cholesky of the n x n matrix at S (lower triangle used), with `extra` right-hand-side rows
-// stored as rows n..n+extra-1 (they receive rhs * L^-T, i.e. (L^-1 rhs')'). Returns false when a pivot is not positive.
+// 1/sqrt(d) from a float seed and two Newton steps (23 -> 46 -> 92 bits); the library sqrt/divide pair costs several
+// hundred cycles on a single dependent chain, and every Cholesky pivot sits on the critical path of the whole CTA.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  if (d > 1e-30 && d < 1e30) {
+    double y = (double)rsqrtf((float)d);
+    y = y * (1.5 - 0.5 * d * y * y);
+    y = y * (1.5 - 0.5 * d * y * y);
+    return y;
+  }
+  return 1.0 / sqrt(d);
+}
+
+// Blocked in-place Cholesky of the n x n matrix at S (lower triangle used), with `extra` right-hand-side rows stored as
+// rows n..n+extra-1 (they receive rhs * L^-T, i.e. (L^-1 rhs')').
+//   diag0 == nullptr : strict mode, a pivot <= 0 (or NaN) raises *flag and the result must be discarded.
+//   diag0 != nullptr : semidefinite mode, a pivot <= psd_tol * diag0[j] (roundoff-level: the direction carries no
+//                      information) zeroes column j of L instead of failing.
+// invd: 8 doubles of shared memory scratch. inv_out (optional, n doubles): receives 1/L[j][j]. Returns true when no strict-mode pivot failed.
 template <int THREADS>
-__device__ bool chol_lower_block(double *S, int ld, int n, int extra, int *flag) {
+__device__ bool chol_lower_block(double *S, int ld, int n, int extra, int *flag, double *invd, const double *diag0 = nullptr,
+                                 double psd_tol = 0.0, double *inv_out = nullptr) {
   const int NWARPS = THREADS / 32;
   const int NBK = 8;
-  int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int kb = 0; kb < n; kb += NBK) {
-    int nbk = min(NBK, n - kb);
+    const int nbk = min(NBK, n - kb);
     if (wid == 0) {
-      for (int j = 0; j < nbk; j++) {
-        double d = S[(kb + j) * ld + kb + j];
-        if (!(d > 0.0)) {
-          if (lane == 0)
+      // ---- 8x8 diagonal block in registers: lane i (< nbk) holds row i; pivots broadcast by shuffle
+      double x[NBK];
+      const int li = min(lane, nbk - 1);
+#pragma unroll
+      for (int c = 0; c < NBK; c++)
+        x[c] = (c < nbk && c <= li) ? S[(kb + li) * ld + kb + c] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NBK; j++) {
+        const double d = __shfl_sync(0xffffffffu, x[j], j);
+        double inv = 0.0, ljj = 0.0;
+        if (j < nbk) {
+          bool ok = d > 0.0;
+          if (diag0 != nullptr) {
+            ok = d > psd_tol * diag0[kb + j];
+          } else if (!ok && lane == 0) {
             *flag = 1;
-          d = 1.0; // keep going with a harmless value; the caller discards the result
+          }
+          if (ok) {
+            inv = fast_rsqrt(d);
+            ljj = d * inv;
+          }
         }
-        d = sqrt(d);
-        __syncwarp();
-        if (lane == 0)
-          S[(kb + j) * ld + kb + j] = d;
-        if (lane > j && lane < nbk)
-          S[(kb + lane) * ld + kb + j] /= d;
-        __syncwarp();
-        // trailing update inside the diagonal block
-        for (int e = lane; e < nbk * nbk; e += 32) {
-          int i = e / nbk, c = e % nbk;
-          if (c > j && i >= c)
-            S[(kb + i) * ld + kb + c] -= S[(kb + i) * ld + kb + j] * S[(kb + c) * ld + kb + j];
+        if (lane == j)
+          x[j] = ljj;
+        else if (lane > j)
+          x[j] *= inv;
+#pragma unroll
+        for (int c = 0; c < NBK; c++) {
+          if (c > j) {
+            const double lcj = __shfl_sync(0xffffffffu, x[j], c);
+            if (lane >= c)
+              x[c] -= x[j] * lcj;
+          }
         }
-        __syncwarp();
+        if (lane == 0) {
+          invd[j] = inv;
+          if (inv_out != nullptr && j < nbk)
+            inv_out[kb + j] = inv; // reciprocal pivots for later triangular solves
+        }
+      }
+      if (lane < nbk) {
+#pragma unroll
+        for (int c = 0; c < NBK; c++)
+          if (c <= lane)
+            S[(kb + lane) * ld + kb + c] = x[c];
       }
     }
     __syncthreads();
-    // panel rows below: x L_kk' = S[i][kb..kb+nbk)
+    // ---- panel rows below: x L_kk' = S[i][kb..kb+nbk), using the stored reciprocal pivots (no divisions)
     for (int i = kb + nbk + tid; i < n + extra; i += THREADS) {
       double x[NBK];
 #pragma unroll
@@ -47,7 +89,7 @@ __device__ bool chol_lower_block(double *S, int ld, int n, int extra, int *flag)
           for (int t = 0; t < NBK; t++)
             if (t < c)
               v -= x[t] * S[(kb + c) * ld + kb + t];
-          x[c] = v / S[(kb + c) * ld + kb + c];
+          x[c] = v * invd[c];
         }
       }
 #pragma unroll
@@ -56,25 +98,24 @@ __device__ bool chol_lower_block(double *S, int ld, int n, int extra, int *flag)
           S[i * ld + kb + c] = x[c];
     }
     __syncthreads();
-    // trailing update: S[i][j] -= sum_t S[i][kb+t] S[j][kb+t], kb+nbk <= j <= min(i, n-1)
-    int first = kb + nbk;
+    // ---- trailing update: S[i][j] -= sum_t S[i][kb+t] S[j][kb+t], kb+nbk <= j <= min(i, n-1)
+    const int first = kb + nbk;
     for (int i = first + wid; i < n + extra; i += NWARPS) {
       double li[NBK];
 #pragma unroll
       for (int t = 0; t < NBK; t++)
         li[t] = (t < nbk) ? S[i * ld + kb + t] : 0.0;
-      int jmax = min(i, n - 1);
+      const int jmax = min(i, n - 1);
       for (int j = first + lane; j <= jmax; j += 32) {
-        double acc = 0.0;
+        // eight products summed as a tree (3 dependent adds instead of an 8-long FMA chain: FP64 latency is ~19 cycles)
+        double pr[NBK];
 #pragma unroll
         for (int t = 0; t < NBK; t++)
-          if (t < nbk)
-            acc += li[t] * S[j * ld + kb + t];
-        S[i * ld + j] -= acc;
+          pr[t] = (t < nbk) ? li[t] * S[j * ld + kb + t] : 0.0;
+        S[i * ld + j] -= ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
       }
     }
     __syncthreads();
   }
   return *flag == 0;
 }
-

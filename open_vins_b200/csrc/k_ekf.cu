@@ -81,9 +81,10 @@ __global__ void __launch_bounds__(256) k_ekf_gemm(int mode, const double *__rest
 // single CTA: S (r x r, lower) plus the residual as row r  ->  L and w = L^-1 res in row r. Works in shared memory when
 // it fits, else in place in global memory (L2).
 __global__ void __launch_bounds__(1024) k_ekf_chol(double *__restrict__ S, int ldS, int r, const double *__restrict__ res, double *__restrict__ w,
-                                                   DevUpdateInfo *__restrict__ info, int use_smem) {
+                                                   double *__restrict__ invdiag, DevUpdateInfo *__restrict__ info, int use_smem) {
   extern __shared__ __align__(16) double chol_sm[];
   __shared__ int flag;
+  __shared__ double invd_sh[8];
   const int tid = threadIdx.x;
   if (tid == 0)
     flag = 0;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(1024) k_ekf_chol(double *__restrict__ S, int l
     }
     __syncthreads();
   }
-  chol_lower_block<1024>(W, ld, r, 1, &flag);
+  chol_lower_block<1024>(W, ld, r, 1, &flag, invd_sh, nullptr, 0.0, invdiag);
   __syncthreads();
   if (use_smem) {
     for (int e = tid; e < (r + 1) * r; e += 1024) {
@@ -117,47 +118,85 @@ __global__ void __launch_bounds__(1024) k_ekf_chol(double *__restrict__ S, int l
     info->not_spd = 1;
 }
 
-// Y = M L^-T : each CTA owns 32 rows of M (independent triangular solves), blocked by 16 columns.
-__global__ void __launch_bounds__(256) k_ekf_trsm(const double *__restrict__ M, int ldM, const double *__restrict__ L, int ldL, int N, int r,
-                                                  double *__restrict__ Yout, int ldY) {
-  extern __shared__ __align__(16) double ysm[]; // [32][ldy]
-  const int ldy = r | 1;
-  const int a0 = blockIdx.x * 32;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < 32 * r; e += 256) {
-    int a = e / r, j = e % r;
-    ysm[a * ldy + j] = (a0 + a < N) ? M[(size_t)(a0 + a) * ldM + j] : 0.0;
+// Y = M L^-T : one WARP per row of M (independent forward substitutions y = L^-1 m), blocked by 8 columns. L is staged
+// once per CTA in shared memory (the substitution is a serial chain: an L2 round trip per step would dominate); the eight
+// dot products against the solved part run as independent chains, one butterfly reduces them, then every lane solves
+// the 8x8 triangle redundantly with the reciprocal pivots written by the Cholesky kernel.
+#define TR_ROWS 8 // rows of M (warps) per CTA
+__global__ void __launch_bounds__(32 * TR_ROWS) k_ekf_trsm(const double *__restrict__ M, int ldM, const double *__restrict__ L, int ldL,
+                                                           const double *__restrict__ invdiag, int N, int r, double *__restrict__ Yout, int ldY,
+                                                           int L_in_smem) {
+  extern __shared__ __align__(16) double tsm[]; // [TR_ROWS][r] y rows, then r reciprocal pivots, then L (r x ldl) when it fits
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ldl = r | 1;
+  double *inv_s = tsm + (size_t)TR_ROWS * r;
+  double *Ls = inv_s + r;
+  for (int e = threadIdx.x; e < r; e += 32 * TR_ROWS)
+    inv_s[e] = invdiag[e];
+  if (L_in_smem) {
+    for (int e = threadIdx.x; e < r * r; e += 32 * TR_ROWS) {
+      const int i = e / r, j = e % r;
+      if (j <= i)
+        Ls[i * ldl + j] = L[(size_t)i * ldL + j];
+    }
   }
   __syncthreads();
-  for (int kb = 0; kb < r; kb += 16) {
-    int nbk = min(16, r - kb);
-    // y[a][kb+c] -= sum_{t<kb} y[a][t] L[kb+c][t]
-    for (int e = tid; e < 32 * nbk; e += 256) {
-      int c = e >> 5, a = e & 31; // lanes over rows a (y column access is conflict-free with odd ldy), warps over c
-      const double *Lr = L + (size_t)(kb + c) * ldL;
-      double acc = 0.0;
-      for (int t = 0; t < kb; t++)
-        acc += ysm[a * ldy + t] * Lr[t];
-      ysm[a * ldy + kb + c] -= acc;
+  const double *Lp = L_in_smem ? Ls : L;
+  const int lp = L_in_smem ? ldl : ldL;
+  const int a = blockIdx.x * TR_ROWS + wid;
+  if (a >= N)
+    return;
+  double *y = tsm + (size_t)wid * r;
+  for (int t = lane; t < r; t += 32)
+    y[t] = M[(size_t)a * ldM + t];
+  __syncwarp();
+  for (int kb = 0; kb < r; kb += 8) {
+    const int nbk = min(8, r - kb);
+    double s[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      s[c] = 0.0;
+    for (int t = lane; t < kb; t += 32) {
+      const double yt = y[t];
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        if (c < nbk)
+          s[c] += Lp[(size_t)(kb + c) * lp + t] * yt;
     }
-    __syncthreads();
-    if (tid < 32) {
-      int a = tid;
-      for (int c = 0; c < nbk; c++) {
-        const double *Lr = L + (size_t)(kb + c) * ldL;
-        double v = ysm[a * ldy + kb + c];
-        for (int t = 0; t < c; t++)
-          v -= ysm[a * ldy + kb + t] * Lr[kb + t];
-        ysm[a * ldy + kb + c] = v / Lr[kb + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+    }
+    double yn[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      if (c < nbk) {
+        const double *Lr = Lp + (size_t)(kb + c) * lp + kb;
+        // everything that does not depend on yn[c-1] first: the serial chain is one FMA + one multiply per column
+        double v = y[kb + c] - s[c];
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+          if (t + 1 < c)
+            v -= Lr[t] * yn[t];
+        if (c > 0)
+          v -= Lr[c - 1] * yn[c - 1];
+        yn[c] = v * inv_s[kb + c];
       }
     }
-    __syncthreads();
+    __syncwarp();
+    if (lane < nbk) {
+      double v = yn[0];
+#pragma unroll
+      for (int c = 1; c < 8; c++)
+        v = (lane == c) ? yn[c] : v;
+      y[kb + lane] = v;
+    }
+    __syncwarp();
   }
-  for (int e = tid; e < 32 * r; e += 256) {
-    int a = e / r, j = e % r;
-    if (a0 + a < N)
-      Yout[(size_t)(a0 + a) * ldY + j] = ysm[a * ldy + j];
-  }
+  for (int t = lane; t < r; t += 32)
+    Yout[(size_t)a * ldY + t] = y[t];
 }
 
 // P <- sym_U(P - Y Y'): upper tiles only, mirrored on write; negative-diagonal check; dx = Y w on the diagonal tiles' rows
@@ -239,9 +278,13 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
     attr_set = true;
   }
   // the residual vector is column n of H's row (TSQR output) or a separate buffer: callers stage it in d_w
-  k_ekf_chol<<<1, 1024, use_smem ? chol_bytes : 0, ctx->stream>>>(ctx->d_S, ld, r, ctx->d_w, ctx->d_w, ctx->d_info, use_smem);
-  size_t trsm_bytes = sizeof(double) * 32 * (size_t)(r | 1);
-  k_ekf_trsm<<<(N + 31) / 32, 256, trsm_bytes, ctx->stream>>>(ctx->d_M, ld, ctx->d_S, ld, N, r, ctx->d_Y, ld);
+  double *invdiag = ctx->d_w + ctx->cfg.max_state; // d_w holds 4 x max_state doubles: [w | 1/diag(L) | ...]
+  k_ekf_chol<<<1, 1024, use_smem ? chol_bytes : 0, ctx->stream>>>(ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
+  size_t trsm_small = sizeof(double) * ((size_t)TR_ROWS * r + r);
+  size_t trsm_full = trsm_small + sizeof(double) * (size_t)r * (size_t)(r | 1);
+  int L_in_smem = trsm_full <= 200 * 1024;
+  k_ekf_trsm<<<(N + TR_ROWS - 1) / TR_ROWS, 32 * TR_ROWS, L_in_smem ? trsm_full : trsm_small, ctx->stream>>>(ctx->d_M, ld, ctx->d_S, ld, invdiag, N,
+                                                                                                              r, ctx->d_Y, ld, L_in_smem);
   dim3 g2((N + EK_T - 1) / EK_T, (N + EK_T - 1) / EK_T);
   k_ekf_downdate<<<g2, 256, 0, ctx->stream>>>(P, ld, ctx->d_Y, ld, N, r, ctx->d_w, ctx->d_dx, ctx->d_info);
 }

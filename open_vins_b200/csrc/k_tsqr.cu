@@ -20,7 +20,6 @@
 #define QR_CT 32
 #define QR_THREADS QR_CR
 #define QR_WARPS (QR_THREADS / 32)
-#define QR_KG 4 // k-groups in the Y = V'A product
 #ifdef OVB_TSQR_TIMING
 #include <cstdio>
 #define TPROBE(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) tprobe[i] = clock64(); } while (0)
@@ -28,55 +27,26 @@
 #define TPROBE(i) do { } while (0)
 #endif
 
+#define QR_VPITCH 20 // pitch of Vs: conflict-free 8x4 / 4x8 double fragments (2*20 mod 32 = 8)
+#define QR_APITCH 36 // pitch of At / Ys / Zs (2*36 mod 32 = 8)
 struct QrSmem {
-  double Vs[QR_CR][QR_NB];            // reflectors (unit lower trapezoid)
-  double At[QR_CR][QR_CT];            // trailing tile
-  double Yp[QR_KG][QR_NB][QR_CT];     // partial V'A
-  double Zs[QR_NB][QR_CT];            // (T' V'A)
-  double wred[2][QR_WARPS][QR_NB];    // per-warp partial sums, double buffered
-  double fin[2][QR_NB];               // block totals
-  double rowk[2][QR_NB];              // pivot row broadcast
+  double Vs[QR_CR][QR_VPITCH];        // reflectors, unit lower trapezoid: V[r][j] at Vs[r][j ^ ((r >> 4) & 15)] (swizzled)
+  double At[QR_CR][QR_APITCH];        // trailing tile (also the panel staging buffer)
+  double Ys[QR_NB][QR_APITCH];        // V'A of the tile
+  double Zs[QR_NB][QR_APITCH];        // -(Tt Y): the update is At + V Zs
   double G[QR_NB][QR_NB];             // strict lower: v_k'v_i
-  double tau[QR_NB];
-  double vbuf[16 * 18];               // pivot column broadcast [row group][16 rows], pitch 18 against bank conflicts
-  double sc[4];                       // tau, 1/(alpha-beta) of the current step
   double Rb[QR_NB][QR_NB];            // finished R entries of this chunk
+  double Tt[QR_NB][QR_NB];            // reflector coupling (lower triangular): z = Tt y
+  double tau[QR_NB];
+  double vbuf[2][16 * 18];            // pivot column broadcast, double buffered by step parity, pitch 18
+  double sc[4];                       // [2 + parity]: pivot element alpha of the current step
   int rowidx[QR_CR];
 };
 
-// sum of 16 per-lane values over the warp with the halving butterfly: 16 double shuffles instead of 80.
-// On return lane L holds in `out` the warp total of value index j(L) = 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of L).
-__device__ __forceinline__ double warp_reduce16(const double x[QR_NB], int lane) {
-  double y8[8], y4[4], y2[2], y1;
-  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    double send = h16 ? x[i] : x[i + 8];
-    double keep = h16 ? x[i + 8] : x[i];
-    y8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    double send = h8 ? y8[i] : y8[i + 4];
-    double keep = h8 ? y8[i + 4] : y8[i];
-    y4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    double send = h4 ? y4[i] : y4[i + 2];
-    double keep = h4 ? y4[i + 2] : y4[i];
-    y2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    double send = h2 ? y2[0] : y2[1];
-    double keep = h2 ? y2[1] : y2[0];
-    y1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
-  return y1;
-}
-__device__ __forceinline__ int reduce16_index(int lane) {
-  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+// D(8x8) += A(8x4) B(4x8) on the FP64 tensor-core path (DMMA). Fragments: a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
+// d0/d1 = D[lane>>2][2*(lane&3) + {0,1}].
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 // One (panel, level) step. grid = (chunks, column-tile groups).
@@ -89,7 +59,6 @@ __global__ void __launch_bounds__(QR_THREADS)
   const int chunk = blockIdx.x;
 #ifdef OVB_TSQR_TIMING
   long long tprobe[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long tacc[5] = {0, 0, 0, 0, 0}, tlast = 0;
 #endif
   TPROBE(0);
   const int rows_i = min(QR_CR, len - chunk * QR_CR);
@@ -101,10 +70,9 @@ __global__ void __launch_bounds__(QR_THREADS)
     sm.rowidx[tid] = c0 + g;
   }
   // ---- panel factorisation. Ownership: thread (j = tid>>4, g = tid&15) holds rows 16g..16g+15 of panel column j in
-  // registers, so a half-warp owns one column and every column dot product v'a_j is 16 FMAs + a 4-level half-warp
-  // butterfly (the previous row-per-thread layout needed a 16-value block reduction per column: ~6x the instructions,
-  // all on one dependent chain). The 16 rows sit in a rotating window: after k rotations slot t holds local row
-  // (k + t) mod 16, hence the pivot row of step k is slot 0 of group g == k/16 and every register index is static.
+  // registers, so a half-warp owns one column and every column dot product is 16 FMAs + a 4-level half-warp butterfly.
+  // The 16 rows sit in a rotating window (after k rotations slot t holds local row (k + t) mod 16): the pivot row of
+  // step k is slot 0 of group 0 and every register index is static, so the loop stays rolled (one copy in the I-cache).
   double *Bp = &sm.At[0][0]; // staging [j][t][g], pitch 257: conflict-free both ways (aliases the tile buffer)
   {
     const int lj = tid & 15, rr = tid >> 4;
@@ -129,91 +97,84 @@ __global__ void __launch_bounds__(QR_THREADS)
   for (int t = 0; t < QR_NB; t++)
     a[t] = Bp[pj * 257 + t * 16 + pg];
   __syncthreads(); // Bp (== At) is free again
-  // Finished rows (row k of columns j >= k after step k) leave the register window: their value goes to sm.Rb and
-  // the slot is zeroed, so every later dot product and update runs unmasked over all 16 slots.
+  // Finished rows (row k of columns j >= k after step k) leave the register window: their value goes to sm.Rb and the
+  // slot is zeroed, so dot products and updates run unmasked. ONE barrier per step: the pivot column and the pivot
+  // element are broadcast through (double-buffered) shared memory; every thread then derives the reflector scalars
+  // itself (the column norm is reduced redundantly by every half-warp in the same butterfly as its own dot product).
 #pragma unroll 1
   for (int k = 0; k < nbp; k++) {
-#ifdef OVB_TSQR_TIMING
-    tlast = clock64();
-#define TSTEP(i) do { long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
-#else
-#define TSTEP(i) do { } while (0)
-#endif
-    // pivot row k lives in group 0, window slot 0 (k < 16)
+    const int par = k & 1;
     double pv = 0.0;
-    if (pg == 0 && pj >= k) {
+    if (pg == 0 && pj >= k) { // pivot row k lives in group 0, window slot 0
       pv = a[0];
       a[0] = 0.0;
     }
     if (pj == k) {
 #pragma unroll
       for (int t = 0; t < QR_NB; t++)
-        sm.vbuf[pg * 18 + t] = a[t];
+        sm.vbuf[par][pg * 18 + t] = a[t];
+      if (pg == 0)
+        sm.sc[2 + par] = pv;
     }
     __syncthreads();
-    TSTEP(0);
     double v[QR_NB];
 #pragma unroll
     for (int t = 0; t < QR_NB; t += 2) {
-      const double2 vv = *reinterpret_cast<const double2 *>(&sm.vbuf[pg * 18 + t]);
+      const double2 vv = *reinterpret_cast<const double2 *>(&sm.vbuf[par][pg * 18 + t]);
       v[t] = vv.x;
       v[t + 1] = vv.y;
     }
-    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    const double alpha = sm.sc[2 + par];
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int t = 0; t < QR_NB; t += 4) {
       d0 += v[t] * a[t];
       d1 += v[t + 1] * a[t + 1];
       d2 += v[t + 2] * a[t + 2];
       d3 += v[t + 3] * a[t + 3];
+      s0 += v[t] * v[t];
+      s1 += v[t + 1] * v[t + 1];
+      s2 += v[t + 2] * v[t + 2];
+      s3 += v[t + 3] * v[t + 3];
     }
-    double dot = (d0 + d1) + (d2 + d3);
+    double dot = (d0 + d1) + (d2 + d3), sigma = (s0 + s1) + (s2 + s3);
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1)
+    for (int o = 8; o > 0; o >>= 1) {
       dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      sigma += __shfl_xor_sync(0xffffffffu, sigma, o);
+    }
     // pivot-row entry of this thread's column (held by the g == 0 thread of the half-warp; for j < k it is V[k][j])
     const double akj = __shfl_sync(0xffffffffu, (pj >= k) ? pv : a[0], lane & 16);
-    TSTEP(1);
-    if (pj == k && pg == 0) {
-      const double alpha = akj, sigma = dot;
-      double tk = 0.0, scale = 0.0, beta = alpha;
-      if (sigma != 0.0) {
-        // |x|, 1/|x| and 1/(|alpha|+|x|) from float-seeded Newton iterations (2 steps: 23 -> 46 -> 92 bits). The library
-        // sqrt + two divisions cost ~1600 cycles in this single thread while the whole CTA waits at the barrier.
-        const double n2 = alpha * alpha + sigma;
-        const double aa = fabs(alpha);
-        double nrm, tkk, sc;
-        if (n2 > 1e-30 && n2 < 1e30) {
-          double y = (double)rsqrtf((float)n2);
-          y = y * (1.5 - 0.5 * n2 * y * y);
-          y = y * (1.5 - 0.5 * n2 * y * y);
-          nrm = n2 * y;
-          nrm = nrm + 0.5 * y * (n2 - nrm * nrm); // one Heron correction: nrm = sqrt(n2) to ~1 ulp
-          const double x = aa + nrm;
-          double rc = (double)(1.0f / (float)x);
-          rc = rc * (2.0 - x * rc);
-          rc = rc * (2.0 - x * rc);
-          rc = rc * (2.0 - x * rc);
-          sc = rc;
-          tkk = 1.0 + aa * y; // tau = (|alpha| + nrm)/nrm = 1 + |alpha|/nrm, with 1/nrm = y to working precision
-        } else { // out of float range: the slow exact path
-          nrm = sqrt(n2);
-          sc = 1.0 / (aa + nrm);
-          tkk = (aa + nrm) / nrm;
-        }
-        beta = (alpha >= 0.0) ? -nrm : nrm;
-        tk = tkk;                               // (beta - alpha)/beta = (|alpha| + nrm)/nrm
-        scale = (alpha >= 0.0) ? sc : -sc;      // 1/(alpha - beta) = sign(alpha)/(|alpha| + nrm)
+    // reflector scalars: beta = -sign(alpha) |x|, tau = (beta - alpha)/beta = 1 + |alpha|/|x|, scale = 1/(alpha - beta)
+    double tk = 0.0, scale = 0.0, beta = alpha;
+    if (sigma != 0.0) {
+      const double n2 = alpha * alpha + sigma;
+      const double aa = fabs(alpha);
+      double nrm, sc;
+      if (n2 > 1e-30 && n2 < 1e30) {
+        // No library sqrt/divide on the critical path (FP64 dependent latency is ~19 cycles per op). Float seeds
+        // (22 bits), then ONE third-order step each (22 -> 66 bits): y = 1/sqrt(n2), rc = 1/(|alpha| + |x|).
+        // The reciprocal's seed comes from the float estimate of |x| so that it overlaps the rsqrt refinement.
+        const float n2f = (float)n2;
+        const float yf = rsqrtf(n2f);
+        double rc = (double)(1.0f / ((float)aa + n2f * yf));
+        double y = (double)yf;
+        const double e = 1.0 - n2 * (y * y);
+        y = y + y * (e * (0.5 + 0.375 * e));
+        nrm = n2 * y;
+        const double x = aa + nrm;
+        const double f = 1.0 - x * rc;
+        rc = rc + rc * (f + f * f);
+        sc = rc + rc * (1.0 - x * rc); // one cheap Newton touch-up: the seed of rc saw only the float |x|
+        tk = 1.0 + aa * y;
+      } else {
+        nrm = sqrt(n2);
+        sc = 1.0 / (aa + nrm);
+        tk = (aa + nrm) / nrm;
       }
-      sm.sc[0] = tk;
-      sm.sc[1] = scale;
-      sm.tau[k] = tk;
-      sm.Rb[k][k] = beta;
+      beta = (alpha >= 0.0) ? -nrm : nrm;
+      scale = (alpha >= 0.0) ? sc : -sc;
     }
-    TSTEP(2);
-    __syncthreads();
-    TSTEP(3);
-    const double tk = sm.sc[0], scale = sm.sc[1];
     const double wj = akj + dot * scale; // v'a_j (for j < k: v_k'v_j)
     if (pj > k) {
       const double tw = tk * wj * scale;
@@ -226,6 +187,10 @@ __global__ void __launch_bounds__(QR_THREADS)
 #pragma unroll
       for (int t = 0; t < QR_NB; t++)
         a[t] = v[t] * scale;
+      if (pg == 0) {
+        sm.tau[k] = tk;
+        sm.Rb[k][k] = beta;
+      }
     } else if (pg == 0) {
       sm.G[k][pj] = wj;
     }
@@ -236,7 +201,6 @@ __global__ void __launch_bounds__(QR_THREADS)
         a[t] = a[t + 1];
       a[QR_NB - 1] = t0;
     }
-    TSTEP(4);
   }
 #pragma unroll 1
   for (int s2 = nbp; s2 < QR_NB; s2++) { // complete the cycle: slot t is local row t again
@@ -248,14 +212,14 @@ __global__ void __launch_bounds__(QR_THREADS)
   }
   __syncthreads();
   TPROBE(2);
-  // ---- publish V (unit lower trapezoid) and emit this chunk's R
+  // ---- publish V (unit lower trapezoid; column index swizzled by the row group: conflict-free) and emit this chunk's R
 #pragma unroll
   for (int t = 0; t < QR_NB; t++) {
     const int r = pg * 16 + t;
     double vv = 0.0;
     if (pj < nbp && r < rows_i)
       vv = (r > pj) ? a[t] : (r == pj ? 1.0 : 0.0);
-    sm.Vs[r][pj] = vv;
+    sm.Vs[r][pj ^ pg] = vv;
   }
   if (blockIdx.y == 0 && pg == 0) {
     // thread (j, g=0) emits column j of the chunk's R from sm.Rb (rows t <= j; zeros below the diagonal)
@@ -270,104 +234,127 @@ __global__ void __launch_bounds__(QR_THREADS)
       }
     }
   }
+  // ---- reflector coupling Tt (lower triangular 16x16): z = Tt y solves z_k = tau_k (y_k - sum_{i<k} G[k][i] z_i).
+  // Column c by thread c, in the same barrier interval as the publish/emit above.
+  if (tid < QR_NB) {
+    const int c = tid;
+    double x[QR_NB];
+#pragma unroll
+    for (int k = 0; k < QR_NB; k++) {
+      double val = 0.0;
+      if (k == c)
+        val = sm.tau[c];
+      else if (k > c && k < nbp) {
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < QR_NB; i += 2) {
+          if (i >= c && i < k)
+            acc0 += sm.G[k][i] * x[i];
+          if (i + 1 >= c && i + 1 < k)
+            acc1 += sm.G[k][i + 1] * x[i + 1];
+        }
+        val = -sm.tau[k] * (acc0 + acc1);
+      }
+      if (c >= nbp || k >= nbp)
+        val = 0.0;
+      x[k] = val;
+    }
+#pragma unroll
+    for (int k = 0; k < QR_NB; k++)
+      sm.Tt[k][c] = x[k];
+  }
   __syncthreads();
-  // ---- apply Q' to the trailing column tiles owned by this CTA
+  // ---- apply Q' to the trailing column tiles owned by this CTA: two small GEMMs on the FP64 tensor-core path
   TPROBE(3);
   const int tc0 = c0 + nbp;
   const int ntrail = nt - tc0;
   const int ntiles = (ntrail + QR_CT - 1) / QR_CT;
+  const int fr = lane >> 2, fk = lane & 3; // DMMA fragment coordinates
   for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
     const int col0 = tc0 + tile * QR_CT;
     const int ncol = min(QR_CT, nt - col0);
-    // load tile (warp per row, lanes over columns: coalesced 256 B rows); 8 independent loads in flight per lane
-    for (int rb = 0; rb < QR_CR; rb += 8 * QR_WARPS) {
-      double vals[8];
+    // load tile (warp per row, lanes over columns: coalesced 256 B rows); 16 independent loads in flight per lane
+    for (int rb = 0; rb < QR_CR; rb += 16 * QR_WARPS) {
+      double vals[16];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
+      for (int u = 0; u < 16; u++) {
         const int r = rb + u * QR_WARPS + wid;
         vals[u] = (r < rows_i && lane < ncol) ? A[(size_t)sm.rowidx[r] * ldA + col0 + lane] : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 8; u++)
+      for (int u = 0; u < 16; u++)
         sm.At[rb + u * QR_WARPS + wid][lane] = vals[u];
     }
     __syncthreads();
     if (tile == (int)blockIdx.y) TPROBE(4);
-    // Y = V'At : thread = (kgroup, 4 V-columns, 2 tile columns), 64 rows each
+    // Y = V'At (16 x 32, K = 256): warp w owns the 8x8 output tile (w>>2, w&3); 4 interleaved accumulator pairs
     {
-      const int kg = tid >> 6, within = tid & 63, ib = within >> 4, cb = within & 15;
-      double acc[4][2];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        acc[i][0] = acc[i][1] = 0.0;
-      const int r0 = kg * (QR_CR / QR_KG);
+      const int i0 = 8 * (wid >> 2), cc0 = 8 * (wid & 3);
+      double y0[4] = {0.0, 0.0, 0.0, 0.0}, y1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
-      for (int r = r0; r < r0 + QR_CR / QR_KG; r++) {
-        const double2 v01 = *reinterpret_cast<const double2 *>(&sm.Vs[r][4 * ib]);
-        const double2 v23 = *reinterpret_cast<const double2 *>(&sm.Vs[r][4 * ib + 2]);
-        const double2 at = *reinterpret_cast<const double2 *>(&sm.At[r][2 * cb]);
-        acc[0][0] += v01.x * at.x;
-        acc[0][1] += v01.x * at.y;
-        acc[1][0] += v01.y * at.x;
-        acc[1][1] += v01.y * at.y;
-        acc[2][0] += v23.x * at.x;
-        acc[2][1] += v23.x * at.y;
-        acc[3][0] += v23.y * at.x;
-        acc[3][1] += v23.y * at.y;
-      }
+      for (int r0 = 0; r0 < QR_CR; r0 += 16) {
+        const int sw = (r0 >> 4) & 15;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        sm.Yp[kg][4 * ib + i][2 * cb] = acc[i][0];
-        sm.Yp[kg][4 * ib + i][2 * cb + 1] = acc[i][1];
+        for (int q = 0; q < 4; q++) {
+          const int r = r0 + 4 * q + fk;
+          dmma884(y0[q], y1[q], sm.Vs[r][(i0 + fr) ^ sw], sm.At[r][cc0 + fr]);
+        }
       }
+      sm.Ys[i0 + fr][cc0 + 2 * fk] = (y0[0] + y0[1]) + (y0[2] + y0[3]);
+      sm.Ys[i0 + fr][cc0 + 2 * fk + 1] = (y1[0] + y1[1]) + (y1[2] + y1[3]);
     }
     __syncthreads();
     if (tile == (int)blockIdx.y) TPROBE(5);
-    // Z: sequential reflector coupling per column, z_k = tau_k (y_k - sum_{i<k} G[k][i] z_i)
-    if (tid < QR_CT) {
-      double z[QR_NB];
+    // Zs = -(Tt Y) (lower triangular 16x16 times 16x32): thread = (row k, 2 columns), two interleaved chains
+    {
+      const int k = tid >> 4, c2 = (tid & 15) * 2;
+      double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
 #pragma unroll
-      for (int k = 0; k < QR_NB; k++) {
-        double y = 0.0;
-        if (k < nbp) {
-#pragma unroll
-          for (int g = 0; g < QR_KG; g++)
-            y += sm.Yp[g][k][tid];
-#pragma unroll
-          for (int i = 0; i < QR_NB; i++)
-            if (i < k)
-              y -= sm.G[k][i] * z[i];
-          y *= sm.tau[k];
-        }
-        z[k] = y;
-        sm.Zs[k][tid] = y;
+      for (int i = 0; i < QR_NB; i += 2) {
+        const double t0 = (i <= k) ? sm.Tt[k][i] : 0.0, t1 = (i + 1 <= k) ? sm.Tt[k][i + 1] : 0.0;
+        z0 += t0 * sm.Ys[i][c2];
+        z1 += t0 * sm.Ys[i][c2 + 1];
+        z2 += t1 * sm.Ys[i + 1][c2];
+        z3 += t1 * sm.Ys[i + 1][c2 + 1];
       }
+      sm.Zs[k][c2] = -(z0 + z2);
+      sm.Zs[k][c2 + 1] = -(z1 + z3);
     }
     __syncthreads();
     if (tile == (int)blockIdx.y) TPROBE(6);
-    // At -= V Z : lanes over columns (Z column in registers), warps over rows; then store back
+    // At + V Zs (256 x 32, K = 16): warp w owns row tiles w, w+8, w+16, w+24 (8 rows each) x 4 column tiles
     {
-      double z[QR_NB];
 #pragma unroll
-      for (int k = 0; k < QR_NB; k++)
-        z[k] = sm.Zs[k][lane];
-      for (int r0 = wid; r0 < rows_i; r0 += 4 * QR_WARPS) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int rq = 0; rq < 4; rq++) {
+        const int r0 = 8 * (wid + 8 * rq);
+        const int sw = (r0 >> 4) & 15;
+        const int r = r0 + fr;
+        double va[4];
 #pragma unroll
-        for (int k = 0; k < QR_NB; k += 2) {
+        for (int kq = 0; kq < 4; kq++)
+          va[kq] = sm.Vs[r][(4 * kq + fk) ^ sw];
+        double c[4][2];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int r = min(r0 + u * QR_WARPS, QR_CR - 1);
-            const double2 v = *reinterpret_cast<const double2 *>(&sm.Vs[r][k]);
-            acc[u] += v.x * z[k];
-            acc[u] += v.y * z[k + 1];
-          }
+        for (int ct = 0; ct < 4; ct++) {
+          const double2 cc = *reinterpret_cast<const double2 *>(&sm.At[r][8 * ct + 2 * fk]);
+          c[ct][0] = cc.x;
+          c[ct][1] = cc.y;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int r = r0 + u * QR_WARPS;
-          if (r < rows_i && lane < ncol)
-            A[(size_t)sm.rowidx[r] * ldA + col0 + lane] = sm.At[r][lane] - acc[u];
+        for (int kq = 0; kq < 4; kq++)
+#pragma unroll
+          for (int ct = 0; ct < 4; ct++)
+            dmma884(c[ct][0], c[ct][1], va[kq], sm.Zs[4 * kq + fk][8 * ct + fr]);
+        if (r < rows_i) {
+          double *dst = A + (size_t)sm.rowidx[r] * ldA + col0;
+#pragma unroll
+          for (int ct = 0; ct < 4; ct++) {
+            const int cj = 8 * ct + 2 * fk;
+            if (cj < ncol)
+              dst[cj] = c[ct][0];
+            if (cj + 1 < ncol)
+              dst[cj + 1] = c[ct][1];
+          }
         }
       }
     }
@@ -376,11 +363,9 @@ __global__ void __launch_bounds__(QR_THREADS)
   TPROBE(7);
 #ifdef OVB_TSQR_TIMING
   if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
-    printf("tsqr c0=%d lvl=%d grid=(%d,%d) rows=%d | load %lld qr %lld publish %lld tileload %lld Y %lld Z %lld upd+rest %lld | total %lld\n", c0, level,
-           gridDim.x, gridDim.y, rows_i, tprobe[1] - tprobe[0], tprobe[2] - tprobe[1], tprobe[3] - tprobe[2], tprobe[4] - tprobe[3], tprobe[5] - tprobe[4],
-           tprobe[6] - tprobe[5], tprobe[7] - tprobe[6], tprobe[7] - tprobe[0]);
-  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && c0 == 0)
-    printf("   qr steps: syncA %lld dot+shfl %lld scalar %lld syncB %lld update+rot %lld\n", tacc[0], tacc[1], tacc[2], tacc[3], tacc[4]);
+    printf("tsqr c0=%d lvl=%d grid=(%d,%d) rows=%d | load %lld qr %lld publish+Tt %lld tileload %lld Y %lld Z %lld upd+rest %lld | total %lld\n", c0,
+           level, gridDim.x, gridDim.y, rows_i, tprobe[1] - tprobe[0], tprobe[2] - tprobe[1], tprobe[3] - tprobe[2], tprobe[4] - tprobe[3],
+           tprobe[5] - tprobe[4], tprobe[6] - tprobe[5], tprobe[7] - tprobe[6], tprobe[7] - tprobe[0]);
 #endif
 }
 
@@ -427,14 +412,13 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
       int chunks = (len + QR_CR - 1) / QR_CR;
       int last = (chunks == 1);
       // few chunks: spread the trailing tiles over more CTAs; many chunks: one CTA walks all tiles (no redundant panels)
-      int gy = 1;
-      if (chunks < 2 * ctx->sm_count) {
-        gy = (2 * ctx->sm_count + chunks - 1) / chunks;
-        if (gy > ntiles)
-          gy = ntiles;
-        if (gy < 1)
-          gy = 1;
-      }
+      // one CTA per SM (128 KB of shared memory): fill the SMs in ONE wave; every column group of a chunk repeats the
+      // panel factorisation, so never use more groups than that
+      int gy = ctx->sm_count / chunks;
+      if (gy > ntiles)
+        gy = ntiles;
+      if (gy < 1)
+        gy = 1;
       dim3 grid(chunks, gy);
       k_tsqr_level<<<grid, QR_THREADS, sizeof(QrSmem), ctx->stream>>>(A, ldA, nt, c0, nbp, level, len, level > 0 ? ctx->d_W[(level - 1) & 1] : nullptr,
                                                                        ctx->d_W[level & 1], Rout, ldR, last);

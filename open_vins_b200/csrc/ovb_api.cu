@@ -52,6 +52,7 @@ void ovb_opts_default(ovb_opts *o) {
   o->do_calib_camera_pose = 0;
   o->do_calib_camera_intrinsics = 0;
   o->col_order = OVB_COLS_CANONICAL;
+  o->compress = OVB_COMPRESS_HOUSEHOLDER_TSQR;
 }
 
 const char *ovb_last_error(const ovb_ctx *ctx) { return ctx ? ctx->err : "null context"; }
@@ -163,7 +164,7 @@ void ovb_destroy(ovb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
   void *dev[] = {ctx->P[0],   ctx->P[1], ctx->d_arena, ctx->d_cc, ctx->d_feat_order, ctx->d_info, ctx->d_chi2_table, ctx->d_Hs, ctx->d_W[0],
                  ctx->d_W[1], ctx->d_R,  ctx->d_R2,    ctx->d_M,  ctx->d_S,          ctx->d_Y,    ctx->d_w,          ctx->d_dx, ctx->d_scratch,
-                 ctx->d_dump, ctx->P_snap, ctx->d_flush};
+                 ctx->d_dump, ctx->P_snap, ctx->d_flush, ctx->d_Gpart, ctx->d_G};
   for (void *p : dev)
     if (p)
       cudaFree(p);
@@ -647,7 +648,10 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
   const int ldR = ldH;
   const double *Rfinal = ctx->d_R;
   if (m_total > 0) {
-    launch_tsqr(ctx, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
+    if (ctx->h_opts->o.compress == OVB_COMPRESS_NORMAL_EQUATIONS)
+      launch_compress_gram(ctx, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
+    else
+      launch_tsqr(ctx, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
     if (col_order == OVB_COLS_REFERENCE_FIRST_SEEN) {
       launch_reorder_R(ctx, ctx->d_R, n_all, ldR, ctx->d_R2, ldR);
       Rfinal = ctx->d_R2;
@@ -655,7 +659,8 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
   }
   if (ev)
     cudaEventRecord(ev[4], ctx->stream);
-  const int r = std::min(m_total, n_all);
+  // the Householder path leaves min(m, n) non-zero rows; the Cholesky factor of the Gram matrix is always n x n
+  const int r = (ctx->h_opts->o.compress == OVB_COMPRESS_NORMAL_EQUATIONS && m_total > 0) ? n_all : std::min(m_total, n_all);
   if (r > 0) {
     k_take_z<<<(r + 127) / 128, 128, 0, ctx->stream>>>(Rfinal, ldR, r, n_all, ctx->d_w);
     launch_ekf_update(ctx, Rfinal, ldR, r, n_all, false, ctx->h_opts->sigma_pix_sq, nullptr);
@@ -986,6 +991,30 @@ ovb_status ovb_compress(ovb_ctx *ctx, const double *H, int m, int n, const doubl
   if (st != OVB_OK)
     return st;
   launch_tsqr(ctx, ctx->d_Hs, m, n, ld, ctx->d_R, ld);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  double *hs = ctx->h_stage;
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(hs, ctx->d_R, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < n; j++)
+      R_out[(size_t)i * n + j] = hs[(size_t)i * ld + j];
+    z_out[i] = hs[(size_t)i * ld + n];
+  }
+  return OVB_OK;
+}
+
+ovb_status ovb_compress_gram(ovb_ctx *ctx, const double *H, int m, int n, const double *res, double *R_out, double *z_out) {
+  if (!ctx || !H || !res || !R_out || !z_out || m < 1 || n < 1)
+    return OVB_ERR_ARG;
+  if (n > ctx->cfg.max_state)
+    return OVB_ERR_CAPACITY;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  int ld;
+  ovb_status st = stage_dense(ctx, H, m, n, res, nullptr, &ld);
+  if (st != OVB_OK)
+    return st;
+  if (launch_compress_gram(ctx, ctx->d_Hs, m, n, ld, ctx->d_R, ld) < 0)
+    return OVB_ERR_CUDA;
   OVB_CUDA_CHECK(ctx, cudaGetLastError());
   double *hs = ctx->h_stage;
   OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(hs, ctx->d_R, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToHost, ctx->stream));

@@ -138,6 +138,9 @@ struct ovb_ctx {
   void *d_flush;
   // bookkeeping for bench.py: kernels launched by the last update pipeline, bytes moved by the last ovb_msckf_update
   int n_launch, n_launch_tsqr_level;
+  // normal-equations compression (k_gram.cu)
+  double *d_Gpart, *d_G;
+  size_t Gpart_cap, G_cap;
   size_t last_h2d_bytes, last_d2h_bytes;
 };
 
@@ -160,6 +163,8 @@ void launch_column_map(ovb_ctx *ctx, int n_feats, BlobView bv);
 // TSQR of A [m x (n+1)] (last column = residual) in place; R (n x (n+1), diag>=0) to Rout with leading dimension ldR
 void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR);
 // gather columns of Rin in the order info->col_canon (n_used of them) into Hs scratch and re-triangularise into Rout
+// [R | z] <- chol([H r]'[H r]) (k_gram.cu); returns the number of kernels launched or -1
+int launch_compress_gram(ovb_ctx *ctx, const double *A, int m, int n, int ldA, double *Rout, int ldR);
 void launch_reorder_R(ovb_ctx *ctx, const double *Rin, int n_all, int ldRin, double *Rout, int ldRout);
 // EKF update from an upper-trapezoidal / dense H [r x n] with column->state map in d_info (device-side sizes)
 void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r_max, int n_max, bool sizes_from_info, double sigma2,
