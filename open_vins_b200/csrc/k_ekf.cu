@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(1024) k_ekf_chol(double *__restrict__ S, int l
                                                    double *__restrict__ invdiag, DevUpdateInfo *__restrict__ info, int use_smem) {
   extern __shared__ __align__(16) double chol_sm[];
   __shared__ int flag;
-  __shared__ double invd_sh[8];
+  __shared__ double invd_sh[16];
   const int tid = threadIdx.x;
   if (tid == 0)
     flag = 0;

@@ -22,42 +22,27 @@
 #define FT_THREADS 256
 #define FT_WARPS (FT_THREADS / 32)
 
-struct MeasJ {
-  double Hf[6];  // [2][3]
-  double B0[12]; // clone            [2][6]
-  double B1[12]; // extrinsics       [2][6]
-  double B2[16]; // intrinsics       [2][8]
-  double B3[12]; // anchor clone     [2][6]  (only when its slot differs from the measurement's clone)
-  double B4[12]; // anchor extrinsic [2][6]  (only when its slot differs from the measurement's camera)
-  double res[2];
-  int slot[5]; // slot id per block or -1
-  int pad;
+// Per-measurement Jacobian blocks live in shared memory as structure-of-arrays:
+//   Bsh[I][b][16]  blocks [2][8] (row stride 8): 0 clone(6) 1 extrinsics(6) 2 intrinsics(8) 3 anchor clone(6) 4 anchor extrinsics(6);
+//                  blocks 3/4 exist only for the anchored representations (nblk = 5, else 3)
+//   Hfs[I][6], ress[I][2], mslot[I][8] (slot id per block or -1; blocks 3/4 only when their slot differs from blocks 0/1)
+//   lut[I][lutw]   slot -> block index (255 = the measurement does not touch the slot)
+struct MeasView {
+  double *B;
+  double *Hf;
+  double *res;
+  signed char *slot;
+  unsigned char *lut;
+  int nblk, lutw;
+  __device__ __forceinline__ double *blk(int I, int b) const { return B + ((size_t)I * nblk + b) * 16; }
+  // value of Jacobian row (I, r) in column k of slot s (0 when the measurement does not touch the slot)
+  __device__ __forceinline__ double x_at(int I, int r, int s, int k) const {
+    const int b = lut[(size_t)I * lutw + s];
+    return (b == 255) ? 0.0 : B[((size_t)I * nblk + b) * 16 + 8 * r + k];
+  }
 };
 
-__device__ __forceinline__ const double *blk_ptr(const MeasJ &m, int b) {
-  switch (b) {
-  case 0:
-    return m.B0;
-  case 1:
-    return m.B1;
-  case 2:
-    return m.B2;
-  case 3:
-    return m.B3;
-  default:
-    return m.B4;
-  }
-}
 __device__ __forceinline__ int blk_w(int b) { return b == 2 ? 8 : 6; }
-
-// value of Jacobian row (I, r) in column k of slot s (0 when the measurement does not touch the slot)
-__device__ __forceinline__ double x_at(const MeasJ &m, int r, int s, int k) {
-#pragma unroll
-  for (int b = 0; b < 5; b++)
-    if (m.slot[b] == s)
-      return blk_ptr(m, b)[r * blk_w(b) + k];
-  return 0.0;
-}
 
 // block-wide sum of three values; every thread gets the result. red: FT_WARPS*3 doubles of shared memory.
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double *red) {
@@ -212,20 +197,28 @@ __device__ __forceinline__ bool rep_is_relative(int rep) {
 
 // =====================================================================================================================
 // mode 0: full (gate + write projected rows to Hs)   mode 1: dump pre-nullspace dense rows to `dump`
-__global__ void __launch_bounds__(FT_THREADS)
+__global__ void __launch_bounds__(FT_THREADS, 2)
     k_feature_system(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, DevFeat *__restrict__ feats, int n_feats, BlobView bv,
                      const double *__restrict__ P, int ldP, const double *__restrict__ chi2_table, double *__restrict__ Hs, int ldH,
-                     unsigned char *__restrict__ feat_order, int mode, int maxM, double *__restrict__ scratch, size_t scratch_per_cta,
-                     double *__restrict__ dump, int ld_dump, int dump_rows) {
+                     unsigned char *__restrict__ feat_order, int mode, int maxM, int nblk, double *__restrict__ scratch,
+                     size_t scratch_per_cta, double *__restrict__ dump, int ld_dump, int dump_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ovb_opts &op = dop->o;
   const int n_all = fr->n_all;
   const int n_slots = fr->n_slots;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // ---- shared memory carve-up
+  const int n_all8 = (n_all + 7) & ~7;
+  // ---- shared memory carve-up (mirrors feature_smem_bytes)
   size_t o = 0;
-  MeasJ *mj = (MeasJ *)(smem_raw + o);
-  o += sizeof(MeasJ) * (size_t)maxM;
+  MeasView mv;
+  mv.nblk = nblk;
+  mv.lutw = (n_slots + 3) & ~3;
+  mv.B = (double *)(smem_raw + o);
+  o += sizeof(double) * 16 * (size_t)nblk * maxM;
+  mv.Hf = (double *)(smem_raw + o);
+  o += sizeof(double) * 6 * (size_t)maxM;
+  mv.res = (double *)(smem_raw + o);
+  o += sizeof(double) * 2 * (size_t)maxM;
   double *V = (double *)(smem_raw + o); // [2M][3]
   o += sizeof(double) * 3 * 2 * (size_t)maxM;
   double *Z = (double *)(smem_raw + o); // [3][n_all+1]
@@ -233,17 +226,44 @@ __global__ void __launch_bounds__(FT_THREADS)
   double *Tw = (double *)(smem_raw + o); // [FT_WARPS][2][n_all]
   o += sizeof(double) * FT_WARPS * 2 * (size_t)n_all;
   double *red = (double *)(smem_raw + o);
-  o += sizeof(double) * (FT_WARPS * 3 + 16);
-  short *lcol_slot = (short *)(smem_raw + o); // [n_all] slot of compact column c
-  o += sizeof(short) * (size_t)((n_all + 7) & ~7);
-  short *lcol_k = (short *)(smem_raw + o);
-  o += sizeof(short) * (size_t)((n_all + 7) & ~7);
+  o += sizeof(double) * (FT_WARPS * 3 + 24);
   int *slot2l = (int *)(smem_raw + o); // [OVB_MAX_VARS] compact column start of a slot or -1
+  o += sizeof(int) * OVB_MAX_VARS;
+  int *fslot_off = (int *)(smem_raw + o); // frame tables, staged once per CTA
   o += sizeof(int) * OVB_MAX_VARS;
   int *ishare = (int *)(smem_raw + o); // misc ints: [0]=wf [1]=flag [2]=gated
   o += sizeof(int) * 8;
+  short *lcol_slot = (short *)(smem_raw + o); // [n_all] slot of compact column c
+  o += sizeof(short) * (size_t)n_all8;
+  short *lcol_k = (short *)(smem_raw + o);
+  o += sizeof(short) * (size_t)n_all8;
+  unsigned char *ccol_slot = smem_raw + o; // [n_all] slot / offset-in-slot of canonical column j
+  o += (size_t)n_all8;
+  unsigned char *ccol_k = smem_raw + o;
+  o += (size_t)n_all8;
+  unsigned char *fslot_size = smem_raw + o;
+  o += OVB_MAX_VARS;
+  mv.slot = (signed char *)(smem_raw + o); // [maxM][8]
+  o += (size_t)maxM * 8;
+  unsigned char *mcam = smem_raw + o; // [maxM] camera id / clone slot of each measurement
+  o += (size_t)((maxM + 7) & ~7);
+  unsigned char *mcs = smem_raw + o;
+  o += (size_t)((maxM + 7) & ~7);
+  mv.lut = smem_raw + o;
+  o += (size_t)maxM * mv.lutw;
   o = (o + 15) & ~(size_t)15;
   double *S_sh = (double *)(smem_raw + o); // [(2M+1)][ldS] when it fits, else per-CTA global scratch
+
+  // ---- frame tables -> shared memory (the bookkeeping below would otherwise chase them through L2 serially)
+  for (int s = tid; s < n_slots; s += FT_THREADS) {
+    fslot_off[s] = fr->slot_off[s];
+    fslot_size[s] = (unsigned char)fr->slot_size[s];
+    const int c0 = fr->slot_col[s], w = fr->slot_size[s];
+    for (int k = 0; k < w; k++) {
+      ccol_slot[c0 + k] = (unsigned char)s;
+      ccol_k[c0 + k] = (unsigned char)k;
+    }
+  }
 
   for (int f = blockIdx.x; f < n_feats; f += gridDim.x) {
     DevFeat *F = &feats[f];
@@ -294,8 +314,18 @@ __global__ void __launch_bounds__(FT_THREADS)
     }
     const dv3 p_FinG_fej = p_FinG; // MSCKF features: p_FinG_fej = p_FinG (UpdaterMSCKF.cpp:190-193, UpdaterHelper.cpp:284-287)
 
-    // ---- thread 0: slot bookkeeping (Hx_order in the reference's first-seen order + compact column map)
-    if (tid == 0) {
+    for (int e = tid; e < M * mv.lutw; e += FT_THREADS)
+      mv.lut[e] = 255;
+    // measurement metadata -> shared memory, one coalesced pass
+    for (int i = tid; i < M; i += FT_THREADS) {
+      mcam[i] = bv.cam[m0 + i];
+      mcs[i] = (unsigned char)fr->clone_slot[bv.clone[m0 + i]];
+    }
+    __syncthreads();
+    // ---- one thread of the last warp (it computes no Jacobian unless M is huge): slot bookkeeping
+    //      (Hx_order in the reference's first-seen order + compact column map)
+    const int bk_tid = (M <= FT_THREADS - 32) ? FT_THREADS - 32 : 0;
+    if (tid == bk_tid) {
       unsigned long long seen = 0ull;
       unsigned char *ord = feat_order ? feat_order + (size_t)f * (OVB_MAX_VARS + 1) : nullptr;
       int no = 0;
@@ -320,9 +350,9 @@ __global__ void __launch_bounds__(FT_THREADS)
           }
         }
         for (int i = 0; i < M; i++) {
-          if (bv.cam[m0 + i] != key)
+          if (mcam[i] != key)
             continue;
-          int s = fr->clone_slot[bv.clone[m0 + i]];
+          int s = mcs[i];
           if (!((seen >> s) & 1ull)) {
             seen |= 1ull << s;
             if (ord)
@@ -352,11 +382,12 @@ __global__ void __launch_bounds__(FT_THREADS)
       for (int s = 0; s < n_slots; s++) {
         if ((seen >> s) & 1ull) {
           slot2l[s] = wf;
-          for (int k = 0; k < fr->slot_size[s]; k++) {
+          const int w = fslot_size[s];
+          for (int k = 0; k < w; k++) {
             lcol_slot[wf + k] = (short)s;
             lcol_k[wf + k] = (short)k;
           }
-          wf += fr->slot_size[s];
+          wf += w;
         } else
           slot2l[s] = -1;
       }
@@ -368,8 +399,10 @@ __global__ void __launch_bounds__(FT_THREADS)
     // ---- per-measurement Jacobian (UpdaterHelper.cpp:313-423), one thread per measurement
     if (tid < M) {
       const int i = m0 + tid;
-      const int cam = bv.cam[i], cl = bv.clone[i];
-      MeasJ &m = mj[tid];
+      const int cam = mcam[tid], cl = bv.clone[i];
+      double *B0 = mv.blk(tid, 0), *B1 = mv.blk(tid, 1), *B2 = mv.blk(tid, 2);
+      double *mHf = mv.Hf + 6 * tid;
+      signed char *msl = mv.slot + 8 * tid;
       dm3 R_ItoC = ld_m3(fr->cam_R[cam]);
       dv3 p_IinC = ld_v3(fr->cam_p[cam]);
       dm3 R_GtoIi = ld_m3(fr->clone_R[cl]);
@@ -379,8 +412,8 @@ __global__ void __launch_bounds__(FT_THREADS)
       double un = p_FinCi.x / p_FinCi.z, vn = p_FinCi.y / p_FinCi.z;
       double ud, vd;
       cam_distort_d(fr->cam_model[cam], fr->cam_intr[cam], un, vn, ud, vd);
-      m.res[0] = (double)bv.uv[2 * i] - ud;
-      m.res[1] = (double)bv.uv[2 * i + 1] - vd;
+      mv.res[2 * tid] = (double)bv.uv[2 * i] - ud;
+      mv.res[2 * tid + 1] = (double)bv.uv[2 * i + 1] - vd;
       if (op.do_fej) {
         R_GtoIi = ld_m3(fr->clone_R_fej[cl]);
         p_IiinG = ld_v3(fr->clone_p_fej[cl]);
@@ -410,26 +443,28 @@ __global__ void __launch_bounds__(FT_THREADS)
       for (int r = 0; r < 2; r++)
 #pragma unroll
         for (int k = 0; k < 3; k++)
-          m.Hf[3 * r + k] = (dz_dpfg[r][0] * L[k] + dz_dpfg[r][1] * L[3 + k]) + dz_dpfg[r][2] * L[6 + k];
+          mHf[3 * r + k] = (dz_dpfg[r][0] * L[k] + dz_dpfg[r][1] * L[3 + k]) + dz_dpfg[r][2] * L[6 + k];
       // clone block: dz_dpfc * [R_ItoC skew(p_FinIi), -R_ItoC R_GtoIi]
 #pragma unroll
       for (int r = 0; r < 2; r++)
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          m.B0[6 * r + k] = (dz_dpfc[r][0] * dpfc_dth.m[k] + dz_dpfc[r][1] * dpfc_dth.m[3 + k]) + dz_dpfc[r][2] * dpfc_dth.m[6 + k];
-          m.B0[6 * r + 3 + k] =
+          B0[8 * r + k] = (dz_dpfc[r][0] * dpfc_dth.m[k] + dz_dpfc[r][1] * dpfc_dth.m[3 + k]) + dz_dpfc[r][2] * dpfc_dth.m[6 + k];
+          B0[8 * r + 3 + k] =
               (dz_dpfc[r][0] * (-dpfc_dpfg.m[k]) + dz_dpfc[r][1] * (-dpfc_dpfg.m[3 + k])) + dz_dpfc[r][2] * (-dpfc_dpfg.m[6 + k]);
         }
-      m.slot[0] = fr->clone_slot[cl];
-      m.slot[1] = op.do_calib_camera_pose ? fr->cam_ext_slot[cam] : -1;
-      m.slot[2] = op.do_calib_camera_intrinsics ? fr->cam_intr_slot[cam] : -1;
-      m.slot[3] = -1;
-      m.slot[4] = -1;
+      int sl[5];
+      sl[0] = mcs[tid];
+      sl[1] = op.do_calib_camera_pose ? fr->cam_ext_slot[cam] : -1;
+      sl[2] = op.do_calib_camera_intrinsics ? fr->cam_intr_slot[cam] : -1;
+      sl[3] = -1;
+      sl[4] = -1;
 #pragma unroll
-      for (int k = 0; k < 12; k++)
-        m.B1[k] = 0.0;
+      for (int k = 0; k < 16; k++)
+        B1[k] = 0.0;
       // anchored extras: H(anchor clone) += dz_dpfg*H_anc ; H(anchor ext) += dz_dpfg*H_calib (:396-398)
       if (relative) {
+        double *B3 = mv.blk(tid, 3), *B4 = mv.blk(tid, 4);
         double Ea[12], Ec[12];
 #pragma unroll
         for (int r = 0; r < 2; r++)
@@ -438,26 +473,34 @@ __global__ void __launch_bounds__(FT_THREADS)
             Ea[6 * r + k] = (dz_dpfg[r][0] * Hanc[k] + dz_dpfg[r][1] * Hanc[6 + k]) + dz_dpfg[r][2] * Hanc[12 + k];
             Ec[6 * r + k] = (dz_dpfg[r][0] * Hcal[k] + dz_dpfg[r][1] * Hcal[6 + k]) + dz_dpfg[r][2] * Hcal[12 + k];
           }
-        if (s_anchor == m.slot[0]) {
+        if (s_anchor == sl[0]) {
 #pragma unroll
-          for (int k = 0; k < 12; k++)
-            m.B0[k] += Ea[k];
+          for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              B0[8 * r + k] += Ea[6 * r + k];
         } else {
-          m.slot[3] = s_anchor;
+          sl[3] = s_anchor;
 #pragma unroll
-          for (int k = 0; k < 12; k++)
-            m.B3[k] = Ea[k];
+          for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              B3[8 * r + k] = Ea[6 * r + k];
         }
         if (s_anchor_ext >= 0) {
-          if (s_anchor_ext == m.slot[1]) {
+          if (s_anchor_ext == sl[1]) {
 #pragma unroll
-            for (int k = 0; k < 12; k++)
-              m.B1[k] += Ec[k];
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+              for (int k = 0; k < 6; k++)
+                B1[8 * r + k] += Ec[6 * r + k];
           } else {
-            m.slot[4] = s_anchor_ext;
+            sl[4] = s_anchor_ext;
 #pragma unroll
-            for (int k = 0; k < 12; k++)
-              m.B4[k] = Ec[k];
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+              for (int k = 0; k < 6; k++)
+                B4[8 * r + k] = Ec[6 * r + k];
           }
         }
       }
@@ -468,14 +511,20 @@ __global__ void __launch_bounds__(FT_THREADS)
         for (int r = 0; r < 2; r++)
 #pragma unroll
           for (int k = 0; k < 3; k++) {
-            m.B1[6 * r + k] += (dz_dpfc[r][0] * sk.m[k] + dz_dpfc[r][1] * sk.m[3 + k]) + dz_dpfc[r][2] * sk.m[6 + k];
-            m.B1[6 * r + 3 + k] += (dz_dpfc[r][0] * (k == 0 ? 1.0 : 0.0) + dz_dpfc[r][1] * (k == 1 ? 1.0 : 0.0)) + dz_dpfc[r][2] * (k == 2 ? 1.0 : 0.0);
+            B1[8 * r + k] += (dz_dpfc[r][0] * sk.m[k] + dz_dpfc[r][1] * sk.m[3 + k]) + dz_dpfc[r][2] * sk.m[6 + k];
+            B1[8 * r + 3 + k] += (dz_dpfc[r][0] * (k == 0 ? 1.0 : 0.0) + dz_dpfc[r][1] * (k == 1 ? 1.0 : 0.0)) + dz_dpfc[r][2] * (k == 2 ? 1.0 : 0.0);
           }
       }
       if (op.do_calib_camera_intrinsics) {
 #pragma unroll
         for (int k = 0; k < 16; k++)
-          m.B2[k] = dz_dzeta[k];
+          B2[k] = dz_dzeta[k];
+      }
+#pragma unroll
+      for (int b = 0; b < 5; b++) {
+        msl[b] = (signed char)sl[b];
+        if (sl[b] >= 0)
+          mv.lut[(size_t)tid * mv.lutw + sl[b]] = (unsigned char)b;
       }
     }
     __syncthreads();
@@ -486,18 +535,13 @@ __global__ void __launch_bounds__(FT_THREADS)
       for (int e = tid; e < rows * (n_all + 4); e += FT_THREADS) {
         int i = e / (n_all + 4), j = e % (n_all + 4);
         size_t grow = (size_t)(2 * m0 + i);
-        const MeasJ &m = mj[i >> 1];
         int r = i & 1;
-        if (j < n_all) {
-          // canonical column j -> (slot, k)
-          int s = 0;
-          while (s + 1 < n_slots && fr->slot_col[s + 1] <= j)
-            s++;
-          dHx[grow * ld_dump + j] = x_at(m, r, s, j - fr->slot_col[s]);
-        } else if (j < n_all + 3)
-          dHf[grow * 3 + (j - n_all)] = m.Hf[3 * r + (j - n_all)];
+        if (j < n_all)
+          dHx[grow * ld_dump + j] = mv.x_at(i >> 1, r, ccol_slot[j], ccol_k[j]);
+        else if (j < n_all + 3)
+          dHf[grow * 3 + (j - n_all)] = mv.Hf[6 * (i >> 1) + 3 * r + (j - n_all)];
         else
-          dres[grow] = m.res[r];
+          dres[grow] = mv.res[i];
       }
       continue;
     }
@@ -505,11 +549,9 @@ __global__ void __launch_bounds__(FT_THREADS)
     // ---- Householder QR of H_f (rows x 3): V (unit lower trapezoid) and tau; one thread per row
     double a[3] = {0, 0, 0};
     if (tid < rows) {
-      const MeasJ &m = mj[tid >> 1];
-      int r = tid & 1;
-      a[0] = m.Hf[3 * r];
-      a[1] = m.Hf[3 * r + 1];
-      a[2] = m.Hf[3 * r + 2];
+      a[0] = mv.Hf[3 * tid];
+      a[1] = mv.Hf[3 * tid + 1];
+      a[2] = mv.Hf[3 * tid + 2];
     }
     double tau[3];
     double *rowk = red + FT_WARPS * 3; // 3 doubles: the pivot row's values
@@ -572,14 +614,14 @@ __global__ void __launch_bounds__(FT_THREADS)
     for (int j = tid; j <= n_all; j += FT_THREADS) {
       double w0 = 0, w1 = 0, w2 = 0;
       if (j < n_all) {
-        int s = 0;
-        while (s + 1 < n_slots && fr->slot_col[s + 1] <= j)
-          s++;
-        int kk = j - fr->slot_col[s];
+        const int s = ccol_slot[j], kk = ccol_k[j];
         if (slot2l[s] >= 0) {
           for (int I = 0; I < M; I++) {
-            const MeasJ &m = mj[I];
-            double x0 = x_at(m, 0, s, kk), x1 = x_at(m, 1, s, kk);
+            const int b = mv.lut[(size_t)I * mv.lutw + s];
+            if (b == 255)
+              continue;
+            const double *Bb = mv.blk(I, b);
+            double x0 = Bb[kk], x1 = Bb[8 + kk];
             const double *v = V + 6 * I;
             w0 += v[0] * x0 + v[3] * x1;
             w1 += v[1] * x0 + v[4] * x1;
@@ -588,11 +630,11 @@ __global__ void __launch_bounds__(FT_THREADS)
         }
       } else {
         for (int I = 0; I < M; I++) {
-          const MeasJ &m = mj[I];
+          const double r0 = mv.res[2 * I], r1 = mv.res[2 * I + 1];
           const double *v = V + 6 * I;
-          w0 += v[0] * m.res[0] + v[3] * m.res[1];
-          w1 += v[1] * m.res[0] + v[4] * m.res[1];
-          w2 += v[2] * m.res[0] + v[5] * m.res[1];
+          w0 += v[0] * r0 + v[3] * r1;
+          w1 += v[1] * r0 + v[4] * r1;
+          w2 += v[2] * r0 + v[5] * r1;
         }
       }
       double z0 = tau[0] * w0;
@@ -611,25 +653,72 @@ __global__ void __launch_bounds__(FT_THREADS)
     if (scratch != nullptr) // features too large for shared memory: per-CTA slice of an L2-resident scratch buffer
       S = scratch + (size_t)blockIdx.x * scratch_per_cta;
     double *Tmy = Tw + (size_t)wid * 2 * n_all;
-    for (int I = wid; I < M; I += FT_WARPS) {
-      const MeasJ &mI = mj[I];
-      // T_I[r][c] = sum_b sum_k B_b[r][k] * P[off_b + k][state(c)]
+    // row pairs are dealt out so that every warp gets a similar share of the triangular J >= I sweep
+    for (int it = 0; it * FT_WARPS < M; it++) {
+      const int I = (it & 1) ? (it * FT_WARPS + (FT_WARPS - 1 - wid)) : (it * FT_WARPS + wid);
+      if (I >= M)
+        continue;
+      const signed char *slI = mv.slot + 8 * I;
+      const int s0 = slI[0], s1 = slI[1], s2 = slI[2];
+      const double *B0 = mv.blk(I, 0), *B1 = mv.blk(I, 1), *B2 = mv.blk(I, 2);
+      // T_I[r][c] = sum_b sum_k B_b[r][k] * P[off_b + k][state(c)]; all loads of a column are issued before their use
+      // (P is L2-resident: ~20 dependent-latency round trips per column otherwise)
       for (int c = lane; c < wf; c += 32) {
-        int sc = lcol_slot[c];
-        int pc = fr->slot_off[sc] + lcol_k[c];
+        const int pc = fslot_off[lcol_slot[c]] + lcol_k[c];
+        double pv[20];
+        const double *P0 = P + (size_t)fslot_off[s0] * ldP + pc;
+        const double *P1 = P + (size_t)fslot_off[s1 >= 0 ? s1 : s0] * ldP + pc;
+        const double *P2 = P + (size_t)fslot_off[s2 >= 0 ? s2 : s0] * ldP + pc;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          pv[k] = __ldg(P0 + (size_t)k * ldP);
+        if (s1 >= 0) {
+#pragma unroll
+          for (int k = 0; k < 6; k++)
+            pv[6 + k] = __ldg(P1 + (size_t)k * ldP);
+        }
+        if (s2 >= 0) {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            pv[12 + k] = __ldg(P2 + (size_t)k * ldP);
+        }
         double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-        for (int b = 0; b < 5; b++) {
-          int sb = mI.slot[b];
-          if (sb < 0)
-            continue;
-          const double *B = blk_ptr(mI, b);
-          int wb = blk_w(b);
-          const double *Prow = P + (size_t)fr->slot_off[sb] * ldP + pc;
-          for (int k = 0; k < wb; k++) {
-            double pv = __ldg(Prow + (size_t)k * ldP);
-            t0 += B[k] * pv;
-            t1 += B[wb + k] * pv;
+        for (int k = 0; k < 6; k++) {
+          t0 += B0[k] * pv[k];
+          t1 += B0[8 + k] * pv[k];
+        }
+        if (s1 >= 0) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            t0 += B1[k] * pv[6 + k];
+            t1 += B1[8 + k] * pv[6 + k];
+          }
+        }
+        if (s2 >= 0) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            t0 += B2[k] * pv[12 + k];
+            t1 += B2[8 + k] * pv[12 + k];
+          }
+        }
+        if (nblk > 3) {
+#pragma unroll
+          for (int b = 3; b < 5; b++) {
+            const int sb = slI[b];
+            if (sb < 0)
+              continue;
+            const double *B = mv.blk(I, b);
+            const double *Pb = P + (size_t)fslot_off[sb] * ldP + pc;
+            double pw[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              pw[k] = __ldg(Pb + (size_t)k * ldP);
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+              t0 += B[k] * pw[k];
+              t1 += B[8 + k] * pw[k];
+            }
           }
         }
         Tmy[c] = t0;
@@ -637,22 +726,24 @@ __global__ void __launch_bounds__(FT_THREADS)
       }
       __syncwarp();
       for (int J = I + lane; J < M; J += 32) {
-        const MeasJ &mJ = mj[J];
+        const signed char *slJ = mv.slot + 8 * J;
         double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
 #pragma unroll
         for (int b = 0; b < 5; b++) {
-          int sb = mJ.slot[b];
+          if (b >= nblk)
+            break;
+          int sb = slJ[b];
           if (sb < 0)
             continue;
-          const double *B = blk_ptr(mJ, b);
+          const double *B = mv.blk(J, b);
           int wb = blk_w(b);
           int c0 = slot2l[sb];
           for (int k = 0; k < wb; k++) {
             double ta = Tmy[c0 + k], tb = Tmy[n_all + c0 + k];
             s00 += ta * B[k];
-            s01 += ta * B[wb + k];
+            s01 += ta * B[8 + k];
             s10 += tb * B[k];
-            s11 += tb * B[wb + k];
+            s11 += tb * B[8 + k];
           }
         }
         if (J == I) {
@@ -698,7 +789,7 @@ __global__ void __launch_bounds__(FT_THREADS)
     {
       double z0 = Z[n_all], z1 = Z[(n_all + 1) + n_all], z2 = Z[2 * (n_all + 1) + n_all];
       for (int i = tid; i < rows; i += FT_THREADS) {
-        double rv = mj[i >> 1].res[i & 1] - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2);
+        double rv = mv.res[i] - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2);
         S[(size_t)rows * ldS + i] = rv;
       }
     }
@@ -727,44 +818,46 @@ __global__ void __launch_bounds__(FT_THREADS)
       int j = jb + tid;
       if (j > n_all)
         break;
-      int s = -1, kk = 0;
+      int s = 0, kk = 0;
       bool present = false;
       if (j < n_all) {
-        s = 0;
-        while (s + 1 < n_slots && fr->slot_col[s + 1] <= j)
-          s++;
-        kk = j - fr->slot_col[s];
+        s = ccol_slot[j];
+        kk = ccol_k[j];
         present = slot2l[s] >= 0;
       }
       double z0 = Z[j], z1 = Z[(n_all + 1) + j], z2 = Z[2 * (n_all + 1) + j];
-      for (int i = 3; i < rows; i++) {
-        double val = 0.0;
-        if (!gated) {
-          double xv;
-          if (j == n_all)
-            xv = mj[i >> 1].res[i & 1];
-          else
-            xv = present ? x_at(mj[i >> 1], i & 1, s, kk) : 0.0;
-          val = xv - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2);
-          if (j < n_all && !present)
-            val = 0.0;
+      double *out = Hs + (size_t)F->row0 * ldH + j;
+      if (gated || (j < n_all && !present)) {
+        for (int i = 3; i < rows; i++)
+          out[(size_t)(i - 3) * ldH] = 0.0;
+      } else {
+        for (int i = 3; i < rows; i++) {
+          double xv = (j == n_all) ? mv.res[i] : mv.x_at(i >> 1, i & 1, s, kk);
+          out[(size_t)(i - 3) * ldH] = xv - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2);
         }
-        Hs[(size_t)(F->row0 + i - 3) * ldH + j] = val;
       }
     }
   }
 }
 
-static size_t feature_smem_bytes(int maxM, int n_all, bool S_in_smem) {
+static size_t feature_smem_bytes(int maxM, int n_all, int n_slots, int nblk, bool S_in_smem) {
   size_t o = 0;
-  o += sizeof(MeasJ) * (size_t)maxM;
+  const size_t n_all8 = (size_t)((n_all + 7) & ~7);
+  o += sizeof(double) * 16 * (size_t)nblk * maxM;
+  o += sizeof(double) * 6 * (size_t)maxM;
+  o += sizeof(double) * 2 * (size_t)maxM;
   o += sizeof(double) * 3 * 2 * (size_t)maxM;
   o += sizeof(double) * 3 * (size_t)(n_all + 1);
   o += sizeof(double) * FT_WARPS * 2 * (size_t)n_all;
-  o += sizeof(double) * (FT_WARPS * 3 + 16);
-  o += sizeof(short) * (size_t)((n_all + 7) & ~7) * 2;
-  o += sizeof(int) * OVB_MAX_VARS;
+  o += sizeof(double) * (FT_WARPS * 3 + 24);
+  o += sizeof(int) * OVB_MAX_VARS * 2;
   o += sizeof(int) * 8;
+  o += sizeof(short) * n_all8 * 2;
+  o += n_all8 * 2;
+  o += OVB_MAX_VARS;
+  o += (size_t)maxM * 8;
+  o += (size_t)((maxM + 7) & ~7) * 2;
+  o += (size_t)maxM * (size_t)((n_slots + 3) & ~3);
   o = (o + 15) & ~(size_t)15;
   if (S_in_smem) {
     int rows = 2 * maxM;
@@ -779,13 +872,16 @@ extern unsigned char *ovb_feat_order_ptr(ovb_ctx *ctx);
 void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int mode, int max_M) {
   if (n_feats <= 0)
     return;
-  int n_all = ctx->h_frame->n_all;
+  const int n_all = ctx->h_frame->n_all, n_slots = ctx->h_frame->n_slots;
   int maxM = max_M < 2 ? 2 : max_M;
   if (maxM > OVB_MAX_MEAS_PER_FEAT)
     maxM = OVB_MAX_MEAS_PER_FEAT;
+  // anchor blocks exist only for the anchored representations (same remap as DevOpts::rep)
+  const int rep = ctx->h_opts->rep;
+  const int nblk = (rep == OVB_REP_GLOBAL_3D || rep == OVB_REP_GLOBAL_FULL_INVERSE_DEPTH) ? 3 : 5;
   const size_t smem_limit = 227 * 1024;
-  bool S_in_smem = feature_smem_bytes(maxM, n_all, true) <= smem_limit;
-  size_t smem = feature_smem_bytes(maxM, n_all, S_in_smem);
+  bool S_in_smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, true) <= smem_limit;
+  size_t smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, S_in_smem);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_feature_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
@@ -800,6 +896,6 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
   }
   int dump_rows = ctx->dump_rows; // rows of the current dump (set by ovb_feature_jacobians)
   k_feature_system<<<grid, FT_THREADS, smem, ctx->stream>>>(ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv, ctx->P[ctx->cur], ctx->ldP,
-                                                            ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, scratch,
-                                                            ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
+                                                            ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk,
+                                                            scratch, ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
 }

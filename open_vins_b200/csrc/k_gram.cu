@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(1024) k_gram_chol(const double *__restrict__ G
                                                     double *__restrict__ work, int use_smem) {
   extern __shared__ __align__(16) double gsm[];
   __shared__ int flag;
-  __shared__ double invd_sh[8];
+  __shared__ double invd_sh[16];
   const int tid = threadIdx.x;
   if (tid == 0)
     flag = 0;
