@@ -11,15 +11,24 @@
 //   3. the chunk's 16 x 16 R goes to a small workspace; the next level repeats 1-2 on the stacked R factors
 //      (rows addressed in place through an index map), until one chunk is left.
 // Chunks never exchange data inside a level (no grid-wide sync, no atomics: bitwise reproducible); Q is never formed.
+// Upper levels: as soon as a level has <= QR_CLUSTER chunks, those chunks are factored TOGETHER by one thread-block
+// cluster (one CTA per chunk): the 17 per-step dot products and the 16 x 32 V'A block of every trailing tile are
+// summed across the cluster through distributed shared memory, so the level finishes the panel in ONE launch instead
+// of two or three latency-bound ones.
 // The reference's Givens R has diag >= 0; rows of R (and z) are sign-flipped at the end to match.
 #include "ovb_internal.cuh"
 #include <math.h>
+#include <cstddef>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 #define QR_NB OVB_NB
 #define QR_CR OVB_CR
 #define QR_CT 32
 #define QR_THREADS QR_CR
 #define QR_WARPS (QR_THREADS / 32)
+#define QR_CLUSTER 8 // portable maximum cluster size
+#define QR_XW 36     // exchange record: [0..15] dots, [16] sigma, [17] alpha, [18..33] pivot-row entries
 #ifdef OVB_TSQR_TIMING
 #include <cstdio>
 #define TPROBE(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) tprobe[i] = clock64(); } while (0)
@@ -41,7 +50,13 @@ struct QrSmem {
   double vbuf[2][16 * 18];            // pivot column broadcast, double buffered by step parity, pitch 18
   double sc[4];                       // [2 + parity]: pivot element alpha of the current step
   int rowidx[QR_CR];
+  // cluster mode only (written by the peer CTAs through DSMEM)
+  double xch[2][QR_CLUSTER][QR_XW];          // per-step partial sums, double buffered by step parity
+  double Yx[QR_CLUSTER][QR_NB][QR_APITCH];   // per-tile partial V'A of every CTA of the cluster
 };
+
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // D(8x8) += A(8x4) B(4x8) on the FP64 tensor-core path (DMMA). Fragments: a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
 // d0/d1 = D[lane>>2][2*(lane&3) + {0,1}].
@@ -49,10 +64,11 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// One (panel, level) step. grid = (chunks, column-tile groups).
+// One (panel, level) step. grid = (chunks, column-tile groups). csize > 1: the grid's x extent is one cluster of csize
+// CTAs (rank = chunk) that factor their chunks as ONE tall block; chunks past the data are padded with zero rows.
 __global__ void __launch_bounds__(QR_THREADS)
     k_tsqr_level(double *__restrict__ A, int ldA, int nt, int c0, int nbp, int level, int len, const double *__restrict__ Win,
-                 double *__restrict__ Wout, double *__restrict__ Rout, int ldR, int is_last) {
+                 double *__restrict__ Wout, double *__restrict__ Rout, int ldR, int is_last, int csize) {
   extern __shared__ __align__(16) unsigned char qr_smem_raw[];
   QrSmem &sm = *reinterpret_cast<QrSmem *>(qr_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -61,7 +77,25 @@ __global__ void __launch_bounds__(QR_THREADS)
   long long tprobe[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   TPROBE(0);
-  const int rows_i = min(QR_CR, len - chunk * QR_CR);
+  const int rows_i = max(0, min(QR_CR, len - chunk * QR_CR));
+  const bool clustered = csize > 1;
+  const int crank = clustered ? chunk : 0; // gridDim.x == cluster size
+  const bool has_pivots = (crank == 0);    // the pivot rows of a clustered block all live in its first chunk
+  double *xch_peer[QR_CLUSTER];
+#pragma unroll
+  for (int r = 0; r < QR_CLUSTER; r++)
+    xch_peer[r] = nullptr;
+  if (clustered) {
+    cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+    for (int r = 0; r < QR_CLUSTER; r++)
+      if (r < csize)
+        xch_peer[r] = cl.map_shared_rank(&sm.xch[0][crank][0], r);
+  }
+  if (clustered) { // every CTA of the cluster is running before anyone writes into a peer's shared memory
+    cluster_arrive_release();
+    cluster_wait_acquire();
+  }
   // ---- row map of this level back to rows of A
   {
     int g = chunk * QR_CR + tid;
@@ -105,7 +139,7 @@ __global__ void __launch_bounds__(QR_THREADS)
   for (int k = 0; k < nbp; k++) {
     const int par = k & 1;
     double pv = 0.0;
-    if (pg == 0 && pj >= k) { // pivot row k lives in group 0, window slot 0
+    if (has_pivots && pg == 0 && pj >= k) { // pivot row k lives in group 0, window slot 0
       pv = a[0];
       a[0] = 0.0;
     }
@@ -124,7 +158,7 @@ __global__ void __launch_bounds__(QR_THREADS)
       v[t] = vv.x;
       v[t + 1] = vv.y;
     }
-    const double alpha = sm.sc[2 + par];
+    double alpha = sm.sc[2 + par];
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int t = 0; t < QR_NB; t += 4) {
@@ -144,7 +178,39 @@ __global__ void __launch_bounds__(QR_THREADS)
       sigma += __shfl_xor_sync(0xffffffffu, sigma, o);
     }
     // pivot-row entry of this thread's column (held by the g == 0 thread of the half-warp; for j < k it is V[k][j])
-    const double akj = __shfl_sync(0xffffffffu, (pj >= k) ? pv : a[0], lane & 16);
+    double akj = __shfl_sync(0xffffffffu, (pj >= k) ? pv : a[0], lane & 16);
+    if (clustered) {
+      // every CTA adds its rows' share: post (dots, sigma[, alpha, pivot row]) into slot `crank` of every peer, one
+      // cluster barrier, then everybody sums the csize slots in the same order (bitwise identical scalars cluster-wide)
+      if (pg == 0) {
+#pragma unroll
+        for (int r = 0; r < QR_CLUSTER; r++) {
+          if (r < csize) {
+            double *dst = xch_peer[r] + par * (QR_CLUSTER * QR_XW);
+            dst[pj] = dot;
+            if (has_pivots)
+              dst[18 + pj] = akj;
+            if (pj == 0) {
+              dst[16] = sigma;
+              if (has_pivots)
+                dst[17] = alpha;
+            }
+          }
+        }
+      }
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      double ds[QR_CLUSTER], ss[QR_CLUSTER];
+#pragma unroll
+      for (int r = 0; r < QR_CLUSTER; r++) {
+        ds[r] = (r < csize) ? sm.xch[par][r][pj] : 0.0;
+        ss[r] = (r < csize) ? sm.xch[par][r][16] : 0.0;
+      }
+      dot = ((ds[0] + ds[1]) + (ds[2] + ds[3])) + ((ds[4] + ds[5]) + (ds[6] + ds[7]));
+      sigma = ((ss[0] + ss[1]) + (ss[2] + ss[3])) + ((ss[4] + ss[5]) + (ss[6] + ss[7]));
+      alpha = sm.xch[par][0][17];
+      akj = sm.xch[par][0][18 + pj];
+    }
     // reflector scalars: beta = -sign(alpha) |x|, tau = (beta - alpha)/beta = 1 + |alpha|/|x|, scale = 1/(alpha - beta)
     double tk = 0.0, scale = 0.0, beta = alpha;
     if (sigma != 0.0) {
@@ -182,7 +248,7 @@ __global__ void __launch_bounds__(QR_THREADS)
       for (int t = 0; t < QR_NB; t++)
         a[t] -= tw * v[t];
       if (pg == 0)
-        sm.Rb[k][pj] = pv - tk * wj; // finished entry R[k][j]
+        sm.Rb[k][pj] = akj - tk * wj; // finished entry R[k][j]
     } else if (pj == k) {
 #pragma unroll
       for (int t = 0; t < QR_NB; t++)
@@ -218,10 +284,10 @@ __global__ void __launch_bounds__(QR_THREADS)
     const int r = pg * 16 + t;
     double vv = 0.0;
     if (pj < nbp && r < rows_i)
-      vv = (r > pj) ? a[t] : (r == pj ? 1.0 : 0.0);
+      vv = (!has_pivots || r > pj) ? a[t] : (r == pj ? 1.0 : 0.0);
     sm.Vs[r][pj ^ pg] = vv;
   }
-  if (blockIdx.y == 0 && pg == 0) {
+  if (blockIdx.y == 0 && pg == 0 && has_pivots) {
     // thread (j, g=0) emits column j of the chunk's R from sm.Rb (rows t <= j; zeros below the diagonal)
     const int nr = min(nbp, rows_i);
     for (int t = 0; t < nr; t++) {
@@ -300,8 +366,30 @@ __global__ void __launch_bounds__(QR_THREADS)
           dmma884(y0[q], y1[q], sm.Vs[r][(i0 + fr) ^ sw], sm.At[r][cc0 + fr]);
         }
       }
-      sm.Ys[i0 + fr][cc0 + 2 * fk] = (y0[0] + y0[1]) + (y0[2] + y0[3]);
-      sm.Ys[i0 + fr][cc0 + 2 * fk + 1] = (y1[0] + y1[1]) + (y1[2] + y1[3]);
+      const double ya = (y0[0] + y0[1]) + (y0[2] + y0[3]), yb = (y1[0] + y1[1]) + (y1[2] + y1[3]);
+      if (!clustered) {
+        sm.Ys[i0 + fr][cc0 + 2 * fk] = ya;
+        sm.Ys[i0 + fr][cc0 + 2 * fk + 1] = yb;
+      } else {
+        cg::cluster_group cl = cg::this_cluster();
+        double *mine = &sm.Yx[crank][i0 + fr][cc0 + 2 * fk];
+#pragma unroll
+        for (int r = 0; r < QR_CLUSTER; r++)
+          if (r < csize)
+            *reinterpret_cast<double2 *>(cl.map_shared_rank(mine, r)) = make_double2(ya, yb);
+      }
+    }
+    if (clustered) {
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      // Ys = sum over the cluster (fixed order), two entries per thread
+      const int i = tid >> 4, c2 = (tid & 15) * 2;
+      double2 acc[QR_CLUSTER];
+#pragma unroll
+      for (int r = 0; r < QR_CLUSTER; r++)
+        acc[r] = (r < csize) ? *reinterpret_cast<const double2 *>(&sm.Yx[r][i][c2]) : make_double2(0.0, 0.0);
+      sm.Ys[i][c2] = ((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x)) + ((acc[4].x + acc[5].x) + (acc[6].x + acc[7].x));
+      sm.Ys[i][c2 + 1] = ((acc[0].y + acc[1].y) + (acc[2].y + acc[3].y)) + ((acc[4].y + acc[5].y) + (acc[6].y + acc[7].y));
     }
     __syncthreads();
     if (tile == (int)blockIdx.y) TPROBE(5);
@@ -359,6 +447,14 @@ __global__ void __launch_bounds__(QR_THREADS)
       }
     }
     __syncthreads();
+    if (clustered && tile + (int)gridDim.y < ntiles) { // Yx is reused by the next tile: nobody may still be reading it
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    }
+  }
+  if (clustered) { // no CTA may exit while a peer can still write into its shared memory
+    cluster_arrive_release();
+    cluster_wait_acquire();
   }
   TPROBE(7);
 #ifdef OVB_TSQR_TIMING
@@ -410,18 +506,38 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
     const int ntiles = (nt - (c0 + nbp) + QR_CT - 1) / QR_CT;
     while (true) {
       int chunks = (len + QR_CR - 1) / QR_CR;
-      int last = (chunks == 1);
+      // 2..QR_CLUSTER chunks: one thread-block cluster factors them as a single tall block and finishes the panel
+      const bool clustered = ctx->tsqr_cluster && chunks > 1 && chunks <= QR_CLUSTER;
+      int last = (chunks == 1) || clustered;
       // few chunks: spread the trailing tiles over more CTAs; many chunks: one CTA walks all tiles (no redundant panels)
       // one CTA per SM (128 KB of shared memory): fill the SMs in ONE wave; every column group of a chunk repeats the
       // panel factorisation, so never use more groups than that
-      int gy = ctx->sm_count / chunks;
+      int gx = clustered ? QR_CLUSTER : chunks;
+      int gy = ctx->sm_count / gx;
       if (gy > ntiles)
         gy = ntiles;
       if (gy < 1)
         gy = 1;
-      dim3 grid(chunks, gy);
-      k_tsqr_level<<<grid, QR_THREADS, sizeof(QrSmem), ctx->stream>>>(A, ldA, nt, c0, nbp, level, len, level > 0 ? ctx->d_W[(level - 1) & 1] : nullptr,
-                                                                       ctx->d_W[level & 1], Rout, ldR, last);
+      const double *Win = level > 0 ? ctx->d_W[(level - 1) & 1] : nullptr;
+      double *Wout = ctx->d_W[level & 1];
+      if (clustered) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx, gy);
+        cfg.blockDim = dim3(QR_THREADS);
+        cfg.dynamicSmemBytes = sizeof(QrSmem);
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = QR_CLUSTER;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_tsqr_level, A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, 1, (int)QR_CLUSTER);
+      } else {
+        dim3 grid(gx, gy);
+        k_tsqr_level<<<grid, QR_THREADS, offsetof(QrSmem, xch), ctx->stream>>>(A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, last, 1);
+      }
       ctx->n_launch++;
       ctx->n_launch_tsqr_level++;
       if (last)

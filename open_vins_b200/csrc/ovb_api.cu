@@ -91,6 +91,10 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, ctx->device));
   ctx->sm_count = prop.multiProcessorCount;
+  {
+    const char *e = getenv("OVB_TSQR_CLUSTER");
+    ctx->tsqr_cluster = e ? atoi(e) : 1;
+  }
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = 1;
   for (int i = 0; i < 8; i++)

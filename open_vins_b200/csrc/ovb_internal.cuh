@@ -129,6 +129,7 @@ struct ovb_ctx {
   int dump_rows;
   int max_rows;
   int sm_count;
+  int tsqr_cluster; // upper TSQR levels as one thread-block cluster (OVB_TSQR_CLUSTER=0 disables: A/B timing only)
   float stage_ms[6];
   // replay of the last update on device-resident inputs (bench: `value` leg; see ovb_msckf_replay)
   int replay_enabled, last_pk_valid;
