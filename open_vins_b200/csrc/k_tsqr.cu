@@ -13,8 +13,8 @@
 // Chunks never exchange data inside a level (no grid-wide sync, no atomics: bitwise reproducible); Q is never formed.
 // Upper levels: as soon as a level has <= QR_CLUSTER chunks, those chunks are factored TOGETHER by one thread-block
 // cluster (one CTA per chunk): the 17 per-step dot products and the 16 x 32 V'A block of every trailing tile are
-// summed across the cluster through distributed shared memory, so the level finishes the panel in ONE launch instead
-// of two or three latency-bound ones.
+// summed across the cluster through distributed shared memory (st.async + mbarrier complete_tx, no cluster barrier
+// in the loop), so the level finishes the panel in ONE launch instead of two or three latency-bound ones.
 // The reference's Givens R has diag >= 0; rows of R (and z) are sign-flipped at the end to match.
 #include "ovb_internal.cuh"
 #include <math.h>
@@ -53,7 +53,36 @@ struct QrSmem {
   // cluster mode only (written by the peer CTAs through DSMEM)
   double xch[2][QR_CLUSTER][QR_XW];          // per-step partial sums, double buffered by step parity
   double Yx[QR_CLUSTER][QR_NB][QR_APITCH];   // per-tile partial V'A of every CTA of the cluster
+  unsigned long long mbar[4];                // [0..1] per-step exchange (by step parity), [2] tile exchange
 };
+
+// DSMEM exchange without a cluster barrier: the sender stores straight into the peer's shared memory and the same
+// instruction credits the bytes to an mbarrier there (st.async ... mbarrier::complete_tx); the receiver only polls its
+// own mbarrier (one DSMEM latency instead of latency + barrier.cluster round trip).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f64(unsigned raddr, double v, unsigned rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_f64x2(unsigned raddr, double a, double b, unsigned rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr), "l"(__double_as_longlong(a)),
+               "l"(__double_as_longlong(b)), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tOVB_WAIT:\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t@p bra OVB_DONE;\n\tbra OVB_WAIT;\n\tOVB_DONE:\n\t}" ::"r"(bar),
+               "r"(parity)
+               : "memory");
+}
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -81,18 +110,20 @@ __global__ void __launch_bounds__(QR_THREADS)
   const bool clustered = csize > 1;
   const int crank = clustered ? chunk : 0; // gridDim.x == cluster size
   const bool has_pivots = (crank == 0);    // the pivot rows of a clustered block all live in its first chunk
-  double *xch_peer[QR_CLUSTER];
-#pragma unroll
-  for (int r = 0; r < QR_CLUSTER; r++)
-    xch_peer[r] = nullptr;
+  // my exchange slot and mbarriers as seen by the peer this lane serves (lane group index pg = tid & 15 -> peer rank)
+  unsigned peer_xch = 0, peer_bar = 0, peer_yx = 0;
   if (clustered) {
-    cg::cluster_group cl = cg::this_cluster();
-#pragma unroll
-    for (int r = 0; r < QR_CLUSTER; r++)
-      if (r < csize)
-        xch_peer[r] = cl.map_shared_rank(&sm.xch[0][crank][0], r);
-  }
-  if (clustered) { // every CTA of the cluster is running before anyone writes into a peer's shared memory
+    const unsigned peer = (unsigned)(tid & 15) % (unsigned)csize;
+    peer_xch = mapa_u32(smem_u32(&sm.xch[0][crank][0]), peer);
+    peer_bar = mapa_u32(smem_u32(&sm.mbar[0]), peer);
+    peer_yx = smem_u32(&sm.Yx[crank][0][0]);
+    if (tid == 0) {
+      mbar_init(smem_u32(&sm.mbar[0]), 1);
+      mbar_init(smem_u32(&sm.mbar[1]), 1);
+      mbar_init(smem_u32(&sm.mbar[2]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // every CTA of the cluster is running and has its mbarriers initialised before anyone writes into a peer
     cluster_arrive_release();
     cluster_wait_acquire();
   }
@@ -180,26 +211,25 @@ __global__ void __launch_bounds__(QR_THREADS)
     // pivot-row entry of this thread's column (held by the g == 0 thread of the half-warp; for j < k it is V[k][j])
     double akj = __shfl_sync(0xffffffffu, (pj >= k) ? pv : a[0], lane & 16);
     if (clustered) {
-      // every CTA adds its rows' share: post (dots, sigma[, alpha, pivot row]) into slot `crank` of every peer, one
-      // cluster barrier, then everybody sums the csize slots in the same order (bitwise identical scalars cluster-wide)
-      if (pg == 0) {
-#pragma unroll
-        for (int r = 0; r < QR_CLUSTER; r++) {
-          if (r < csize) {
-            double *dst = xch_peer[r] + par * (QR_CLUSTER * QR_XW);
-            dst[pj] = dot;
-            if (has_pivots)
-              dst[18 + pj] = akj;
-            if (pj == 0) {
-              dst[16] = sigma;
-              if (has_pivots)
-                dst[17] = alpha;
-            }
-          }
+      // every CTA adds its rows' share: post (dots, sigma[, alpha, pivot row]) into slot `crank` of every peer, wait on
+      // the own mbarrier, then sum the csize slots in the same order everywhere (bitwise identical scalars cluster-wide).
+      // After the butterfly every lane of the half-warp holds the column's dot: lane group pg posts it to peer pg.
+      const unsigned bar_l = smem_u32(&sm.mbar[par]);
+      if (tid == 0) // bytes this CTA receives in this step: (16 dots + sigma) from everybody, (alpha + 16 pivot entries) from rank 0
+        mbar_expect_tx(bar_l, (unsigned)(csize * 17 * 8 + 17 * 8));
+      if (pg < csize) {
+        const unsigned dst = peer_xch + (unsigned)(par * (QR_CLUSTER * QR_XW) * 8);
+        const unsigned rb = peer_bar + (unsigned)(par * 8);
+        st_async_f64(dst + pj * 8, dot, rb);
+        if (has_pivots)
+          st_async_f64(dst + (18 + pj) * 8, akj, rb);
+        if (pj == 0) {
+          st_async_f64(dst + 16 * 8, sigma, rb);
+          if (has_pivots)
+            st_async_f64(dst + 17 * 8, alpha, rb);
         }
       }
-      cluster_arrive_release();
-      cluster_wait_acquire();
+      mbar_wait(bar_l, (unsigned)((k >> 1) & 1));
       double ds[QR_CLUSTER], ss[QR_CLUSTER];
 #pragma unroll
       for (int r = 0; r < QR_CLUSTER; r++) {
@@ -336,7 +366,9 @@ __global__ void __launch_bounds__(QR_THREADS)
   const int ntrail = nt - tc0;
   const int ntiles = (ntrail + QR_CT - 1) / QR_CT;
   const int fr = lane >> 2, fk = lane & 3; // DMMA fragment coordinates
+  int tile_it = -1;
   for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+    tile_it++;
     const int col0 = tc0 + tile * QR_CT;
     const int ncol = min(QR_CT, nt - col0);
     // load tile (warp per row, lanes over columns: coalesced 256 B rows); 16 independent loads in flight per lane
@@ -371,17 +403,19 @@ __global__ void __launch_bounds__(QR_THREADS)
         sm.Ys[i0 + fr][cc0 + 2 * fk] = ya;
         sm.Ys[i0 + fr][cc0 + 2 * fk + 1] = yb;
       } else {
-        cg::cluster_group cl = cg::this_cluster();
-        double *mine = &sm.Yx[crank][i0 + fr][cc0 + 2 * fk];
+        const unsigned off = (unsigned)(((i0 + fr) * QR_APITCH + cc0 + 2 * fk) * 8);
+        const unsigned bar2 = smem_u32(&sm.mbar[2]);
 #pragma unroll
         for (int r = 0; r < QR_CLUSTER; r++)
           if (r < csize)
-            *reinterpret_cast<double2 *>(cl.map_shared_rank(mine, r)) = make_double2(ya, yb);
+            st_async_f64x2(mapa_u32(peer_yx + off, r), ya, yb, mapa_u32(bar2, r));
       }
     }
     if (clustered) {
-      cluster_arrive_release();
-      cluster_wait_acquire();
+      const unsigned bar2 = smem_u32(&sm.mbar[2]);
+      if (tid == 0)
+        mbar_expect_tx(bar2, (unsigned)(csize * QR_NB * QR_CT * 8));
+      mbar_wait(bar2, (unsigned)(tile_it & 1));
       // Ys = sum over the cluster (fixed order), two entries per thread
       const int i = tid >> 4, c2 = (tid & 15) * 2;
       double2 acc[QR_CLUSTER];
