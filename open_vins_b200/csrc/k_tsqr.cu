@@ -40,7 +40,7 @@ namespace cg = cooperative_groups;
 #define QR_APITCH 36 // pitch of At / Ys / Zs (2*36 mod 32 = 8)
 struct QrSmem {
   double Vs[QR_CR][QR_VPITCH];        // reflectors, unit lower trapezoid: V[r][j] at Vs[r][j ^ ((r >> 4) & 15)] (swizzled)
-  double At[QR_CR][QR_APITCH];        // trailing tile (also the panel staging buffer)
+  double At[QR_CR][QR_APITCH];        // trailing tile, buffer 0 (also the panel staging buffer)
   double Ys[QR_NB][QR_APITCH];        // V'A of the tile
   double Zs[QR_NB][QR_APITCH];        // -(Tt Y): the update is At + V Zs
   double G[QR_NB][QR_NB];             // strict lower: v_k'v_i
@@ -52,9 +52,21 @@ struct QrSmem {
   int rowidx[QR_CR];
   // cluster mode only (written by the peer CTAs through DSMEM)
   double xch[2][QR_CLUSTER][QR_XW];          // per-step partial sums, double buffered by step parity
-  double Yx[QR_CLUSTER][QR_NB][QR_APITCH];   // per-tile partial V'A of every CTA of the cluster
   unsigned long long mbar[4];                // [0..1] per-step exchange (by step parity), [2] tile exchange
+  union {
+    double At1[QR_CR][QR_APITCH];            // trailing tile, buffer 1 (next tile streams in while this one is updated)
+    double Yx[QR_CLUSTER][QR_NB][QR_APITCH]; // cluster mode: per-tile partial V'A of every CTA of the cluster
+  };
 };
+
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned dst, const void *src, unsigned src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // DSMEM exchange without a cluster barrier: the sender stores straight into the peer's shared memory and the same
 // instruction credits the bytes to an mbarrier there (st.async ... mbarrier::complete_tx); the receiver only polls its
@@ -97,7 +109,7 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // CTAs (rank = chunk) that factor their chunks as ONE tall block; chunks past the data are padded with zero rows.
 __global__ void __launch_bounds__(QR_THREADS)
     k_tsqr_level(double *__restrict__ A, int ldA, int nt, int c0, int nbp, int level, int len, const double *__restrict__ Win,
-                 double *__restrict__ Wout, double *__restrict__ Rout, int ldR, int is_last, int csize) {
+                 double *__restrict__ Wout, double *__restrict__ Rout, int ldR, int is_last, int csize, int cr0) {
   extern __shared__ __align__(16) unsigned char qr_smem_raw[];
   QrSmem &sm = *reinterpret_cast<QrSmem *>(qr_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -106,7 +118,10 @@ __global__ void __launch_bounds__(QR_THREADS)
   long long tprobe[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   TPROBE(0);
-  const int rows_i = max(0, min(QR_CR, len - chunk * QR_CR));
+  // rows per chunk: cr0 (<= QR_CR, multiple of 16) at level 0 so that the chunks fill the SMs, QR_CR above
+  const int crl = (level == 0) ? cr0 : QR_CR;
+  const int rows_i = max(0, min(crl, len - chunk * crl));
+  const int rows16 = (rows_i + 15) & ~15;
   const bool clustered = csize > 1;
   const int crank = clustered ? chunk : 0; // gridDim.x == cluster size
   const bool has_pivots = (crank == 0);    // the pivot rows of a clustered block all live in its first chunk
@@ -129,9 +144,9 @@ __global__ void __launch_bounds__(QR_THREADS)
   }
   // ---- row map of this level back to rows of A
   {
-    int g = chunk * QR_CR + tid;
+    int g = chunk * crl + tid;
     for (int l = level; l >= 1; l--)
-      g = (g / nbp) * QR_CR + (g % nbp);
+      g = (g / nbp) * (l == 1 ? cr0 : QR_CR) + (g % nbp);
     sm.rowidx[tid] = c0 + g;
   }
   // ---- panel factorisation. Ownership: thread (j = tid>>4, g = tid&15) holds rows 16g..16g+15 of panel column j in
@@ -147,7 +162,7 @@ __global__ void __launch_bounds__(QR_THREADS)
       double v = 0.0;
       if (r < rows_i && lj < nbp) {
         if (level == 0)
-          v = A[(size_t)(c0 + chunk * QR_CR + r) * ldA + c0 + lj];
+          v = A[(size_t)(c0 + chunk * crl + r) * ldA + c0 + lj];
         else
           v = Win[(size_t)(chunk * QR_CR + r) * QR_NB + lj];
       }
@@ -162,6 +177,37 @@ __global__ void __launch_bounds__(QR_THREADS)
   for (int t = 0; t < QR_NB; t++)
     a[t] = Bp[pj * 257 + t * 16 + pg];
   __syncthreads(); // Bp (== At) is free again
+  // ---- trailing tiles of this CTA stream in with cp.async: the first one during the panel factorisation, the next one
+  // while the current one is updated (cluster mode: single buffer, the second buffer holds the exchange slots)
+  const int tc0 = c0 + nbp;
+  const int ntiles = (nt - tc0 + QR_CT - 1) / QR_CT;
+  auto prefetch_tile = [&](int tile, int buf) {
+    const int col0 = tc0 + tile * QR_CT;
+    const int ncol = min(QR_CT, nt - col0);
+    double(*At)[QR_APITCH] = buf ? sm.At1 : sm.At;
+    if (((ldA | col0) & 1) == 0 && (((size_t)A) & 15) == 0) {
+      const int ch = tid & 15, rr = tid >> 4; // 16-byte chunk of the 256-byte row
+      const int nb = max(0, min(16, ncol * 8 - ch * 16));
+      for (int r = rr; r < rows16; r += 16) {
+        const bool ok = (r < rows_i) && nb > 0;
+        const double *src = ok ? A + (size_t)sm.rowidx[r] * ldA + col0 + 2 * ch : A;
+        cp_async16(smem_u32(&At[r][2 * ch]), src, ok ? (unsigned)nb : 0u);
+      }
+    } else {
+      const int cc = tid & 31, rr = tid >> 5;
+      for (int r = rr; r < rows16; r += 8) {
+        const bool ok = (r < rows_i) && cc < ncol;
+        const double *src = ok ? A + (size_t)sm.rowidx[r] * ldA + col0 + cc : A;
+        cp_async8(smem_u32(&At[r][cc]), src, ok ? 8u : 0u);
+      }
+    }
+    cp_async_commit();
+  };
+  bool tile_pending = false;
+  if ((int)blockIdx.y < ntiles) {
+    prefetch_tile(blockIdx.y, 0);
+    tile_pending = true;
+  }
   // Finished rows (row k of columns j >= k after step k) leave the register window: their value goes to sm.Rb and the
   // slot is zeroed, so dot products and updates run unmasked. ONE barrier per step: the pivot column and the pivot
   // element are broadcast through (double-buffered) shared memory; every thread then derives the reflector scalars
@@ -362,40 +408,34 @@ __global__ void __launch_bounds__(QR_THREADS)
   __syncthreads();
   // ---- apply Q' to the trailing column tiles owned by this CTA: two small GEMMs on the FP64 tensor-core path
   TPROBE(3);
-  const int tc0 = c0 + nbp;
-  const int ntrail = nt - tc0;
-  const int ntiles = (ntrail + QR_CT - 1) / QR_CT;
   const int fr = lane >> 2, fk = lane & 3; // DMMA fragment coordinates
-  int tile_it = -1;
+  int tile_it = -1, buf = 0;
   for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
     tile_it++;
     const int col0 = tc0 + tile * QR_CT;
     const int ncol = min(QR_CT, nt - col0);
-    // load tile (warp per row, lanes over columns: coalesced 256 B rows); 16 independent loads in flight per lane
-    for (int rb = 0; rb < QR_CR; rb += 16 * QR_WARPS) {
-      double vals[16];
-#pragma unroll
-      for (int u = 0; u < 16; u++) {
-        const int r = rb + u * QR_WARPS + wid;
-        vals[u] = (r < rows_i && lane < ncol) ? A[(size_t)sm.rowidx[r] * ldA + col0 + lane] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 16; u++)
-        sm.At[rb + u * QR_WARPS + wid][lane] = vals[u];
-    }
+    double(*At)[QR_APITCH] = buf ? sm.At1 : sm.At;
+    if (!tile_pending)
+      prefetch_tile(tile, buf);
+    cp_async_wait_all();
     __syncthreads();
+    tile_pending = false;
+    if (!clustered && tile + (int)gridDim.y < ntiles) {
+      prefetch_tile(tile + gridDim.y, buf ^ 1);
+      tile_pending = true;
+    }
     if (tile == (int)blockIdx.y) TPROBE(4);
     // Y = V'At (16 x 32, K = 256): warp w owns the 8x8 output tile (w>>2, w&3); 4 interleaved accumulator pairs
     {
       const int i0 = 8 * (wid >> 2), cc0 = 8 * (wid & 3);
       double y0[4] = {0.0, 0.0, 0.0, 0.0}, y1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
-      for (int r0 = 0; r0 < QR_CR; r0 += 16) {
+      for (int r0 = 0; r0 < rows16; r0 += 16) {
         const int sw = (r0 >> 4) & 15;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const int r = r0 + 4 * q + fk;
-          dmma884(y0[q], y1[q], sm.Vs[r][(i0 + fr) ^ sw], sm.At[r][cc0 + fr]);
+          dmma884(y0[q], y1[q], sm.Vs[r][(i0 + fr) ^ sw], At[r][cc0 + fr]);
         }
       }
       const double ya = (y0[0] + y0[1]) + (y0[2] + y0[3]), yb = (y1[0] + y1[1]) + (y1[2] + y1[3]);
@@ -449,6 +489,8 @@ __global__ void __launch_bounds__(QR_THREADS)
 #pragma unroll
       for (int rq = 0; rq < 4; rq++) {
         const int r0 = 8 * (wid + 8 * rq);
+        if (r0 >= rows16)
+          break;
         const int sw = (r0 >> 4) & 15;
         const int r = r0 + fr;
         double va[4];
@@ -458,7 +500,7 @@ __global__ void __launch_bounds__(QR_THREADS)
         double c[4][2];
 #pragma unroll
         for (int ct = 0; ct < 4; ct++) {
-          const double2 cc = *reinterpret_cast<const double2 *>(&sm.At[r][8 * ct + 2 * fk]);
+          const double2 cc = *reinterpret_cast<const double2 *>(&At[r][8 * ct + 2 * fk]);
           c[ct][0] = cc.x;
           c[ct][1] = cc.y;
         }
@@ -481,6 +523,8 @@ __global__ void __launch_bounds__(QR_THREADS)
       }
     }
     __syncthreads();
+    if (!clustered)
+      buf ^= 1;
     if (clustered && tile + (int)gridDim.y < ntiles) { // Yx is reused by the next tile: nobody may still be reading it
       cluster_arrive_release();
       cluster_wait_acquire();
@@ -538,13 +582,26 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
       break;
     int level = 0;
     const int ntiles = (nt - (c0 + nbp) + QR_CT - 1) / QR_CT;
+    // level-0 chunk height: enough chunks to fill the SMs, but no more than one cluster can take over at level 1
+    int cr0 = QR_CR;
+    {
+      int want = ctx->sm_count < QR_CLUSTER * QR_CR / QR_NB ? ctx->sm_count : QR_CLUSTER * QR_CR / QR_NB;
+      if (!ctx->tsqr_cluster)
+        want = ctx->sm_count;
+      int h = ((len + want - 1) / want + 15) & ~15;
+      if (h < 64)
+        h = 64;
+      if (h < QR_CR && len > QR_CLUSTER * QR_CR)
+        cr0 = h;
+    }
     while (true) {
-      int chunks = (len + QR_CR - 1) / QR_CR;
+      const int crl = (level == 0) ? cr0 : QR_CR;
+      int chunks = (len + crl - 1) / crl;
       // 2..QR_CLUSTER chunks: one thread-block cluster factors them as a single tall block and finishes the panel
       const bool clustered = ctx->tsqr_cluster && chunks > 1 && chunks <= QR_CLUSTER;
       int last = (chunks == 1) || clustered;
       // few chunks: spread the trailing tiles over more CTAs; many chunks: one CTA walks all tiles (no redundant panels)
-      // one CTA per SM (128 KB of shared memory): fill the SMs in ONE wave; every column group of a chunk repeats the
+      // one CTA per SM (~200 KB of shared memory): fill the SMs in ONE wave; every column group of a chunk repeats the
       // panel factorisation, so never use more groups than that
       int gx = clustered ? QR_CLUSTER : chunks;
       int gy = ctx->sm_count / gx;
@@ -567,16 +624,16 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_tsqr_level, A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, 1, (int)QR_CLUSTER);
+        cudaLaunchKernelEx(&cfg, k_tsqr_level, A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, 1, (int)QR_CLUSTER, cr0);
       } else {
         dim3 grid(gx, gy);
-        k_tsqr_level<<<grid, QR_THREADS, offsetof(QrSmem, xch), ctx->stream>>>(A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, last, 1);
+        k_tsqr_level<<<grid, QR_THREADS, sizeof(QrSmem), ctx->stream>>>(A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, last, 1, cr0);
       }
       ctx->n_launch++;
       ctx->n_launch_tsqr_level++;
       if (last)
         break;
-      int rows_last = len - (chunks - 1) * QR_CR;
+      int rows_last = len - (chunks - 1) * crl;
       len = (chunks - 1) * nbp + (rows_last < nbp ? rows_last : nbp);
       level++;
     }

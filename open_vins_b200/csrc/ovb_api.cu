@@ -139,7 +139,7 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
   CK(cudaMalloc(&ctx->d_Hs, sizeof(double) * ctx->Hs_cap));
   ctx->h_stage = nullptr; // pinned dense staging is grown on demand (ensure_stage)
   ctx->stage_cap = 0;
-  ctx->W_cap = ((size_t)ctx->max_rows / OVB_CR + 2) * OVB_NB * OVB_NB + 4096;
+  ctx->W_cap = ((size_t)ctx->max_rows / OVB_CR + 2 + (size_t)ctx->sm_count) * OVB_NB * OVB_NB + 4096; // level-0 chunks can be as short as max_rows / sm_count
   CK(cudaMalloc(&ctx->d_W[0], sizeof(double) * ctx->W_cap));
   CK(cudaMalloc(&ctx->d_W[1], sizeof(double) * ctx->W_cap));
   size_t rsz = (size_t)(ms + 8) * (ms + 8);
