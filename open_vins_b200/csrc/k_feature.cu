@@ -265,7 +265,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
   }
 
-  for (int f = blockIdx.x; f < n_feats; f += gridDim.x) {
+  for (int fi = blockIdx.x; fi < n_feats; fi += gridDim.x) {
+    const int f = feats[fi].sched; // longest tracks first: the short ones fill the tail of the last wave
     DevFeat *F = &feats[f];
     const int m0 = F->m0, M = F->m1 - F->m0;
     const int rows = 2 * M;

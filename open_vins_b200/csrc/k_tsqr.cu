@@ -383,21 +383,16 @@ __global__ void __launch_bounds__(QR_THREADS)
     double x[QR_NB];
 #pragma unroll
     for (int k = 0; k < QR_NB; k++) {
-      double val = 0.0;
+      // x[i] = 0 for i < c, so the sum runs over all i < k with static bounds; four interleaved chains
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int i = 0; i < QR_NB; i++)
+        if (i < k)
+          acc[i & 3] += sm.G[k][i] * x[i];
+      double val = -sm.tau[k] * ((acc[0] + acc[1]) + (acc[2] + acc[3]));
       if (k == c)
         val = sm.tau[c];
-      else if (k > c && k < nbp) {
-        double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < QR_NB; i += 2) {
-          if (i >= c && i < k)
-            acc0 += sm.G[k][i] * x[i];
-          if (i + 1 >= c && i + 1 < k)
-            acc1 += sm.G[k][i + 1] * x[i + 1];
-        }
-        val = -sm.tau[k] * (acc0 + acc1);
-      }
-      if (c >= nbp || k >= nbp)
+      if (k < c || c >= nbp || k >= nbp)
         val = 0.0;
       x[k] = val;
     }

@@ -474,6 +474,16 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
       }
     }
   }
+  {
+    // CTA schedule of the per-feature kernels: longest tracks first (counting sort on the track length, stable)
+    int cnt[OVB_MAX_MEAS_PER_FEAT + 2] = {0};
+    for (int f = 0; f < F; f++)
+      cnt[OVB_MAX_MEAS_PER_FEAT - (ctx->h_feat[f].m1 - ctx->h_feat[f].m0) + 1]++;
+    for (int i = 1; i <= OVB_MAX_MEAS_PER_FEAT + 1; i++)
+      cnt[i] += cnt[i - 1];
+    for (int f = 0; f < F; f++)
+      ctx->h_feat[cnt[OVB_MAX_MEAS_PER_FEAT - (ctx->h_feat[f].m1 - ctx->h_feat[f].m0)]++].sched = f;
+  }
   pk->n_feats = F;
   pk->n_meas = M;
   pk->max_M = maxM;

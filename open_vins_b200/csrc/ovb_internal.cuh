@@ -50,6 +50,7 @@ struct DevFeat {
   int key0, key1;    // camera-key range
   int status;        // ovb_feat_status
   int anchor_cam, anchor_clone;
+  int sched, pad0;   // CTA i of the per-feature kernels works on feature feats[i].sched (longest tracks first)
   double p_FinA[3], p_FinG[3];
   double chi2;
 };
