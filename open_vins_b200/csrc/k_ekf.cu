@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_ekf_gemm(int mode, const double *__rest
 
 // single CTA: S (r x r, lower) plus the residual as row r  ->  L and w = L^-1 res in row r. Works in shared memory when
 // it fits, else in place in global memory (L2).
-__global__ void __launch_bounds__(1024) k_ekf_chol(double *__restrict__ S, int ldS, int r, const double *__restrict__ res, double *__restrict__ w,
+__global__ void __launch_bounds__(EKC_THREADS) k_ekf_chol(double *__restrict__ S, int ldS, int r, const double *__restrict__ res, double *__restrict__ w,
                                                    double *__restrict__ invdiag, DevUpdateInfo *__restrict__ info, int use_smem) {
   extern __shared__ __align__(16) double chol_sm[];
   __shared__ int flag;
@@ -88,31 +88,32 @@ __global__ void __launch_bounds__(1024) k_ekf_chol(double *__restrict__ S, int l
   const int tid = threadIdx.x;
   if (tid == 0)
     flag = 0;
-  for (int j = tid; j < r; j += 1024)
+  for (int j = tid; j < r; j += EKC_THREADS)
     S[(size_t)r * ldS + j] = res[j];
   __syncthreads();
   double *W = S;
   int ld = ldS;
+  const int lane = tid & 31, wid = tid >> 5;
   if (use_smem) {
     ld = r | 1;
     W = chol_sm;
-    for (int e = tid; e < (r + 1) * r; e += 1024) {
-      int i = e / r, j = e % r;
-      if (j <= i)
+    // warp per row, lanes over the lower-triangle columns (coalesced; no integer division on the load path)
+    for (int i = wid; i <= r; i += EKC_THREADS / 32) {
+      const int jmax = min(i, r - 1);
+      for (int j = lane; j <= jmax; j += 32)
         W[i * ld + j] = S[(size_t)i * ldS + j];
     }
     __syncthreads();
   }
-  chol_lower_block<1024>(W, ld, r, 1, &flag, invd_sh, nullptr, 0.0, invdiag);
+  chol_lower_block<EKC_THREADS, 4>(W, ld, r, 1, &flag, invd_sh, nullptr, 0.0, invdiag);
   __syncthreads();
   if (use_smem) {
-    for (int e = tid; e < (r + 1) * r; e += 1024) {
-      int i = e / r, j = e % r;
-      if (j <= i)
+    for (int i = wid; i < r; i += EKC_THREADS / 32) {
+      for (int j = lane; j <= i; j += 32)
         S[(size_t)i * ldS + j] = W[i * ld + j];
     }
   }
-  for (int j = tid; j < r; j += 1024)
+  for (int j = tid; j < r; j += EKC_THREADS)
     w[j] = W[(size_t)r * ld + j];
   if (tid == 0 && flag)
     info->not_spd = 1;
@@ -279,7 +280,7 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
   }
   // the residual vector is column n of H's row (TSQR output) or a separate buffer: callers stage it in d_w
   double *invdiag = ctx->d_w + ctx->cfg.max_state; // d_w holds 4 x max_state doubles: [w | 1/diag(L) | ...]
-  k_ekf_chol<<<1, 1024, use_smem ? chol_bytes : 0, ctx->stream>>>(ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
+  k_ekf_chol<<<1, EKC_THREADS, use_smem ? chol_bytes : 0, ctx->stream>>>(ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
   size_t trsm_small = sizeof(double) * ((size_t)TR_ROWS * r + r);
   size_t trsm_full = trsm_small + sizeof(double) * (size_t)r * (size_t)(r | 1);
   int L_in_smem = trsm_full <= 200 * 1024;

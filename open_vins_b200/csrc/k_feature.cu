@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     __syncthreads();
     // ---- chi² = |L^-1 r_o|² on the trailing (rows-3) block
     const int nr = rows - 3;
-    bool spd = chol_lower_block<FT_THREADS>(S + 3 * ldS + 3, ldS, nr, 1, &ishare[1], red + FT_WARPS * 3 + 4);
+    bool spd = chol_lower_block<FT_THREADS, 2>(S + 3 * ldS + 3, ldS, nr, 1, &ishare[1], red + FT_WARPS * 3 + 4);
     double c2 = 0.0;
     for (int i = tid; i < nr; i += FT_THREADS) {
       double y = S[(size_t)rows * ldS + 3 + i];

@@ -103,7 +103,7 @@ __global__ void k_gram_reduce(const double *__restrict__ Gpart, int nslab, int n
 
 // single CTA: semidefinite Cholesky of G[0:n,0:n] with row n (= H'r) carried as right-hand side; writes the
 // upper-triangular R = L' and z = L^-1 H'r into Rout (n x (n+1), row-major)
-__global__ void __launch_bounds__(1024) k_gram_chol(const double *__restrict__ G, int ldG, int n, double *__restrict__ Rout, int ldR,
+__global__ void __launch_bounds__(EKC_THREADS) k_gram_chol(const double *__restrict__ G, int ldG, int n, double *__restrict__ Rout, int ldR,
                                                     double *__restrict__ work, int use_smem) {
   extern __shared__ __align__(16) double gsm[];
   __shared__ int flag;
@@ -114,18 +114,18 @@ __global__ void __launch_bounds__(1024) k_gram_chol(const double *__restrict__ G
   const int ld = use_smem ? (n | 1) : ldG;
   double *W = use_smem ? gsm : work;                 // (n+1) x ld
   double *d0 = use_smem ? (gsm + (size_t)(n + 1) * ld) : (work + (size_t)(n + 1) * ld); // original diagonal
-  for (int e = tid; e < (n + 1) * n; e += 1024) {
+  for (int e = tid; e < (n + 1) * n; e += EKC_THREADS) {
     const int i = e / n, j = e % n;
     if (j <= i)
       W[(size_t)i * ld + j] = G[(size_t)i * ldG + j];
   }
-  for (int j = tid; j < n; j += 1024)
+  for (int j = tid; j < n; j += EKC_THREADS)
     d0[j] = G[(size_t)j * ldG + j];
   __syncthreads();
   // pivots below ~n*eps of the column's own squared norm carry no information (gauge directions, unused variables)
-  chol_lower_block<1024>(W, ld, n, 1, &flag, invd_sh, d0, 1e-13);
+  chol_lower_block<EKC_THREADS, 4>(W, ld, n, 1, &flag, invd_sh, d0, 1e-13);
   __syncthreads();
-  for (int e = tid; e < n * (n + 1); e += 1024) {
+  for (int e = tid; e < n * (n + 1); e += EKC_THREADS) {
     const int i = e / (n + 1), j = e % (n + 1);
     double v = 0.0;
     if (j == n)
@@ -176,7 +176,7 @@ int launch_compress_gram(ovb_ctx *ctx, const double *A, int m, int n, int ldA, d
     attr_set = true;
   }
   double *work = ctx->d_G + (size_t)(nt + 2) * ldG;
-  k_gram_chol<<<1, 1024, use_smem ? smem : 0, ctx->stream>>>(ctx->d_G, ldG, n, Rout, ldR, work, use_smem);
+  k_gram_chol<<<1, EKC_THREADS, use_smem ? smem : 0, ctx->stream>>>(ctx->d_G, ldG, n, Rout, ldR, work, use_smem);
   ctx->n_launch += 3;
   return 3;
 }

@@ -97,6 +97,9 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = 1;
+  CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++)
     CK(cudaEventCreate(&ctx->ev[i]));
   const int ms = ctx->cfg.max_state;
@@ -179,6 +182,12 @@ void ovb_destroy(ovb_ctx *ctx) {
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i])
       cudaEventDestroy(ctx->ev[i]);
+  if (ctx->ev_fork)
+    cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join)
+    cudaEventDestroy(ctx->ev_join);
+  if (ctx->side_stream)
+    cudaStreamDestroy(ctx->side_stream);
   if (ctx->stream && ctx->own_stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -656,7 +665,17 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
   launch_feature_system(ctx, F, bv, ldH, 0, max_M);
   if (ev)
     cudaEventRecord(ev[2], ctx->stream);
-  launch_column_map(ctx, F, bv);
+  // the column bookkeeping (a single serial CTA) only feeds the re-ordering and the EKF update: it runs on the side
+  // stream while the compression owns the GPU, and is joined before its first consumer
+  {
+    cudaEventRecord(ctx->ev_fork, ctx->stream);
+    cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->side_stream;
+    launch_column_map(ctx, F, bv);
+    ctx->stream = main_stream;
+    cudaEventRecord(ctx->ev_join, ctx->side_stream);
+  }
   if (ev)
     cudaEventRecord(ev[3], ctx->stream);
   const int ldR = ldH;
@@ -666,11 +685,14 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
       launch_compress_gram(ctx, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
     else
       launch_tsqr(ctx, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     if (col_order == OVB_COLS_REFERENCE_FIRST_SEEN) {
       launch_reorder_R(ctx, ctx->d_R, n_all, ldR, ctx->d_R2, ldR);
       Rfinal = ctx->d_R2;
     }
   }
+  else
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
   if (ev)
     cudaEventRecord(ev[4], ctx->stream);
   // the Householder path leaves min(m, n) non-zero rows; the Cholesky factor of the Gram matrix is always n x n

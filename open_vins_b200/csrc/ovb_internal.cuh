@@ -83,6 +83,8 @@ struct ovb_ctx {
   int device;
   cudaStream_t stream;
   int own_stream;
+  cudaStream_t side_stream;      // column bookkeeping runs here, concurrently with the compression
+  cudaEvent_t ev_fork, ev_join;
   cudaEvent_t ev[8];
   char err[256];
   // covariance (double buffered for clone/marginalize), row-major with leading dimension ldP

@@ -1,26 +1,26 @@
 // chol.cuh — CTA-cooperative blocked Cholesky used by the chi² gate (k_feature.cu), the EKF update (k_ekf.cu) and the
 // normal-equations compression (k_gram.cu).
-#pragma once
-#include <math.h>
 
-#define EKC_THREADS 512 // threads of the single-CTA Cholesky kernels (16 warps: cheaper barriers, 128 registers per thread)
+#include <math.h>
 
 // 1/sqrt(d) from a float seed refined to full double precision; the library sqrt/divide pair costs several
 // hundred cycles on a single dependent chain, and every Cholesky pivot sits on the critical path of the whole CTA.
-__device__ __forceinline__ double fast_rsqrt(double d) {
+__device__ __forceinline__ double fast_rsqrt_old(double d) {
   if (d > 1e-30 && d < 1e30) {
-    // one third-order (Halley) step: 22 -> ~66 bits
+    // Halley step (cubic: 23 -> ~66 bits) followed by one Newton polish on the residual, two dependent rounds shorter
+    // than three Newton steps
     double y = (double)rsqrtf((float)d);
-    const double e = 1.0 - d * y * y;
-    return y + y * (e * (0.5 + 0.375 * e));
+    double e = 1.0 - d * y * y;
+    y = y + y * e * (0.5 + 0.375 * e);
+    e = 1.0 - d * y * y;
+    return y + 0.5 * y * e;
   }
   return 1.0 / sqrt(d);
 }
 
 // 8x8 diagonal block of the blocked Cholesky, factored in registers by one warp: lane i (< nbk) holds row i and the
-// pivots are broadcast by shuffle (a square-root-free LDL' pivot chain with the scalings batched at the end was
-// measured and is NOT faster here: tools/ubench/chol_bench.cu). Writes L_kk back, the reciprocal pivots 1/L_jj to invd[0..8) (and inv_out[kb..]).
-__device__ __forceinline__ void chol_diag8(double *S, int ld, int kb, int nbk, int *flag, double *invd, const double *diag0, double psd_tol,
+// pivots are broadcast by shuffle. Writes L_kk back, the reciprocal pivots to invd[0..8) (and inv_out[kb..]).
+__device__ __forceinline__ void chol_diag8_old(double *S, int ld, int kb, int nbk, int *flag, double *invd, const double *diag0, double psd_tol,
                                            double *inv_out) {
   const int NBK = 8;
   const int lane = threadIdx.x & 31;
@@ -29,37 +29,38 @@ __device__ __forceinline__ void chol_diag8(double *S, int ld, int kb, int nbk, i
 #pragma unroll
   for (int c = 0; c < NBK; c++)
     x[c] = (c < nbk && c <= li) ? S[(kb + li) * ld + kb + c] : 0.0;
-  {
 #pragma unroll
-    for (int j = 0; j < NBK; j++) {
-      const double d = __shfl_sync(0xffffffffu, x[j], j);
-      bool ok = false;
-      if (j < nbk) {
-        ok = d > 0.0;
-        if (diag0 != nullptr) {
-          ok = d > psd_tol * diag0[kb + j];
-        } else if (!ok && lane == 0) {
-          *flag = 1;
-        }
+  for (int j = 0; j < NBK; j++) {
+    const double d = __shfl_sync(0xffffffffu, x[j], j);
+    double inv = 0.0, ljj = 0.0;
+    if (j < nbk) {
+      bool ok = d > 0.0;
+      if (diag0 != nullptr) {
+        ok = d > psd_tol * diag0[kb + j];
+      } else if (!ok && lane == 0) {
+        *flag = 1;
       }
-      const double inv = ok ? fast_rsqrt(d) : 0.0;
-      if (lane == j)
-        x[j] = d * inv;
-      else if (lane > j)
-        x[j] *= inv;
+      if (ok) {
+        inv = fast_rsqrt_old(d);
+        ljj = d * inv;
+      }
+    }
+    if (lane == j)
+      x[j] = ljj;
+    else if (lane > j)
+      x[j] *= inv;
 #pragma unroll
-      for (int c = 0; c < NBK; c++) {
-        if (c > j) {
-          const double lcj = __shfl_sync(0xffffffffu, x[j], c);
-          if (lane >= c)
-            x[c] -= x[j] * lcj;
-        }
+    for (int c = 0; c < NBK; c++) {
+      if (c > j) {
+        const double lcj = __shfl_sync(0xffffffffu, x[j], c);
+        if (lane >= c)
+          x[c] -= x[j] * lcj;
       }
-      if (lane == 0) {
-        invd[j] = inv;
-        if (inv_out != nullptr && j < nbk)
-          inv_out[kb + j] = inv;
-      }
+    }
+    if (lane == 0) {
+      invd[j] = inv;
+      if (inv_out != nullptr && j < nbk)
+        inv_out[kb + j] = inv; // reciprocal pivots for later triangular solves
     }
   }
   if (lane < nbk) {
@@ -78,10 +79,9 @@ __device__ __forceinline__ void chol_diag8(double *S, int ld, int kb, int nbk, i
 // invd: 16 doubles of shared memory scratch. inv_out (optional, n doubles): receives 1/L[j][j]. Returns true when no
 // strict-mode pivot failed.
 // Look-ahead: during the trailing update of block step k, warp 0 updates only the next 8x8 diagonal block and factors
-// it straight away, so the serial pivot chain hides behind the other warps' update. RB rows per warp are updated
-// together (the panel rows L[j][kb..] are loaded once per RB rows and the RB FMA chains interleave).
-template <int THREADS, int RB>
-__device__ bool chol_lower_block(double *S, int ld, int n, int extra, int *flag, double *invd, const double *diag0 = nullptr,
+// it straight away, so the serial pivot chain (8 dependent rsqrt/shuffle rounds) hides behind the other warps' update.
+template <int THREADS>
+__device__ bool chol_lower_block_old(double *S, int ld, int n, int extra, int *flag, double *invd, const double *diag0 = nullptr,
                                  double psd_tol = 0.0, double *inv_out = nullptr) {
   const int NWARPS = THREADS / 32;
   const int NBK = 8;
@@ -89,18 +89,12 @@ __device__ bool chol_lower_block(double *S, int ld, int n, int extra, int *flag,
   if (n <= 0)
     return *flag == 0;
   if (wid == 0)
-    chol_diag8(S, ld, 0, min(NBK, n), flag, invd, diag0, psd_tol, inv_out);
+    chol_diag8_old(S, ld, 0, min(NBK, n), flag, invd, diag0, psd_tol, inv_out);
   __syncthreads();
-#ifdef CHOL_PROBE
-  long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0, pt4 = 0;
-#endif
   int par = 0; // invd is double-buffered: the look-ahead writes the next step's pivots while nothing reads this step's
   for (int kb = 0; kb < n; kb += NBK) {
     const int nbk = min(NBK, n - kb);
     const double *invk = invd + 8 * par;
-#ifdef CHOL_PROBE
-    pt0 = clock64();
-#endif
     // ---- panel rows below: x L_kk' = S[i][kb..kb+nbk), using the stored reciprocal pivots (no divisions)
     for (int i = kb + nbk + tid; i < n + extra; i += THREADS) {
       double x[NBK];
@@ -120,13 +114,7 @@ __device__ bool chol_lower_block(double *S, int ld, int n, int extra, int *flag,
         if (c < nbk)
           S[i * ld + kb + c] = x[c];
     }
-#ifdef CHOL_PROBE
-    pt1 = clock64();
-#endif
     __syncthreads();
-#ifdef CHOL_PROBE
-    pt2 = clock64();
-#endif
     // ---- trailing update: S[i][j] -= sum_t S[i][kb+t] S[j][kb+t], kb+nbk <= j <= min(i, n-1)
     const int first = kb + nbk;
     const int nb2 = min(NBK, n - first); // rows of the next diagonal block (<= 0 when this was the last step)
@@ -143,56 +131,32 @@ __device__ bool chol_lower_block(double *S, int ld, int n, int extra, int *flag,
         }
       }
       __syncwarp();
-      chol_diag8(S, ld, first, nb2, flag, invd + 8 * (par ^ 1), diag0, psd_tol, inv_out);
+      chol_diag8_old(S, ld, first, nb2, flag, invd + 8 * (par ^ 1), diag0, psd_tol, inv_out);
     }
     {
-      // remaining rows over warps 1.. (all warps when there is no look-ahead work or only one warp), RB rows at a time
+      // remaining rows over warps 1.. (all warps when there is no look-ahead work or only one warp)
       const bool la = (nb2 > 0) && (NWARPS > 1);
       const int w0 = la ? wid - 1 : wid, nw = la ? NWARPS - 1 : NWARPS;
       const int istart = first + max(nb2, 0);
-      const int iend = n + extra;
       if (w0 >= 0) {
-        for (int ib = istart + RB * w0; ib < iend; ib += RB * nw) {
-          double li[RB][NBK];
+        for (int i = istart + w0; i < n + extra; i += nw) {
+          double li[NBK];
 #pragma unroll
-          for (int r = 0; r < RB; r++)
+          for (int t = 0; t < NBK; t++)
+            li[t] = (t < nbk) ? S[i * ld + kb + t] : 0.0;
+          const int jmax = min(i, n - 1);
+          for (int j = first + lane; j <= jmax; j += 32) {
+            // eight products summed as a tree (3 dependent adds instead of an 8-long FMA chain: FP64 latency is ~19 cycles)
+            double pr[NBK];
 #pragma unroll
             for (int t = 0; t < NBK; t++)
-              li[r][t] = (t < nbk && ib + r < iend) ? S[(ib + r) * ld + kb + t] : 0.0;
-          const int jtop = min(ib + RB - 1, n - 1);
-          for (int j = first + lane; j <= jtop; j += 32) {
-            double lj[NBK];
-#pragma unroll
-            for (int t = 0; t < NBK; t++)
-              lj[t] = (t < nbk) ? S[j * ld + kb + t] : 0.0;
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-              const int i = ib + r;
-              if (i < iend && j <= min(i, n - 1)) {
-                // four short chains per row (depth 4 with or without FMA contraction); the RB rows are independent
-                double a0 = li[r][0] * lj[0], a1 = li[r][1] * lj[1], a2 = li[r][2] * lj[2], a3 = li[r][3] * lj[3];
-                a0 += li[r][4] * lj[4];
-                a1 += li[r][5] * lj[5];
-                a2 += li[r][6] * lj[6];
-                a3 += li[r][7] * lj[7];
-                a0 += a2;
-                a1 += a3;
-                S[i * ld + j] -= a0 + a1;
-              }
-            }
+              pr[t] = (t < nbk) ? li[t] * S[j * ld + kb + t] : 0.0;
+            S[i * ld + j] -= ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
           }
         }
       }
     }
-#ifdef CHOL_PROBE
-    pt3 = clock64();
-#endif
     __syncthreads();
-#ifdef CHOL_PROBE
-    pt4 = clock64();
-    if ((kb == 0 || kb == 40) && (tid == 0 || tid == 32 || tid == THREADS - 1))
-      printf("kb=%d tid=%d panel %lld bar %lld trail/diag %lld bar %lld\n", kb, tid, pt1 - pt0, pt2 - pt1, pt3 - pt2, pt4 - pt3);
-#endif
     par ^= 1;
   }
   return *flag == 0;
