@@ -56,6 +56,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_host_test(force: bool = False) -> str:
+    """Compile tests/cpp/host_shim_test.cpp (the C++ host mirror of include/ovb200_host.hpp driving one update) against
+    the in-tree library; returns the executable's path."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "cpp", "host_shim_test.cpp")
+    exe = os.path.join(root, "tests", "cpp", "host_shim_test")
+    deps = [src, os.path.join(root, "include", "ovb200_host.hpp"), os.path.join(root, "include", "ovb200.h"), OUT]
+    if force or _stale(exe, deps):
+        cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-I", os.path.join(root, "include"), src, "-L", HERE, "-lovb200",
+               "-Wl,-rpath,$ORIGIN/../../open_vins_b200", "-o", exe]
+        subprocess.check_call(cmd)
+    return exe
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)

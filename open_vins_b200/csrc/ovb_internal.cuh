@@ -5,7 +5,7 @@
 #include <stdint.h>
 
 #define OVB_MAX_MEAS_PER_FEAT 128 // K*C of config 4 is 124 (SURVEY.md §8 sizes table)
-#define OVB_MAX_COLS 400          // 6*OVB_MAX_CLONES + 14*OVB_MAX_CAMS
+#define OVB_MAX_COLS 512          // >= 6*OVB_MAX_CLONES + 14*OVB_MAX_CAMS; also the widest H of ovb_ekf_update (config 5: n = 500)
 #define OVB_NB 16                 // TSQR panel width
 #define OVB_CR 256                // TSQR rows per chunk
 
