@@ -3,6 +3,24 @@
 #pragma once
 #include <math.h>
 
+// Stage the lower triangle of rows [0, nrows) (columns j <= min(i, ncols-1)) of a row-major global matrix into shared
+// memory with 8-byte cp.async: every load of the CTA is in flight at once instead of one L2 round trip per loop trip.
+// Call from all threads; ends with wait + __syncthreads().
+template <int THREADS>
+__device__ __forceinline__ void stage_lower_async(double *dst, int ldd, const double *__restrict__ src, size_t lds, int nrows, int ncols) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = wid; i < nrows; i += THREADS / 32) {
+    const int jmax = min(i, ncols - 1);
+    for (int j = lane; j <= jmax; j += 32) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + (size_t)i * ldd + j);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + (size_t)i * lds + j) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
 #define EKC_THREADS 512 // threads of the single-CTA Cholesky kernels (16 warps: cheaper barriers, 128 registers per thread)
 
 // 1/sqrt(d) from a float seed refined to full double precision; the library sqrt/divide pair costs several

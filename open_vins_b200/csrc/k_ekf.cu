@@ -97,13 +97,7 @@ __global__ void __launch_bounds__(EKC_THREADS) k_ekf_chol(double *__restrict__ S
   if (use_smem) {
     ld = r | 1;
     W = chol_sm;
-    // warp per row, lanes over the lower-triangle columns (coalesced; no integer division on the load path)
-    for (int i = wid; i <= r; i += EKC_THREADS / 32) {
-      const int jmax = min(i, r - 1);
-      for (int j = lane; j <= jmax; j += 32)
-        W[i * ld + j] = S[(size_t)i * ldS + j];
-    }
-    __syncthreads();
+    stage_lower_async<EKC_THREADS>(W, ld, S, (size_t)ldS, r + 1, r);
   }
   chol_lower_block<EKC_THREADS, 4>(W, ld, r, 1, &flag, invd_sh, nullptr, 0.0, invdiag);
   __syncthreads();
@@ -134,14 +128,10 @@ __global__ void __launch_bounds__(32 * TR_ROWS) k_ekf_trsm(const double *__restr
   double *Ls = inv_s + r;
   for (int e = threadIdx.x; e < r; e += 32 * TR_ROWS)
     inv_s[e] = invdiag[e];
-  if (L_in_smem) {
-    for (int e = threadIdx.x; e < r * r; e += 32 * TR_ROWS) {
-      const int i = e / r, j = e % r;
-      if (j <= i)
-        Ls[i * ldl + j] = L[(size_t)i * ldL + j];
-    }
-  }
-  __syncthreads();
+  if (L_in_smem)
+    stage_lower_async<32 * TR_ROWS>(Ls, ldl, L, (size_t)ldL, r, r);
+  else
+    __syncthreads();
   const double *Lp = L_in_smem ? Ls : L;
   const int lp = L_in_smem ? ldl : ldL;
   const int a = blockIdx.x * TR_ROWS + wid;
