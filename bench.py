@@ -130,6 +130,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+_SAVED_STDOUT = None
+
+
+def quiet_stdout():
+    """N>1: NCCL prints its version banner on stdout at communicator creation. The contract is ONE JSON line on stdout,
+    so file descriptor 1 is pointed at stderr until the line is emitted."""
+    global _SAVED_STDOUT
+    if _SAVED_STDOUT is None:
+        sys.stdout.flush()
+        _SAVED_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    global _SAVED_STDOUT
+    sys.stdout.flush()
+    if _SAVED_STDOUT is not None:
+        os.dup2(_SAVED_STDOUT, 1)
+        os.close(_SAVED_STDOUT)
+        _SAVED_STDOUT = None
+    print(json.dumps(line), flush=True)
+
+
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum per k_tsqr_level launch from the committed `ncu --set full` capture
     (profiles/ncu_tsqr_r01.csv: one level-0 and one cluster level-1 launch of two consecutive panels). ncu flushes the
@@ -158,7 +181,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--features", type=int, default=WORKLOAD["n_feats"],
+                    help="features per update (default: BASELINE config 2 = 400; 4096 = the config-3 sweep point, for scaling studies)")
     args = ap.parse_args()
+    if args.features != WORKLOAD["n_feats"]:
+        global WORKLOAD_NAME
+        WORKLOAD_NAME = WORKLOAD_NAME.replace("400 MSCKF features/update", f"{args.features} MSCKF features/update (NOT the BASELINE config-2 size)")
+        WORKLOAD["n_feats"] = args.features
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,6 +204,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        quiet_stdout()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     case = sim.make_update_case(**WORKLOAD)
@@ -182,9 +212,9 @@ def main():
     F = case.feats.n_feats
     if world > 1:
         from open_vins_b200 import multigpu
-        return multigpu.bench_sharded(args, rank, local_rank, world, case, opts, WORKLOAD_NAME, ClockSampler, peaks)
+        return multigpu.bench_sharded(args, rank, local_rank, world, case, opts, WORKLOAD_NAME, ClockSampler, peaks, emit)
 
-    eng = capi.Engine(max_state=256, max_feats=1024, max_meas=1024 * 48, device=local_rank)
+    eng = capi.Engine(max_state=256, max_feats=max(1024, F), max_meas=max(1024, F) * 48, device=local_rank)
     eng.set_replay(True)
     K, W = args.steps, args.warmup
 

@@ -125,6 +125,10 @@ __global__ void __launch_bounds__(QR_THREADS)
   const bool clustered = csize > 1;
   const int crank = clustered ? chunk : 0; // gridDim.x == cluster size
   const bool has_pivots = (crank == 0);    // the pivot rows of a clustered block all live in its first chunk
+  // Programmatic dependent launch: let the next (panel, level) kernel of the chain be scheduled right away — its CTAs
+  // run their prologue on the SMs this grid leaves idle and then block in griddepcontrol.wait until this grid has
+  // completed and flushed. Everything before OUR wait below touches only shared memory.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // my exchange slot and mbarriers as seen by the peer this lane serves (lane group index pg = tid & 15 -> peer rank)
   unsigned peer_xch = 0, peer_bar = 0, peer_yx = 0;
   if (clustered) {
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(QR_THREADS)
       g = (g / nbp) * (l == 1 ? cr0 : QR_CR) + (g % nbp);
     sm.rowidx[tid] = c0 + g;
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory"); // the previous kernel's writes to A / W are visible from here on
   // ---- panel factorisation. Ownership: thread (j = tid>>4, g = tid&15) holds rows 16g..16g+15 of panel column j in
   // registers, so a half-warp owns one column and every column dot product is 16 FMAs + a 4-level half-warp butterfly.
   // The 16 rows sit in a rotating window (after k rotations slot t holds local row (k + t) mod 16): the pivot row of
@@ -606,23 +611,29 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
         gy = 1;
       const double *Win = level > 0 ? ctx->d_W[(level - 1) & 1] : nullptr;
       double *Wout = ctx->d_W[level & 1];
-      if (clustered) {
+      {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(gx, gy);
         cfg.blockDim = dim3(QR_THREADS);
         cfg.dynamicSmemBytes = sizeof(QrSmem);
         cfg.stream = ctx->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = QR_CLUSTER;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
+        cudaLaunchAttribute at[2];
+        int na = 0;
+        if (ctx->tsqr_pdl) { // overlap this kernel's launch + prologue with the tail of the previous one
+          at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          at[na].val.programmaticStreamSerializationAllowed = 1;
+          na++;
+        }
+        if (clustered) {
+          at[na].id = cudaLaunchAttributeClusterDimension;
+          at[na].val.clusterDim.x = QR_CLUSTER;
+          at[na].val.clusterDim.y = 1;
+          at[na].val.clusterDim.z = 1;
+          na++;
+        }
         cfg.attrs = at;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_tsqr_level, A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, 1, (int)QR_CLUSTER, cr0);
-      } else {
-        dim3 grid(gx, gy);
-        k_tsqr_level<<<grid, QR_THREADS, sizeof(QrSmem), ctx->stream>>>(A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, last, 1, cr0);
+        cfg.numAttrs = na;
+        cudaLaunchKernelEx(&cfg, k_tsqr_level, A, ldA, nt, c0, nbp, level, len, Win, Wout, Rout, ldR, last, clustered ? (int)QR_CLUSTER : 1, cr0);
       }
       ctx->n_launch++;
       ctx->n_launch_tsqr_level++;

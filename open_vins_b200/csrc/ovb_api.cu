@@ -94,6 +94,8 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
   {
     const char *e = getenv("OVB_TSQR_CLUSTER");
     ctx->tsqr_cluster = e ? atoi(e) : 1;
+    const char *e2 = getenv("OVB_TSQR_PDL");
+    ctx->tsqr_pdl = e2 ? atoi(e2) : 1;
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = 1;

@@ -132,6 +132,7 @@ struct ovb_ctx {
   int dump_rows;
   int max_rows;
   int sm_count;
+  int tsqr_pdl;     // programmatic dependent launch between the TSQR level kernels (OVB_TSQR_PDL=0 disables: A/B timing only)
   int tsqr_cluster; // upper TSQR levels as one thread-block cluster (OVB_TSQR_CLUSTER=0 disables: A/B timing only)
   float stage_ms[6];
   // replay of the last update on device-resident inputs (bench: `value` leg; see ovb_msckf_replay)

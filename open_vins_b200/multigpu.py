@@ -79,14 +79,15 @@ def sharded_update(backend, dist, frame, feats, opts, rank: int, world: int):
     return st, out, dx, stats, (f0, f1)
 
 
-def bench_sharded(args, rank, local_rank, world, case, opts, workload_name, ClockSampler, peaks):
+def bench_sharded(args, rank, local_rank, world, case, opts, workload_name, ClockSampler, peaks, emit=None):
     """bench.py's N>1 leg: the config-2 update with its 400 features sharded over N GPUs (strong scaling)."""
     import torch
     import torch.distributed as dist
     from . import capi
 
     dev = torch.device("cuda", local_rank)
-    eng = capi.Engine(max_state=256, max_feats=1024, max_meas=1024 * 48, device=local_rank)
+    cap = max(1024, case.feats.n_feats)
+    eng = capi.Engine(max_state=256, max_feats=cap, max_meas=cap * 48, device=local_rank)
     backend = EngineBackend(eng, dev)
     K, W = args.steps, args.warmup
     F = case.feats.n_feats
@@ -137,6 +138,6 @@ def bench_sharded(args, rank, local_rank, world, case, opts, workload_name, Cloc
             "roofline": {"bound": "hbm", "achieved": None, "peak": peaks()[0], "unit": "GB/s", "frac": None, "traffic": None,
                          "note": "see the N=1 line: the per-rank kernels are the same; at N>1 the step is latency-bound (NCCL + second-level QR)"},
         }
-        print(json.dumps(line), flush=True)
+        (emit or (lambda l: print(json.dumps(l), flush=True)))(line)
     eng.close()
     dist.destroy_process_group()
