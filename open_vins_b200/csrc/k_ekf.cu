@@ -18,6 +18,7 @@
 __global__ void __launch_bounds__(256) k_ekf_gemm(int mode, const double *__restrict__ P, int ldP, const double *__restrict__ H, int ldH,
                                                   const double *__restrict__ Min, int ldM, const DevUpdateInfo *__restrict__ info, int X, int Y,
                                                   int K, double *__restrict__ Cout, int ldC, double sigma2, const double *__restrict__ Rdiag) {
+  OVB_PDL_ENTER();
   __shared__ double As[EK_T][EK_T + 1]; // [j][x]
   __shared__ double Bs[EK_T][EK_T + 1]; // [j][y]
   const int x0 = blockIdx.x * EK_T, y0 = blockIdx.y * EK_T;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) k_ekf_gemm(int mode, const double *__rest
 // it fits, else in place in global memory (L2).
 __global__ void __launch_bounds__(EKC_THREADS) k_ekf_chol(double *__restrict__ S, int ldS, int r, const double *__restrict__ res, double *__restrict__ w,
                                                    double *__restrict__ invdiag, DevUpdateInfo *__restrict__ info, int use_smem) {
+  OVB_PDL_ENTER();
   extern __shared__ __align__(16) double chol_sm[];
   __shared__ int flag;
   __shared__ double invd_sh[16];
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(EKC_THREADS) k_ekf_chol(double *__restrict__ S
 __global__ void __launch_bounds__(32 * TR_ROWS) k_ekf_trsm(const double *__restrict__ M, int ldM, const double *__restrict__ L, int ldL,
                                                            const double *__restrict__ invdiag, int N, int r, double *__restrict__ Yout, int ldY,
                                                            int L_in_smem) {
+  OVB_PDL_ENTER();
   extern __shared__ __align__(16) double tsm[]; // [TR_ROWS][r] y rows, then r reciprocal pivots, then L (r x ldl) when it fits
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ldl = r | 1;
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(32 * TR_ROWS) k_ekf_trsm(const double *__restr
 // P <- sym_U(P - Y Y'): upper tiles only, mirrored on write; negative-diagonal check; dx = Y w on the diagonal tiles' rows
 __global__ void __launch_bounds__(256) k_ekf_downdate(double *__restrict__ P, int ldP, const double *__restrict__ Yin, int ldY, int N, int r,
                                                       const double *__restrict__ w, double *__restrict__ dx, DevUpdateInfo *__restrict__ info) {
+  OVB_PDL_ENTER();
   __shared__ double As[EK_T][EK_T + 1]; // [k][a]
   __shared__ double Bs[EK_T][EK_T + 1]; // [k][b]
   const int a0 = blockIdx.x * EK_T, b0 = blockIdx.y * EK_T;
@@ -241,6 +245,7 @@ __global__ void __launch_bounds__(256) k_ekf_downdate(double *__restrict__ P, in
 }
 
 __global__ void k_ekf_prep(DevUpdateInfo *info) {
+  OVB_PDL_ENTER();
   info->neg_diag_index = 0x7fffffff;
   info->not_spd = 0;
   info->nonfinite = 0;
@@ -253,13 +258,13 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
   const int N = ctx->N;
   const int ld = ctx->ldP;
   double *P = ctx->P[ctx->cur];
-  k_ekf_prep<<<1, 1, 0, ctx->stream>>>(ctx->d_info);
+  ovb_launch(ctx, k_ekf_prep, dim3(1), dim3(1), (size_t)(0), ctx->d_info);
   if (r <= 0 || n <= 0)
     return;
   dim3 g0((N + EK_T - 1) / EK_T, (r + EK_T - 1) / EK_T);
-  k_ekf_gemm<<<g0, 256, 0, ctx->stream>>>(0, P, ld, H, ldHm, nullptr, 0, ctx->d_info, N, r, n, ctx->d_M, ld, 0.0, nullptr);
+  ovb_launch(ctx, k_ekf_gemm, dim3(g0), dim3(256), (size_t)(0), 0, P, ld, H, ldHm, nullptr, 0, ctx->d_info, N, r, n, ctx->d_M, ld, 0.0, nullptr);
   dim3 g1((r + EK_T - 1) / EK_T, (r + EK_T - 1) / EK_T);
-  k_ekf_gemm<<<g1, 256, 0, ctx->stream>>>(1, P, ld, H, ldHm, ctx->d_M, ld, ctx->d_info, r, r, n, ctx->d_S, ld, sigma2, Rdiag_dev);
+  ovb_launch(ctx, k_ekf_gemm, dim3(g1), dim3(256), (size_t)(0), 1, P, ld, H, ldHm, ctx->d_M, ld, ctx->d_info, r, r, n, ctx->d_S, ld, sigma2, Rdiag_dev);
   size_t chol_bytes = sizeof(double) * (size_t)(r + 1) * (size_t)(r | 1);
   int use_smem = chol_bytes <= 200 * 1024;
   static bool attr_set = false;
@@ -270,14 +275,14 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
   }
   // the residual vector is column n of H's row (TSQR output) or a separate buffer: callers stage it in d_w
   double *invdiag = ctx->d_w + ctx->cfg.max_state; // d_w holds 4 x max_state doubles: [w | 1/diag(L) | ...]
-  k_ekf_chol<<<1, EKC_THREADS, use_smem ? chol_bytes : 0, ctx->stream>>>(ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
+  ovb_launch(ctx, k_ekf_chol, dim3(1), dim3(EKC_THREADS), (size_t)(use_smem ? chol_bytes : 0), ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
   size_t trsm_small = sizeof(double) * ((size_t)TR_ROWS * r + r);
   size_t trsm_full = trsm_small + sizeof(double) * (size_t)r * (size_t)(r | 1);
   int L_in_smem = trsm_full <= 200 * 1024;
-  k_ekf_trsm<<<(N + TR_ROWS - 1) / TR_ROWS, 32 * TR_ROWS, L_in_smem ? trsm_full : trsm_small, ctx->stream>>>(ctx->d_M, ld, ctx->d_S, ld, invdiag, N,
+  ovb_launch(ctx, k_ekf_trsm, dim3((N + TR_ROWS - 1) / TR_ROWS), dim3(32 * TR_ROWS), (size_t)(L_in_smem ? trsm_full : trsm_small), ctx->d_M, ld, ctx->d_S, ld, invdiag, N,
                                                                                                               r, ctx->d_Y, ld, L_in_smem);
   dim3 g2((N + EK_T - 1) / EK_T, (N + EK_T - 1) / EK_T);
-  k_ekf_downdate<<<g2, 256, 0, ctx->stream>>>(P, ld, ctx->d_Y, ld, N, r, ctx->d_w, ctx->d_dx, ctx->d_info);
+  ovb_launch(ctx, k_ekf_downdate, dim3(g2), dim3(256), (size_t)(0), P, ld, ctx->d_Y, ld, N, r, ctx->d_w, ctx->d_dx, ctx->d_info);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -391,7 +396,7 @@ __global__ void k_prop_write(double *P, int ld, int N, int new_off, int p, const
 void launch_cov_propagate(ovb_ctx *ctx, int new_off, int p, int q, const int *old_idx_dev, const double *Phi_dev, const double *Q_dev) {
   double *P = ctx->P[ctx->cur];
   int N = ctx->N, ld = ctx->ldP;
-  k_ekf_prep<<<1, 1, 0, ctx->stream>>>(ctx->d_info);
+  ovb_launch(ctx, k_ekf_prep, dim3(1), dim3(1), (size_t)(0), ctx->d_info);
   k_prop_C<<<(N * p + 255) / 256, 256, 0, ctx->stream>>>(P, ld, N, p, q, old_idx_dev, Phi_dev, ctx->d_M, ld);
   k_prop_PCP<<<(p * p + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_M, ld, p, q, old_idx_dev, Phi_dev, Q_dev, ctx->d_S, ld);
   k_prop_write<<<(N * p + 255) / 256, 256, 0, ctx->stream>>>(P, ld, N, new_off, p, ctx->d_M, ld, ctx->d_S, ld, ctx->d_info);

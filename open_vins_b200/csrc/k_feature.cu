@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
                      const double *__restrict__ P, int ldP, const double *__restrict__ chi2_table, double *__restrict__ Hs, int ldH,
                      unsigned char *__restrict__ feat_order, int mode, int maxM, int nblk, double *__restrict__ scratch,
                      size_t scratch_per_cta, double *__restrict__ dump, int ld_dump, int dump_rows) {
+  OVB_PDL_ENTER();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ovb_opts &op = dop->o;
   const int n_all = fr->n_all;
@@ -896,7 +897,7 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
     scratch = ctx->d_scratch;
   }
   int dump_rows = ctx->dump_rows; // rows of the current dump (set by ovb_feature_jacobians)
-  k_feature_system<<<grid, FT_THREADS, smem, ctx->stream>>>(ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv, ctx->P[ctx->cur], ctx->ldP,
+  ovb_launch(ctx, k_feature_system, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv, ctx->P[ctx->cur], ctx->ldP,
                                                             ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk,
                                                             scratch, ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
 }

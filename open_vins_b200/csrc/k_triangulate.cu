@@ -8,6 +8,7 @@
 
 // R_GtoCi = R_ItoC * R_GtoI ; p_CiinG = p_IinG - R_GtoCi' * p_IinC   (UpdaterMSCKF.cpp:106-107)
 __global__ void k_cam_poses(const DevFrame *fr, DevCamPoses *cc) {
+  OVB_PDL_ENTER();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int total = fr->n_cams * fr->n_clones;
   if (idx >= total)
@@ -67,6 +68,7 @@ __device__ __forceinline__ double lm_cost(const DevCamPoses *fr, const BlobView 
 
 __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restrict__ fr, const DevOpts *__restrict__ dop,
                                                      DevFeat *__restrict__ feats, int n_feats, BlobView bv) {
+  OVB_PDL_ENTER();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= n_feats)
@@ -296,5 +298,5 @@ void launch_triangulate(ovb_ctx *ctx, int n_feats, BlobView bv) {
     return;
   int warps_per_cta = 8;
   int grid = (n_feats + warps_per_cta - 1) / warps_per_cta;
-  k_triangulate<<<grid, warps_per_cta * 32, 0, ctx->stream>>>(ctx->d_cc, ctx->d_opts, ctx->d_feat, n_feats, bv);
+  ovb_launch(ctx, k_triangulate, dim3(grid), dim3(warps_per_cta * 32), (size_t)(0), ctx->d_cc, ctx->d_opts, ctx->d_feat, n_feats, bv);
 }

@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(QR_THREADS)
 
 // copy the trailing parts of the finished R rows out of A, zero the strict lower part, normalise diag >= 0
 __global__ void k_tsqr_assemble(const double *__restrict__ A, int ldA, int m, int n, double *__restrict__ Rout, int ldR) {
+  OVB_PDL_ENTER();
   int i = blockIdx.x; // row of R
   if (i >= n)
     return;
@@ -644,7 +645,7 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
       level++;
     }
   }
-  k_tsqr_assemble<<<n, 128, 0, ctx->stream>>>(A, ldA, m, n, Rout, ldR);
+  ovb_launch(ctx, k_tsqr_assemble, dim3(n), dim3(128), (size_t)(0), A, ldA, m, n, Rout, ldR);
   ctx->n_launch++;
 }
 
@@ -737,6 +738,7 @@ void launch_column_map(ovb_ctx *ctx, int n_feats, BlobView bv) {
 // B[i][q] = Rin[i][col_canon[q]] for q < n_all, B[i][n_all] = Rin[i][n_all] (residual)
 __global__ void k_gather_cols(const double *__restrict__ Rin, int ldRin, int n_all, const DevUpdateInfo *__restrict__ info, double *__restrict__ B,
                               int ldB) {
+  OVB_PDL_ENTER();
   int i = blockIdx.x;
   for (int q = threadIdx.x; q <= n_all; q += blockDim.x) {
     int src = (q < n_all) ? info->col_canon[q] : n_all;
@@ -747,7 +749,7 @@ __global__ void k_gather_cols(const double *__restrict__ Rin, int ldRin, int n_a
 void launch_reorder_R(ovb_ctx *ctx, const double *Rin, int n_all, int ldRin, double *Rout, int ldRout) {
   // permuted copy into the (now free) staging matrix, then the same TSQR re-triangularises it
   int ldB = ldRin;
-  k_gather_cols<<<n_all, 128, 0, ctx->stream>>>(Rin, ldRin, n_all, ctx->d_info, ctx->d_Hs, ldB);
+  ovb_launch(ctx, k_gather_cols, dim3(n_all), dim3(128), (size_t)(0), Rin, ldRin, n_all, ctx->d_info, ctx->d_Hs, ldB);
   ctx->n_launch++;
   launch_tsqr(ctx, ctx->d_Hs, n_all, n_all, ldB, Rout, ldRout);
 }

@@ -641,6 +641,7 @@ ovb_status ovb_feature_jacobians(ovb_ctx *ctx, const ovb_frame *frame, const ovb
 
 // copy column n (the residual z) of the n x (n+1) R into d_w so the Cholesky kernel can append it
 __global__ void k_take_z(const double *R, int ldR, int rows, int col, double *w) {
+  OVB_PDL_ENTER();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows)
     w[i] = R[(size_t)i * ldR + col];
@@ -700,7 +701,7 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
   // the Householder path leaves min(m, n) non-zero rows; the Cholesky factor of the Gram matrix is always n x n
   const int r = (ctx->h_opts->o.compress == OVB_COMPRESS_NORMAL_EQUATIONS && m_total > 0) ? n_all : std::min(m_total, n_all);
   if (r > 0) {
-    k_take_z<<<(r + 127) / 128, 128, 0, ctx->stream>>>(Rfinal, ldR, r, n_all, ctx->d_w);
+    ovb_launch(ctx, k_take_z, dim3((r + 127) / 128), dim3(128), (size_t)(0), Rfinal, ldR, r, n_all, ctx->d_w);
     launch_ekf_update(ctx, Rfinal, ldR, r, n_all, false, ctx->h_opts->sigma_pix_sq, nullptr);
     ctx->n_launch += 7; // take_z + prep, 2 gemm, chol, trsm, downdate
   } else {
@@ -928,7 +929,7 @@ ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_block
     launch_tsqr(ctx, stacked_dev, n_blocks * n_all, n_all, ld, ctx->d_R, ld);
     Rfinal = ctx->d_R;
   }
-  k_take_z<<<(n_all + 127) / 128, 128, 0, ctx->stream>>>(Rfinal, ld, n_all, n_all, ctx->d_w);
+  ovb_launch(ctx, k_take_z, dim3((n_all + 127) / 128), dim3(128), (size_t)(0), Rfinal, ld, n_all, n_all, ctx->d_w);
   launch_ekf_update(ctx, Rfinal, ld, n_all, n_all, false, ctx->h_opts->sigma_pix_sq, nullptr);
   ctx->n_launch += 7;
   cudaEventRecord(ctx->ev[5], ctx->stream);
@@ -1110,7 +1111,7 @@ ovb_status ovb_ekf_update(ovb_ctx *ctx, const int *off, const int *sz, int nvar,
     Hdev = ctx->d_R;
     rr = n;
   }
-  k_take_z<<<(rr + 127) / 128, 128, 0, ctx->stream>>>(Hdev, ld, rr, n, ctx->d_w);
+  ovb_launch(ctx, k_take_z, dim3((rr + 127) / 128), dim3(128), (size_t)(0), Hdev, ld, rr, n, ctx->d_w);
   // k_take_z reads column n: for the uncompressed case that is the staged residual column
   launch_ekf_update(ctx, Hdev, ld, rr, n, false, s2, nullptr);
   OVB_CUDA_CHECK(ctx, cudaGetLastError());

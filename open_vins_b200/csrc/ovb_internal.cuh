@@ -177,3 +177,32 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r_max, int n
 void launch_cov_clone(ovb_ctx *ctx, int old_off, int size, const double *dnc_dt_dev, int dt_off);
 void launch_cov_marginalize(ovb_ctx *ctx, int off, int size);
 void launch_cov_propagate(ovb_ctx *ctx, int new_off, int p, int q, const int *old_idx_dev, const double *Phi_dev, const double *Q_dev);
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
+// Every kernel of the update pipeline starts with OVB_PDL_ENTER(): it lets the NEXT kernel of the stream be scheduled
+// while this one runs (its CTAs become resident on idle SMs and block), then waits until the PREVIOUS kernel has
+// completed and flushed. Semantics are those of ordinary stream order; what is saved is the launch latency between the
+// ~30 dependent, latency-bound kernels of one update. Both instructions are no-ops in a kernel launched without the
+// attribute. ovb_launch() adds the attribute when ctx->tsqr_pdl is set (OVB_TSQR_PDL=0 disables it).
+#define OVB_PDL_ENTER()                                                     \
+  do {                                                                      \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");         \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                      \
+  } while (0)
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline void ovb_launch(ovb_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = ctx->tsqr_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
