@@ -121,6 +121,11 @@ class FrameArrays:
         self.n_cams = int(self.cam_model.shape[0])
 
     def struct(self) -> ovb_frame:
+        if getattr(self, "_st", None) is None:
+            self._st = self._make_struct()
+        return self._st
+
+    def _make_struct(self) -> ovb_frame:
         return ovb_frame(self.n_clones, self.n_cams, _ptr(self.clone_R, c_double_p), _ptr(self.clone_p, c_double_p),
                          _ptr(self.clone_R_fej, c_double_p), _ptr(self.clone_p_fej, c_double_p),
                          _ptr(self.clone_off, c_int_p), _ptr(self.cam_R, c_double_p), _ptr(self.cam_p, c_double_p),
@@ -144,6 +149,11 @@ class FeatArrays:
         assert int(self.meas_off[-1]) == self.n_meas
 
     def struct(self) -> ovb_feat_batch:
+        if getattr(self, "_st", None) is None:
+            self._st = self._make_struct()
+        return self._st
+
+    def _make_struct(self) -> ovb_feat_batch:
         return ovb_feat_batch(self.n_feats, self.n_meas, _ptr(self.meas_off, c_int_p), _ptr(self.cam, c_u8_p),
                               _ptr(self.clone, c_u16_p), _ptr(self.uv, c_float_p), _ptr(self.uvn, c_float_p),
                               _ptr(self.cam_keys_off, c_int_p), _ptr(self.cam_keys, c_u8_p))

@@ -267,11 +267,10 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
   ovb_launch(ctx, k_ekf_gemm, dim3(g1), dim3(256), (size_t)(0), 1, P, ld, H, ldHm, ctx->d_M, ld, ctx->d_info, r, r, n, ctx->d_S, ld, sigma2, Rdiag_dev);
   size_t chol_bytes = sizeof(double) * (size_t)(r + 1) * (size_t)(r | 1);
   int use_smem = chol_bytes <= 200 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->attr_done[2]) { // function attributes are per device: one flag per context
     cudaFuncSetAttribute(k_ekf_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_ekf_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
+    ctx->attr_done[2] = 1;
   }
   // the residual vector is column n of H's row (TSQR output) or a separate buffer: callers stage it in d_w
   double *invdiag = ctx->d_w + ctx->cfg.max_state; // d_w holds 4 x max_state doubles: [w | 1/diag(L) | ...]

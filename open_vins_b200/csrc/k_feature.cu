@@ -884,10 +884,9 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
   const size_t smem_limit = 227 * 1024;
   bool S_in_smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, true) <= smem_limit;
   size_t smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, S_in_smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->attr_done[1]) { // function attributes are per device: one flag per context
     cudaFuncSetAttribute(k_feature_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
-    attr_set = true;
+    ctx->attr_done[1] = 1;
   }
   int grid = n_feats;
   double *scratch = nullptr;

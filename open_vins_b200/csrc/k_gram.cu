@@ -170,10 +170,9 @@ int launch_compress_gram(ovb_ctx *ctx, const double *A, int m, int n, int ldA, d
   k_gram_reduce<<<g2, 256, 0, ctx->stream>>>(ctx->d_Gpart, nslab, ntile, ntp, nt, ctx->d_G, ldG);
   const size_t smem = sizeof(double) * ((size_t)(n + 1) * (n | 1) + n + 8);
   const int use_smem = smem <= 220 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->attr_done[3]) { // function attributes are per device: one flag per context
     cudaFuncSetAttribute(k_gram_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
+    ctx->attr_done[3] = 1;
   }
   double *work = ctx->d_G + (size_t)(nt + 2) * ldG;
   k_gram_chol<<<1, EKC_THREADS, use_smem ? smem : 0, ctx->stream>>>(ctx->d_G, ldG, n, Rout, ldR, work, use_smem);

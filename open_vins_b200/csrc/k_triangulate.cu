@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
 void launch_triangulate(ovb_ctx *ctx, int n_feats, BlobView bv) {
   if (n_feats <= 0)
     return;
-  int warps_per_cta = 8;
+  // one warp per feature; spread the warps over all SMs (each warp is one long dependent FP64 chain)
+  int warps_per_cta = (n_feats + ctx->sm_count - 1) / ctx->sm_count;
+  warps_per_cta = warps_per_cta < 1 ? 1 : (warps_per_cta > 8 ? 8 : warps_per_cta);
   int grid = (n_feats + warps_per_cta - 1) / warps_per_cta;
   ovb_launch(ctx, k_triangulate, dim3(grid), dim3(warps_per_cta * 32), (size_t)(0), ctx->d_cc, ctx->d_opts, ctx->d_feat, n_feats, bv);
 }

@@ -568,10 +568,27 @@ __global__ void k_tsqr_assemble(const double *__restrict__ A, int ldA, int m, in
 }
 
 void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->attr_done[0]) { // function attributes are per device: one flag per context
     cudaFuncSetAttribute(k_tsqr_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QrSmem));
-    attr_set = true;
+    if (ctx->tsqr_cluster) { // can this device co-schedule one cluster of QR_CLUSTER CTAs with this much shared memory?
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(QR_CLUSTER, 1);
+      cfg.blockDim = dim3(QR_THREADS);
+      cfg.dynamicSmemBytes = sizeof(QrSmem);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = QR_CLUSTER;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, k_tsqr_level, &cfg) != cudaSuccess || ncl < 1) {
+        cudaGetLastError();
+        ctx->tsqr_cluster = 0; // plain three-level tree instead
+      }
+    }
+    ctx->attr_done[0] = 1;
   }
   const int nt = n + 1;
   // panel blocks of rows that never get factored (m < n) must read as zero
