@@ -221,6 +221,29 @@ ovb_status ovb_cov_propagate(ovb_ctx *ctx, int new_off, int p, const int *old_of
 ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts,
                             ovb_feat_out *out, double *dx, ovb_stats *stats);
 
+/* ---- SLAM landmarks: features that already live in the state (ov_type::Landmark, types/Landmark.h; State::_features_SLAM) ----
+ * One entry per feature of the batch handed to ovb_slam_update. All landmarks of one call share the representation
+ * ovb_opts.feat_rep (feat_rep_slam); ANCHORED_INVERSE_DEPTH_SINGLE (the one case where the reference nullspace-projects
+ * inside the SLAM update, update/UpdaterSLAM.cpp:344-353) is not supported yet and returns OVB_ERR_ARG. */
+typedef struct {
+  const int32_t *lm_off;         /* [n_feats] covariance id of the 3-wide landmark variable (Type::id()) */
+  const double *value;           /* [n_feats][3] Landmark::get_xyz(false): p_FinG (global reps) / p_FinA (anchored reps) */
+  const double *value_fej;       /* [n_feats][3] Landmark::get_xyz(true) */
+  const int32_t *anchor_cam;     /* [n_feats] Landmark::_anchor_cam_id            (anchored reps; else ignored) */
+  const int32_t *anchor_clone;   /* [n_feats] clone index of _anchor_clone_timestamp (anchored reps; else ignored) */
+  const double *sigma_pix;       /* [n_feats] or NULL: per-class pixel noise (aruco vs slam options, UpdaterSLAM.cpp:391-393) */
+  const double *chi2_multipler;  /* [n_feats] or NULL: per-class gate multiplier (UpdaterSLAM.cpp:407-408) */
+} ovb_landmarks;
+
+/* UpdaterSLAM::update steps 4-5 (update/UpdaterSLAM.cpp:310-470): per-feature Jacobians with the landmark's own 3
+ * columns appended (H_xf = [H_x, H_f], no nullspace projection), chi² gate on the marginal of (H_x variables + landmark),
+ * stacking and ONE EKF update of the whole batch. The reference does not compress this system; the engine whitens the
+ * rows by 1/sigma and compresses when rows > columns, which leaves the posterior unchanged. At most OVB_MAX_VARS (64)
+ * state variables (clones + calibration blocks + landmarks) per call: batch like max_slam_in_update does.
+ * out->status: OVB_FEAT_OK or OVB_FEAT_CHI2; out->chi2 filled; p_FinA/p_FinG/anchor_* are not written. */
+ovb_status ovb_slam_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_landmarks *landmarks,
+                           const ovb_opts *opts, ovb_feat_out *out, double *dx, ovb_stats *stats);
+
 /* StateHelper::EKFUpdate with R = sigma2·I (UpdaterMSCKF.cpp:282) or R = diag(Rdiag) (UpdaterSLAM.cpp:444).
  * H is r×n row-major, n = Σ sz.                                                   state/StateHelper.cpp:116-197 */
 ovb_status ovb_ekf_update(ovb_ctx *ctx, const int *off, const int *sz, int nvar, const double *H, int r, const double *res,

@@ -176,6 +176,30 @@ class FeatArrays:
         return FeatArrays(off, self.cam[sel], self.clone[sel], self.uv[sel], self.uvn[sel], ko, kk)
 
 
+class ovb_landmarks(C.Structure):
+    _fields_ = [("lm_off", c_int_p), ("value", c_double_p), ("value_fej", c_double_p), ("anchor_cam", c_int_p),
+                ("anchor_clone", c_int_p), ("sigma_pix", c_double_p), ("chi2_multipler", c_double_p)]
+
+
+class LandmarkArrays:
+    """Owns the arrays behind an ovb_landmarks: the SLAM landmarks (ov_type::Landmark) of the features in a batch."""
+
+    def __init__(self, lm_off, value, value_fej, anchor_cam=None, anchor_clone=None, sigma_pix=None, chi2_multipler=None):
+        n = len(lm_off)
+        self.lm_off = np.ascontiguousarray(lm_off, dtype=np.int32)
+        self.value = np.ascontiguousarray(value, dtype=np.float64).reshape(n, 3)
+        self.value_fej = np.ascontiguousarray(value_fej, dtype=np.float64).reshape(n, 3)
+        self.anchor_cam = np.full(n, -1, dtype=np.int32) if anchor_cam is None else np.ascontiguousarray(anchor_cam, dtype=np.int32)
+        self.anchor_clone = np.full(n, -1, dtype=np.int32) if anchor_clone is None else np.ascontiguousarray(anchor_clone, dtype=np.int32)
+        self.sigma_pix = None if sigma_pix is None else np.ascontiguousarray(sigma_pix, dtype=np.float64)
+        self.chi2_multipler = None if chi2_multipler is None else np.ascontiguousarray(chi2_multipler, dtype=np.float64)
+
+    def struct(self) -> ovb_landmarks:
+        return ovb_landmarks(_ptr(self.lm_off, c_int_p), _ptr(self.value, c_double_p), _ptr(self.value_fej, c_double_p),
+                             _ptr(self.anchor_cam, c_int_p), _ptr(self.anchor_clone, c_int_p), _ptr(self.sigma_pix, c_double_p),
+                             _ptr(self.chi2_multipler, c_double_p))
+
+
 class FeatOut:
     def __init__(self, n_feats: int):
         self.status = np.zeros(n_feats, dtype=np.int32)
@@ -230,6 +254,8 @@ def load_library(path: str | None = None) -> C.CDLL:
                                      C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
     lib.ovb_ekf_update.argtypes = [vp, c_int_p, c_int_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_double,
                                    c_double_p, c_double_p]
+    lib.ovb_slam_update.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_landmarks), C.POINTER(ovb_opts),
+                                    C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
     lib.ovb_triangulate.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts),
                                     C.POINTER(ovb_feat_out)]
     lib.ovb_feature_jacobians.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts),
@@ -255,7 +281,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate",
-    "ovb_msckf_update", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram",
+    "ovb_msckf_update", "ovb_slam_update", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram",
     "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
     "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_finish",
 ]
@@ -342,6 +368,16 @@ class Engine:
         fs, bs, os_ = frame.struct(), feats.struct(), out.struct()
         st = self.lib.ovb_msckf_update(self.h, C.byref(fs), C.byref(bs), C.byref(opts), C.byref(os_),
                                        _ptr(dx, c_double_p), C.byref(stats))
+        self._check(st, allow=(OVB_ERR_NEG_DIAG,))
+        return st, out, dx, stats
+
+    def slam_update(self, frame: FrameArrays, feats: FeatArrays, landmarks: "LandmarkArrays", opts: ovb_opts):
+        out = FeatOut(feats.n_feats)
+        dx = np.zeros(self.cov_dim())
+        stats = ovb_stats()
+        fs, bs, ls, os_ = frame.struct(), feats.struct(), landmarks.struct(), out.struct()
+        st = self.lib.ovb_slam_update(self.h, C.byref(fs), C.byref(bs), C.byref(ls), C.byref(opts), C.byref(os_),
+                                      _ptr(dx, c_double_p), C.byref(stats))
         self._check(st, allow=(OVB_ERR_NEG_DIAG,))
         return st, out, dx, stats
 

@@ -287,6 +287,67 @@ def make_update_case(n_feats=50, n_clones=12, n_cams=1, seed=0, calib_ext=False,
     return UpdateCase(lay, frame, feats, P, np.array(ptrue), meta)
 
 
+@dataclass
+class SlamCase:
+    frame: FrameArrays
+    feats: FeatArrays
+    landmarks: "LandmarkArrays"
+    P: np.ndarray
+    lm_off: np.ndarray
+    meta: dict
+
+
+def make_slam_case(n_landmarks=12, n_clones=8, n_cams=2, seed=0, rep=0, calib_ext=True, calib_intr=True, track_len=(1, 4),
+                   two_classes=True) -> SlamCase:
+    """One UpdaterSLAM::update batch: `n_landmarks` landmarks already in the state (3-wide variables appended after the
+    clone window, as State::_variables does), each observed in the newest 1..4 clones; prior P over the augmented state.
+    rep: ovb_feat_rep of all landmarks (global or anchored; the anchor is camera 0 at the track's oldest clone)."""
+    from .capi import LandmarkArrays
+    rng = np.random.default_rng(seed)
+    base = make_update_case(n_feats=n_landmarks, n_clones=n_clones, n_cams=n_cams, seed=seed, calib_ext=calib_ext, calib_intr=calib_intr,
+                            full_track_frac=1.0, outlier_frac=0.0, degenerate_frac=0.0)
+    lay, fr = base.layout, base.frame
+    N0 = lay.N
+    N = N0 + 3 * n_landmarks
+    lm_off = N0 + 3 * np.arange(n_landmarks)
+    sig = np.concatenate([lay.sigmas(), 0.05 * np.ones(3 * n_landmarks)])
+    U = rng.standard_normal((N, 12))
+    Cn = 0.6 * np.eye(N) + 0.4 * (U @ U.T) / 12
+    P = (sig[:, None] * Cn) * sig[None, :]
+    P = 0.5 * (P + P.T)
+    # keep only the newest `track_len` clones of every track (SLAM features are updated as they are re-observed)
+    fa = base.feats
+    keep, meas_off = [], [0]
+    first_clone = []
+    for f in range(n_landmarks):
+        L = int(rng.integers(track_len[0], track_len[1] + 1))
+        idx = [i for i in range(fa.meas_off[f], fa.meas_off[f + 1]) if fa.clone[i] >= n_clones - L]
+        keep += idx
+        meas_off.append(meas_off[-1] + len(idx))
+        first_clone.append(n_clones - L)
+    keep = np.array(keep, dtype=np.int64)
+    feats = FeatArrays(meas_off, fa.cam[keep], fa.clone[keep], fa.uv[keep], fa.uvn[keep])
+    # landmark estimates: truth minus an error of the prior's size; FEJ value = estimate + a small offset
+    p_est = base.p_true - 0.03 * rng.standard_normal(base.p_true.shape)
+    p_fej = p_est + 2e-3 * rng.standard_normal(p_est.shape)
+    relative = rep in (2, 3, 4, 5)
+    anchor_cam = np.full(n_landmarks, -1, dtype=np.int32)
+    anchor_clone = np.full(n_landmarks, -1, dtype=np.int32)
+    value, value_fej = p_est.copy(), p_fej.copy()
+    if relative:
+        for f in range(n_landmarks):
+            c = first_clone[f]
+            anchor_cam[f], anchor_clone[f] = 0, c
+            to_anchor = lambda pG: fr.cam_R[0] @ (fr.clone_R[c] @ (pG - fr.clone_p[c])) + fr.cam_p[0]
+            value[f], value_fej[f] = to_anchor(p_est[f]), to_anchor(p_fej[f])
+    sigma_pix = chi2_mult = None
+    if two_classes:  # the first third plays the "aruco" class with its own noise / gate (UpdaterSLAM.cpp:391-393, :407-408)
+        sigma_pix = np.where(np.arange(n_landmarks) < n_landmarks // 3, 1.5, 1.0)
+        chi2_mult = np.where(np.arange(n_landmarks) < n_landmarks // 3, 2.0, 1.0)
+    lms = LandmarkArrays(lm_off, value, value_fej, anchor_cam, anchor_clone, sigma_pix, chi2_mult)
+    return SlamCase(fr, feats, lms, P, lm_off, dict(N=N, N0=N0, rep=rep, n_landmarks=n_landmarks))
+
+
 def make_compress_case(m=8000, n=500, seed=0, structured=False):
     """config 5: H m x n, res, SPD P = A A'/n + 1e-4 I."""
     rng = np.random.default_rng(seed)

@@ -150,6 +150,37 @@ int ovo_msckf_update(const ovb_frame *fr, const ovb_feat_batch *fb, const ovb_op
   return st;
 }
 
+// UpdaterSLAM::update steps 4-5. H_big/res_big/Rdiag_big: the stacked system handed to EKFUpdate (row-major, ld = *cols).
+int ovo_slam_update(const ovb_frame *fr, const ovb_feat_batch *fb, const ovb_landmarks *lm, const ovb_opts *op, const double *chi2_table,
+                    double *P, int N, ovb_feat_out *out, double *dx, ovb_stats *stats, int32_t *order_off, int32_t *order_sz, int32_t *n_order,
+                    double *H_big, double *res_big, double *Rdiag_big, int cap_rows) {
+  UpdateDump dump;
+  ovb_stats st_local;
+  if (!stats)
+    stats = &st_local;
+  int st = slam_update(*fr, *fb, *lm, *op, chi2_table, P, N, out, dx, stats, &dump);
+  if (n_order)
+    *n_order = (int)dump.order_big.size();
+  for (size_t i = 0; i < dump.order_big.size() && i < OVB_MAX_VARS; i++) {
+    if (order_off)
+      order_off[i] = dump.order_big[i].off;
+    if (order_sz)
+      order_sz[i] = dump.order_big[i].size;
+  }
+  int cols = dump.H_big.c;
+  if (H_big)
+    for (int i = 0; i < dump.H_big.r && i < cap_rows; i++)
+      for (int k = 0; k < cols; k++)
+        H_big[(size_t)i * cols + k] = dump.H_big(i, k);
+  for (int i = 0; i < (int)dump.res_big.size() && i < cap_rows; i++) {
+    if (res_big)
+      res_big[i] = dump.res_big[i];
+    if (Rdiag_big)
+      Rdiag_big[i] = dump.res_cmp[i];
+  }
+  return st;
+}
+
 // measurement_compress_inplace on a row-major H (m x n); outputs R (min(m,n) x n row-major) and z.
 int ovo_compress(const double *H, int m, int n, const double *res, double *R_out, double *z_out) {
   Mat Hc(m, n);

@@ -1136,4 +1136,132 @@ inline int msckf_update(const ovb_frame &fr, const ovb_feat_batch &fb, const ovb
   return st;
 }
 
+// Steps 4-5 of UpdaterSLAM::update (update/UpdaterSLAM.cpp:310-470). Landmarks live in the state: value / FEJ value
+// come from `lm` (Landmark::get_xyz), H_xf = [H_x, H_f], no nullspace projection (the SINGLE representation, :344-353,
+// is not restated), no compression, ONE EKFUpdate with the block-scaled identity R_big (:444). P updated in place.
+inline int slam_update(const ovb_frame &fr, const ovb_feat_batch &fb, const ovb_landmarks &lm, const ovb_opts &op, const double *chi2_table,
+                       double *P, int N, ovb_feat_out *out, double *dx, ovb_stats *stats, UpdateDump *dump) {
+  const int F = fb.n_feats;
+  int rep = op.feat_rep;
+  if (rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE)
+    return OVB_ERR_ARG;
+  std::vector<int> status(F, OVB_FEAT_OK);
+  std::vector<double> chi2s(F, std::nan(""));
+  size_t max_meas_size = 0;
+  for (int f = 0; f < F; f++)
+    max_meas_size += 2 * (size_t)(fb.meas_off[f + 1] - fb.meas_off[f]);
+  std::vector<double> res_big(max_meas_size, 0.0), R_big(max_meas_size, 1.0);
+  Mat Hx_big((int)max_meas_size, N);
+  std::vector<Var> Hx_order_big;
+  int ct_jacob = 0, ct_meas = 0, used = 0;
+  double T0 = now_s();
+  for (int f = 0; f < F; f++) {
+    if (fb.meas_off[f + 1] - fb.meas_off[f] < 1) { // :283-285 (ct_meas < 1: dropped before the update)
+      status[f] = OVB_FEAT_FEW_MEAS;
+      continue;
+    }
+    // :333-341 — the landmark's value and FEJ value in the frame its representation lives in
+    V3 val = v3(lm.value[3 * f], lm.value[3 * f + 1], lm.value[3 * f + 2]);
+    V3 val_fej = v3(lm.value_fej[3 * f], lm.value_fej[3 * f + 1], lm.value_fej[3 * f + 2]);
+    V3 p_FinG = val, p_FinG_fej = val_fej, p_FinA = val;
+    int acam = -1, aclone = -1;
+    if (is_relative(rep)) {
+      acam = lm.anchor_cam[f];
+      aclone = lm.anchor_clone[f];
+    }
+    FeatJac J;
+    feature_jacobian_full(fr, fb, op, f, rep, p_FinG, p_FinG_fej, p_FinA, acam, aclone, J);
+    // :354-361 — H_xf = [H_x, H_f], order += landmark
+    FeatJac Jxf;
+    Jxf.rows = J.rows;
+    Jxf.order = J.order;
+    Jxf.order.push_back(Var{lm.lm_off[f], 3});
+    Jxf.res = J.res;
+    Jxf.Hx.resize_zero(J.rows, J.Hx.c + 3);
+    for (int i = 0; i < J.rows; i++) {
+      for (int k = 0; k < J.Hx.c; k++)
+        Jxf.Hx(i, k) = J.Hx(i, k);
+      for (int k = 0; k < 3; k++)
+        Jxf.Hx(i, J.Hx.c + k) = J.Hf(i, k);
+    }
+    // :389-420 — chi² gate with the per-class noise and multiplier
+    const double sigma_pix = lm.sigma_pix ? lm.sigma_pix[f] : op.sigma_pix;
+    const double sigma_pix_sq = std::pow(sigma_pix, 2);
+    const double mult = lm.chi2_multipler ? lm.chi2_multipler[f] : op.chi2_multipler;
+    bool spd = true;
+    double chi2 = feature_chi2(P, N, Jxf, sigma_pix_sq, &spd);
+    chi2s[f] = chi2;
+    double chi2_check = chi2_table[std::min(Jxf.rows, OVB_CHI2_TABLE_LEN - 1)];
+    if (!(chi2 <= mult * chi2_check)) {
+      status[f] = OVB_FEAT_CHI2;
+      continue;
+    }
+    // :424-447 — append with the first-seen column map
+    int ct_hx = 0;
+    for (const Var &var : Jxf.order) {
+      int col = find_var(Hx_order_big, var.off);
+      if (col < 0) {
+        col = ct_jacob;
+        Hx_order_big.push_back(var);
+        ct_jacob += var.size;
+      }
+      for (int k = 0; k < var.size; k++)
+        for (int i = 0; i < Jxf.rows; i++)
+          Hx_big(ct_meas + i, col + k) = Jxf.Hx(i, ct_hx + k);
+      ct_hx += var.size;
+    }
+    for (int i = 0; i < Jxf.rows; i++) {
+      res_big[ct_meas + i] = Jxf.res[i];
+      R_big[ct_meas + i] = sigma_pix_sq;
+    }
+    ct_meas += Jxf.rows;
+    used++;
+  }
+  double T1 = now_s();
+  if (out) {
+    for (int f = 0; f < F; f++) {
+      if (out->status)
+        out->status[f] = status[f];
+      if (out->chi2)
+        out->chi2[f] = chi2s[f];
+    }
+  }
+  if (stats) {
+    stats->n_feats_in = F;
+    stats->n_feats_used = used;
+    stats->rows_stacked = ct_meas;
+    stats->cols_stacked = ct_jacob;
+    stats->rows_update = ct_meas;
+    stats->neg_diag_index = -1;
+    stats->ms_total = 0;
+  }
+  for (int i = 0; i < N; i++)
+    dx[i] = 0.0;
+  if (ct_meas < 1)
+    return OVB_OK;
+  Mat H(ct_meas, ct_jacob);
+  for (int k = 0; k < ct_jacob; k++)
+    for (int i = 0; i < ct_meas; i++)
+      H(i, k) = Hx_big(i, k);
+  res_big.resize(ct_meas);
+  R_big.resize(ct_meas);
+  if (dump) {
+    dump->order_big = Hx_order_big;
+    dump->H_big = H;
+    dump->res_big = res_big;
+    dump->H_cmp = H;
+    dump->res_cmp = R_big; // the SLAM path never compresses: this slot carries diag(R_big) instead
+    dump->t_sys = T1 - T0;
+  }
+  int neg = -1;
+  int st = ekf_update(P, N, Hx_order_big, H, res_big, R_big, dx, &neg);
+  if (stats) {
+    stats->neg_diag_index = neg;
+    stats->ms_total = (float)((now_s() - T0) * 1e3);
+  }
+  if (dump)
+    dump->t_upd = now_s() - T1;
+  return st;
+}
+
 } // namespace ovo

@@ -1,0 +1,77 @@
+"""Oracle restatement of UpdaterSLAM::update (steps 4-5, update/UpdaterSLAM.cpp:310-470) against independent numpy code."""
+import numpy as np
+import pytest
+
+from open_vins_b200 import capi, sim
+
+
+def _cols(order_off, order_sz):
+    return np.concatenate([np.arange(o, o + s) for o, s in zip(order_off, order_sz)])
+
+
+@pytest.mark.parametrize("rep", [capi.REP_GLOBAL_3D, capi.REP_GLOBAL_FULL_INVERSE_DEPTH, capi.REP_ANCHORED_3D,
+                                 capi.REP_ANCHORED_FULL_INVERSE_DEPTH, capi.REP_ANCHORED_MSCKF_INVERSE_DEPTH])
+def test_slam_update_is_the_textbook_update_of_its_stacked_system(oracle, rep):
+    case = sim.make_slam_case(n_landmarks=14, n_clones=8, n_cams=2, seed=40 + rep, rep=rep)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, feat_rep=rep)
+    r = oracle.slam_update(case.frame, case.feats, case.landmarks, opts, case.P)
+    assert r["status"] == 0 and r["stats"].n_feats_used >= 8
+    H, res, Rd = r["H_big"], r["res_big"], r["Rdiag_big"]
+    c = _cols(r["order_off"], r["order_sz"])
+    assert H.shape == (r["stats"].rows_stacked, len(c)) and len(set(c.tolist())) == len(c)
+    # every accepted landmark contributes its own 3 columns, and only its own rows touch them
+    used = np.flatnonzero(r["out"].status == 0)
+    row = 0
+    for f in used:
+        m = 2 * int(case.feats.meas_off[f + 1] - case.feats.meas_off[f])
+        j = [int(np.flatnonzero(c == case.lm_off[f] + k)[0]) for k in range(3)]
+        assert np.abs(H[row:row + m, j]).max() > 0
+        mask = np.ones(H.shape[0], dtype=bool)
+        mask[row:row + m] = False
+        assert not H[mask][:, j].any()
+        sig = 1.0 if case.landmarks.sigma_pix is None else case.landmarks.sigma_pix[f]
+        assert np.all(Rd[row:row + m] == sig ** 2)
+        row += m
+    assert row == H.shape[0]
+    # textbook EKF update (StateHelper.cpp:116-197) in numpy
+    P = case.P
+    S = H @ P[np.ix_(c, c)] @ H.T + np.diag(Rd)
+    K = P[:, c] @ H.T @ np.linalg.inv(S)
+    Pn = P - K @ H @ P[c, :]
+    assert np.linalg.norm(r["P"] - Pn) <= 1e-10 * np.linalg.norm(Pn)
+    assert np.linalg.norm(r["dx"] - K @ res) <= 1e-10 * np.linalg.norm(K @ res)
+    # the gate of every feature: chi2 = res' (H_xf P_marg H_xf' + s2 I)^-1 res on its own rows
+    row = 0
+    for f in used:
+        m = 2 * int(case.feats.meas_off[f + 1] - case.feats.meas_off[f])
+        Sf = S[row:row + m, row:row + m]
+        chi2 = res[row:row + m] @ np.linalg.solve(Sf, res[row:row + m])
+        assert abs(chi2 - r["out"].chi2[f]) <= 1e-9 * chi2
+        row += m
+
+
+@pytest.mark.parametrize("rep", [capi.REP_GLOBAL_3D, capi.REP_ANCHORED_3D])
+def test_landmark_columns_by_finite_differences(oracle, rep):
+    """d(residual)/d(landmark) = -H_f: perturb the landmark value (FEJ off, FEJ value = value) and difference the residuals."""
+    case = sim.make_slam_case(n_landmarks=6, n_clones=6, n_cams=2, seed=77, rep=rep, two_classes=False)
+    lm = case.landmarks
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, feat_rep=rep, do_fej=0, chi2_multipler=1e12)
+    mk = lambda v: capi.LandmarkArrays(lm.lm_off, v, v, lm.anchor_cam, lm.anchor_clone)
+    r0 = oracle.slam_update(case.frame, case.feats, mk(lm.value), opts, case.P)
+    c = _cols(r0["order_off"], r0["order_sz"])
+    assert (r0["out"].status == 0).all()
+    h = 1e-2  # residuals carry float32 rounding of the distortion (~3e-5 px): the step must dwarf it
+    row = 0
+    for f in range(6):
+        m = 2 * int(case.feats.meas_off[f + 1] - case.feats.meas_off[f])
+        for k in range(3):
+            vp, vm = lm.value.copy(), lm.value.copy()
+            vp[f, k] += h
+            vm[f, k] -= h
+            rp = oracle.slam_update(case.frame, case.feats, mk(vp), opts, case.P)["res_big"][row:row + m]
+            rm = oracle.slam_update(case.frame, case.feats, mk(vm), opts, case.P)["res_big"][row:row + m]
+            fd = -(rp - rm) / (2 * h)
+            j = int(np.flatnonzero(c == case.lm_off[f] + k)[0])
+            an = r0["H_big"][row:row + m, j]
+            assert np.abs(fd - an).max() <= 2e-3 * max(np.abs(an).max(), 1.0), (f, k)
+        row += m
