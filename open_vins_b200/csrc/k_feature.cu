@@ -24,7 +24,8 @@
 
 // Per-measurement Jacobian blocks live in shared memory as structure-of-arrays:
 //   Bsh[I][b][16]  blocks [2][8] (row stride 8): 0 clone(6) 1 extrinsics(6) 2 intrinsics(8) 3 anchor clone(6) 4 anchor extrinsics(6);
-//                  blocks 3/4 exist only for the anchored representations (nblk = 5, else 3)
+//                  blocks 3/4 exist only for the anchored representations (nblk = 5, else 3); SLAM updates add block 5 =
+//                  the landmark's own 2x3 Jacobian H_f (nblk = 6)
 //   Hfs[I][6], ress[I][2], mslot[I][8] (slot id per block or -1; blocks 3/4 only when their slot differs from blocks 0/1)
 //   lut[I][lutw]   slot -> block index (255 = the measurement does not touch the slot)
 struct MeasView {
@@ -42,7 +43,7 @@ struct MeasView {
   }
 };
 
-__device__ __forceinline__ int blk_w(int b) { return b == 2 ? 8 : 6; }
+__device__ __forceinline__ int blk_w(int b) { return b == 2 ? 8 : (b == 5 ? 3 : 6); }
 
 // block-wide sum of three values; every thread gets the result. red: FT_WARPS*3 doubles of shared memory.
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double *red) {
@@ -197,6 +198,8 @@ __device__ __forceinline__ bool rep_is_relative(int rep) {
 
 // =====================================================================================================================
 // mode 0: full (gate + write projected rows to Hs)   mode 1: dump pre-nullspace dense rows to `dump`
+// mode 2: SLAM update (update/UpdaterSLAM.cpp:310-447): the landmark is a state variable (block 5 = H_f, slot lm_slot),
+//         no nullspace projection (all 2M rows are kept), per-feature noise / gate multiplier, rows whitened by 1/sigma
 __global__ void __launch_bounds__(FT_THREADS, 2)
     k_feature_system(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, DevFeat *__restrict__ feats, int n_feats, BlobView bv,
                      const double *__restrict__ P, int ldP, const double *__restrict__ chi2_table, double *__restrict__ Hs, int ldH,
@@ -209,6 +212,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
   const int n_slots = fr->n_slots;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n_all8 = (n_all + 7) & ~7;
+  const bool slam = (mode == 2);
+  const int r0 = slam ? 0 : 3; // rows removed by the nullspace projection
   // ---- shared memory carve-up (mirrors feature_smem_bytes)
   size_t o = 0;
   MeasView mv;
@@ -278,11 +283,11 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       if (status_in != OVB_FEAT_OK || M < 2 || M > maxM)
         continue;
     } else {
-      if (M < 2)
+      if (M < (slam ? 1 : 2))
         continue; // no rows reserved
       if (status_in != OVB_FEAT_OK || M > maxM) {
         // rows reserved for this feature are zero (they are harmless in the QR)
-        int nr = rows - 3;
+        int nr = rows - r0;
         for (int e = tid; e < nr * (n_all + 1); e += FT_THREADS) {
           int i = e / (n_all + 1), j = e % (n_all + 1);
           Hs[(size_t)(F->row0 + i) * ldH + j] = 0.0;
@@ -314,7 +319,10 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
           RtRt.m[3 * i + j] = (R_GtoI.m[i] * R_ItoC.m[3 * j] + R_GtoI.m[3 + i] * R_ItoC.m[3 * j + 1]) + R_GtoI.m[6 + i] * R_ItoC.m[3 * j + 2];
       p_FinG = add3(mv3(RtRt, sub3(p_FinA, p_IinC)), p_IinG);
     }
-    const dv3 p_FinG_fej = p_FinG; // MSCKF features: p_FinG_fej = p_FinG (UpdaterMSCKF.cpp:190-193, UpdaterHelper.cpp:284-287)
+    // MSCKF features: p_FinG_fej = p_FinG (UpdaterMSCKF.cpp:190-193); anchored: always the "best" p_FinG
+    // (UpdaterHelper.cpp:284-287); SLAM landmarks in a global representation bring their own FEJ value (UpdaterSLAM.cpp:339-340)
+    const dv3 p_FinG_fej = (slam && !relative) ? ld_v3(F->p_FinG_fej) : p_FinG;
+    const double sig2 = F->sigma_sq;
 
     for (int e = tid; e < M * mv.lutw; e += FT_THREADS)
       mv.lut[e] = 255;
@@ -376,6 +384,13 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
             ord[1 + no] = (unsigned char)s_anchor_ext;
           no++;
         }
+      }
+      if (slam) { // Hxf_order.push_back(landmark): always last, never seen before (UpdaterSLAM.cpp:385-387)
+        const int s = F->lm_slot;
+        seen |= 1ull << s;
+        if (ord)
+          ord[1 + no] = (unsigned char)s;
+        no++;
       }
       if (ord)
         ord[0] = (unsigned char)no;
@@ -455,7 +470,17 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
           B0[8 * r + 3 + k] =
               (dz_dpfc[r][0] * (-dpfc_dpfg.m[k]) + dz_dpfc[r][1] * (-dpfc_dpfg.m[3 + k])) + dz_dpfc[r][2] * (-dpfc_dpfg.m[6 + k]);
         }
-      int sl[5];
+      int sl[6];
+      sl[5] = -1;
+      if (slam) { // H_xf = [H_x, H_f]: the landmark's own columns (UpdaterSLAM.cpp:365-383)
+        double *B5 = mv.blk(tid, 5);
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            B5[8 * r + k] = mHf[3 * r + k];
+        sl[5] = F->lm_slot;
+      }
       sl[0] = mcs[tid];
       sl[1] = op.do_calib_camera_pose ? fr->cam_ext_slot[cam] : -1;
       sl[2] = op.do_calib_camera_intrinsics ? fr->cam_intr_slot[cam] : -1;
@@ -523,7 +548,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
           B2[k] = dz_dzeta[k];
       }
 #pragma unroll
-      for (int b = 0; b < 5; b++) {
+      for (int b = 0; b < 6; b++) {
         msl[b] = (signed char)sl[b];
         if (sl[b] >= 0)
           mv.lut[(size_t)tid * mv.lutw + sl[b]] = (unsigned char)b;
@@ -555,10 +580,15 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       a[1] = mv.Hf[3 * tid + 1];
       a[2] = mv.Hf[3 * tid + 2];
     }
-    double tau[3];
+    double tau[3] = {0.0, 0.0, 0.0};
     double *rowk = red + FT_WARPS * 3; // 3 doubles: the pivot row's values
+    if (slam) { // no projection: Q = I (tau = 0, V = 0 make every sweep below a no-op)
+      if (tid < rows)
+        V[3 * tid] = V[3 * tid + 1] = V[3 * tid + 2] = 0.0;
+      __syncthreads();
+    }
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 3 && !slam; k++) {
       const double ak = a[k];
       const bool below = (tid > k && tid < rows);
       // g[j] = sum over rows below the pivot of a_k a_j  (g[k] = squared norm of the sub-column)
@@ -604,7 +634,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
     // Gram of the reflectors: G10 = v1'v0, G20 = v2'v0, G21 = v2'v1
     double G10 = 0, G20 = 0, G21 = 0;
-    if (tid < rows) {
+    if (tid < rows && !slam) {
       double v0 = V[3 * tid], v1 = V[3 * tid + 1], v2 = V[3 * tid + 2];
       G10 = v1 * v0;
       G20 = v2 * v0;
@@ -706,20 +736,25 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
         }
         if (nblk > 3) {
 #pragma unroll
-          for (int b = 3; b < 5; b++) {
+          for (int b = 3; b < 6; b++) {
+            if (b >= nblk)
+              break;
             const int sb = slI[b];
             if (sb < 0)
               continue;
             const double *B = mv.blk(I, b);
             const double *Pb = P + (size_t)fslot_off[sb] * ldP + pc;
+            const int wb = blk_w(b);
             double pw[6];
 #pragma unroll
             for (int k = 0; k < 6; k++)
-              pw[k] = __ldg(Pb + (size_t)k * ldP);
+              pw[k] = (k < wb) ? __ldg(Pb + (size_t)k * ldP) : 0.0;
 #pragma unroll
             for (int k = 0; k < 6; k++) {
-              t0 += B[k] * pw[k];
-              t1 += B[8 + k] * pw[k];
+              if (k < wb) {
+                t0 += B[k] * pw[k];
+                t1 += B[8 + k] * pw[k];
+              }
             }
           }
         }
@@ -731,7 +766,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
         const signed char *slJ = mv.slot + 8 * J;
         double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
 #pragma unroll
-        for (int b = 0; b < 5; b++) {
+        for (int b = 0; b < 6; b++) {
           if (b >= nblk)
             break;
           int sb = slJ[b];
@@ -749,8 +784,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
           }
         }
         if (J == I) {
-          s00 += dop->sigma_pix_sq;
-          s11 += dop->sigma_pix_sq;
+          s00 += sig2;
+          s11 += sig2;
           s10 = s01; // exact symmetry of the diagonal 2x2 block
         }
         S[(2 * I) * ldS + 2 * J] = s00;
@@ -767,7 +802,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     __syncthreads();
 
     // ---- S <- Q' S Q (both sides), only rows/cols 3.. are used afterwards
-    for (int pass = 0; pass < 2; pass++) {
+    for (int pass = 0; pass < 2 && !slam; pass++) {
       for (int j = tid; j < rows; j += FT_THREADS) {
         // pass 0: vector = column j (stride ldS); pass 1: vector = row j (stride 1)
         const int st = (pass == 0) ? ldS : 1;
@@ -797,11 +832,11 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
     __syncthreads();
     // ---- chi² = |L^-1 r_o|² on the trailing (rows-3) block
-    const int nr = rows - 3;
-    bool spd = chol_lower_block<FT_THREADS, 2>(S + 3 * ldS + 3, ldS, nr, 1, &ishare[1], red + FT_WARPS * 3 + 4);
+    const int nr = rows - r0;
+    bool spd = chol_lower_block<FT_THREADS, 2>(S + r0 * ldS + r0, ldS, nr, 1, &ishare[1], red + FT_WARPS * 3 + 4);
     double c2 = 0.0;
     for (int i = tid; i < nr; i += FT_THREADS) {
-      double y = S[(size_t)rows * ldS + 3 + i];
+      double y = S[(size_t)rows * ldS + r0 + i];
       c2 += y * y;
     }
     double dummy1 = 0, dummy2 = 0;
@@ -809,7 +844,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double chi2 = spd ? c2 : qnan;
     double chi2_check = chi2_table[min(nr, OVB_CHI2_TABLE_LEN - 1)];
-    bool gated = !(chi2 <= op.chi2_multipler * chi2_check); // UpdaterMSCKF.cpp:225 (NaN rejects)
+    bool gated = !(chi2 <= F->chi2_mult * chi2_check); // UpdaterMSCKF.cpp:225, UpdaterSLAM.cpp:409 (NaN rejects)
     if (tid == 0) {
       F->chi2 = chi2;
       if (gated)
@@ -829,13 +864,16 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       }
       double z0 = Z[j], z1 = Z[(n_all + 1) + j], z2 = Z[2 * (n_all + 1) + j];
       double *out = Hs + (size_t)F->row0 * ldH + j;
+      // SLAM: rows whitened by 1/sigma of the feature's class, the EKF update then runs with R = I (R_big of
+      // UpdaterSLAM.cpp:444 is sigma^2 I per feature)
+      const double wgt = slam ? 1.0 / sqrt(sig2) : 1.0;
       if (gated || (j < n_all && !present)) {
-        for (int i = 3; i < rows; i++)
-          out[(size_t)(i - 3) * ldH] = 0.0;
+        for (int i = r0; i < rows; i++)
+          out[(size_t)(i - r0) * ldH] = 0.0;
       } else {
-        for (int i = 3; i < rows; i++) {
+        for (int i = r0; i < rows; i++) {
           double xv = (j == n_all) ? mv.res[i] : mv.x_at(i >> 1, i & 1, s, kk);
-          out[(size_t)(i - 3) * ldH] = xv - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2);
+          out[(size_t)(i - r0) * ldH] = (xv - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2)) * wgt;
         }
       }
     }
@@ -880,7 +918,7 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
     maxM = OVB_MAX_MEAS_PER_FEAT;
   // anchor blocks exist only for the anchored representations (same remap as DevOpts::rep)
   const int rep = ctx->h_opts->rep;
-  const int nblk = (rep == OVB_REP_GLOBAL_3D || rep == OVB_REP_GLOBAL_FULL_INVERSE_DEPTH) ? 3 : 5;
+  const int nblk = (mode == 2) ? 6 : ((rep == OVB_REP_GLOBAL_3D || rep == OVB_REP_GLOBAL_FULL_INVERSE_DEPTH) ? 3 : 5);
   const size_t smem_limit = 227 * 1024;
   bool S_in_smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, true) <= smem_limit;
   size_t smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, S_in_smem);

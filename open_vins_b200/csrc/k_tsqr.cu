@@ -671,7 +671,7 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
 extern unsigned char *ovb_feat_order_ptr(ovb_ctx *ctx);
 
 __global__ void k_column_map(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, const DevFeat *__restrict__ feats, int n_feats,
-                             const unsigned char *__restrict__ feat_order, DevUpdateInfo *__restrict__ info) {
+                             const unsigned char *__restrict__ feat_order, DevUpdateInfo *__restrict__ info, int rows_drop) {
   __shared__ unsigned int key[OVB_MAX_VARS];
   __shared__ int n_used_feats, rows_stacked;
   __shared__ int order[OVB_MAX_VARS];
@@ -689,7 +689,7 @@ __global__ void k_column_map(const DevFrame *__restrict__ fr, const DevOpts *__r
     if (feats[f].status != OVB_FEAT_OK)
       continue;
     atomicAdd(&n_used_feats, 1);
-    atomicAdd(&rows_stacked, 2 * (feats[f].m1 - feats[f].m0) - 3);
+    atomicAdd(&rows_stacked, 2 * (feats[f].m1 - feats[f].m0) - rows_drop); // 3 rows lost to the nullspace projection (MSCKF), 0 (SLAM)
     const unsigned char *ord = feat_order + (size_t)f * (OVB_MAX_VARS + 1);
     int no = ord[0];
     for (int q = 0; q < no; q++)
@@ -748,8 +748,8 @@ __global__ void k_column_map(const DevFrame *__restrict__ fr, const DevOpts *__r
   }
 }
 
-void launch_column_map(ovb_ctx *ctx, int n_feats, BlobView bv) {
-  k_column_map<<<1, 256, 0, ctx->stream>>>(ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, ovb_feat_order_ptr(ctx), ctx->d_info);
+void launch_column_map(ovb_ctx *ctx, int n_feats, BlobView bv, int rows_drop) {
+  k_column_map<<<1, 256, 0, ctx->stream>>>(ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, ovb_feat_order_ptr(ctx), ctx->d_info, rows_drop);
 }
 
 // B[i][q] = Rin[i][col_canon[q]] for q < n_all, B[i][n_all] = Rin[i][n_all] (residual)

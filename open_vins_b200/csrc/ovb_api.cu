@@ -333,9 +333,13 @@ struct Packed {
   BlobView bv;
 };
 
+// lm != nullptr: SLAM batch — every feature brings its landmark (a 3-wide state variable that becomes one more slot),
+// rows are NOT nullspace-projected (2M per feature instead of 2M-3), values/anchors come from the landmark.
 static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_batch *fb, const ovb_opts *op, const ovb_feat_out *given,
-                              Packed *pk) {
+                              Packed *pk, const ovb_landmarks *lm = nullptr) {
   if (!fr || !fb || !op)
+    return OVB_ERR_ARG;
+  if (lm && (!lm->lm_off || !lm->value || !lm->value_fej))
     return OVB_ERR_ARG;
   if (fr->n_clones < 1 || fr->n_clones > OVB_MAX_CLONES || fr->n_cams < 1 || fr->n_cams > OVB_MAX_CAMS) {
     snprintf(ctx->err, sizeof(ctx->err), "frame: n_clones=%d (max %d) n_cams=%d (max %d)", fr->n_clones, OVB_MAX_CLONES, fr->n_cams, OVB_MAX_CAMS);
@@ -362,8 +366,12 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
   // ---- slots in ascending covariance offset
   struct SlotRec {
     int off, size, kind, idx;
-  }; // kind 0 clone, 1 ext, 2 intr
+  }; // kind 0 clone, 1 ext, 2 intr, 3 landmark
   std::vector<SlotRec> slots;
+  std::vector<int> lm_slot_of((size_t)(lm ? fb->n_feats : 0), -1);
+  if (lm)
+    for (int f = 0; f < fb->n_feats; f++)
+      slots.push_back({lm->lm_off[f], 3, 3, f});
   for (int k = 0; k < fr->n_cams; k++) {
     hf->cam_ext_slot[k] = hf->cam_intr_slot[k] = -1;
     if (op->do_calib_camera_pose) {
@@ -384,8 +392,11 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
   for (int c = 0; c < fr->n_clones; c++)
     slots.push_back({fr->clone_off[c], 6, 0, c});
   std::sort(slots.begin(), slots.end(), [](const SlotRec &a, const SlotRec &b) { return a.off < b.off; });
-  if ((int)slots.size() > OVB_MAX_VARS)
+  if ((int)slots.size() > OVB_MAX_VARS) {
+    snprintf(ctx->err, sizeof(ctx->err), "%d state variables in one update (clones + calibration + landmarks), max %d: split the batch",
+             (int)slots.size(), OVB_MAX_VARS);
     return OVB_ERR_CAPACITY;
+  }
   int col = 0;
   for (size_t s = 0; s < slots.size(); s++) {
     if (slots[s].off < 0 || slots[s].off + slots[s].size > ctx->N) {
@@ -404,8 +415,10 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
       hf->clone_slot[slots[s].idx] = (int)s;
     else if (slots[s].kind == 1)
       hf->cam_ext_slot[slots[s].idx] = (int)s;
-    else
+    else if (slots[s].kind == 2)
       hf->cam_intr_slot[slots[s].idx] = (int)s;
+    else
+      lm_slot_of[(size_t)slots[s].idx] = (int)s;
   }
   hf->n_slots = (int)slots.size();
   hf->n_all = col;
@@ -448,7 +461,10 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
     }
     maxM = std::max(maxM, Mf);
     d.row0 = row;
-    row += Mf >= 2 ? 2 * Mf - 3 : 0;
+    if (lm)
+      row += 2 * Mf; // UpdaterSLAM.cpp:365-387: H_xf = [H_x, H_f], all 2M rows kept
+    else
+      row += Mf >= 2 ? 2 * Mf - 3 : 0;
     d.key0 = (int)nkeys;
     if (fb->cam_keys_off && fb->cam_keys) {
       for (int k = fb->cam_keys_off[f]; k < fb->cam_keys_off[f + 1]; k++) {
@@ -475,6 +491,31 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
     d.chi2 = NAN;
     for (int k = 0; k < 3; k++)
       d.p_FinA[k] = d.p_FinG[k] = NAN;
+    d.sigma_sq = std::pow(op->sigma_pix, 2);
+    d.chi2_mult = op->chi2_multipler;
+    d.lm_slot = -1;
+    for (int k = 0; k < 3; k++)
+      d.p_FinG_fej[k] = NAN;
+    if (lm) {
+      d.lm_slot = lm_slot_of[(size_t)f];
+      d.status = Mf >= 1 ? OVB_FEAT_OK : OVB_FEAT_FEW_MEAS; // UpdaterSLAM.cpp:283-285
+      const bool rel = op->feat_rep >= OVB_REP_ANCHORED_3D;
+      d.anchor_cam = rel && lm->anchor_cam ? lm->anchor_cam[f] : -1;
+      d.anchor_clone = rel && lm->anchor_clone ? lm->anchor_clone[f] : -1;
+      if (rel && (d.anchor_cam < 0 || d.anchor_cam >= fr->n_cams || d.anchor_clone < 0 || d.anchor_clone >= fr->n_clones)) {
+        snprintf(ctx->err, sizeof(ctx->err), "landmark %d: anchored representation without a valid anchor", f);
+        return OVB_ERR_ARG;
+      }
+      for (int k = 0; k < 3; k++) {
+        d.p_FinA[k] = lm->value[3 * f + k]; // meaning depends on the representation: the kernel reads the right one
+        d.p_FinG[k] = lm->value[3 * f + k];
+        d.p_FinG_fej[k] = lm->value_fej[3 * f + k];
+      }
+      if (lm->sigma_pix)
+        d.sigma_sq = std::pow(lm->sigma_pix[f], 2);
+      if (lm->chi2_multipler)
+        d.chi2_mult = lm->chi2_multipler[f];
+    }
     if (given) {
       d.status = given->status ? given->status[f] : OVB_FEAT_OK;
       d.anchor_cam = given->anchor_cam ? given->anchor_cam[f] : -1;
@@ -656,16 +697,21 @@ __global__ void k_fill_zero_dx(double *dx, int N) {
 // The device pipeline of one update on inputs already in the arena: steps 2-6 of UpdaterMSCKF::update.
 // ev (optional): ev[1] after triangulation, ev[2] after the per-feature systems, ev[3] after the column map, ev[4] after
 // compression, ev[5] after the EKF update. Returns the row count handed to the EKF update.
-static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, int m_total, int n_all, int col_order, cudaEvent_t *ev) {
+// slam: UpdaterSLAM::update — landmarks come from the state (no triangulation), rows are kept unprojected and whitened.
+static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, int m_total, int n_all, int col_order, cudaEvent_t *ev,
+                          bool slam = false) {
   const int N = ctx->N;
   ctx->n_launch = 0;
   ctx->n_launch_tsqr_level = 0;
-  launch_cam_poses(ctx);
-  launch_triangulate(ctx, F, bv);
-  ctx->n_launch += 4; // cam poses, triangulate, feature systems, column map
+  if (!slam) {
+    launch_cam_poses(ctx);
+    launch_triangulate(ctx, F, bv);
+    ctx->n_launch += 2;
+  }
+  ctx->n_launch += 2; // feature systems, column map
   if (ev)
     cudaEventRecord(ev[1], ctx->stream);
-  launch_feature_system(ctx, F, bv, ldH, 0, max_M);
+  launch_feature_system(ctx, F, bv, ldH, slam ? 2 : 0, max_M);
   if (ev)
     cudaEventRecord(ev[2], ctx->stream);
   // the column bookkeeping (a single serial CTA) only feeds the re-ordering and the EKF update: it runs on the side
@@ -675,7 +721,7 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
     cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = ctx->side_stream;
-    launch_column_map(ctx, F, bv);
+    launch_column_map(ctx, F, bv, slam ? 0 : 3);
     ctx->stream = main_stream;
     cudaEventRecord(ctx->ev_join, ctx->side_stream);
   }
@@ -702,7 +748,7 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
   const int r = (ctx->h_opts->o.compress == OVB_COMPRESS_NORMAL_EQUATIONS && m_total > 0) ? n_all : std::min(m_total, n_all);
   if (r > 0) {
     ovb_launch(ctx, k_take_z, dim3((r + 127) / 128), dim3(128), (size_t)(0), Rfinal, ldR, r, n_all, ctx->d_w);
-    launch_ekf_update(ctx, Rfinal, ldR, r, n_all, false, ctx->h_opts->sigma_pix_sq, nullptr);
+    launch_ekf_update(ctx, Rfinal, ldR, r, n_all, false, slam ? 1.0 : ctx->h_opts->sigma_pix_sq, nullptr);
     ctx->n_launch += 7; // take_z + prep, 2 gemm, chol, trsm, downdate
   } else {
     k_fill_zero_dx<<<(N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_dx, N);
@@ -837,6 +883,85 @@ ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat
     stats->rows_stacked = inf->rows_stacked;
     stats->cols_stacked = inf->n_used;
     stats->rows_update = std::min(inf->rows_stacked, inf->n_used);
+    stats->neg_diag_index = (r > 0 && inf->neg_diag_index != 0x7fffffff) ? inf->neg_diag_index : -1;
+    stats->ms_total = ctx->stage_ms[5];
+  }
+  if (r > 0) {
+    if (inf->not_spd) {
+      snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: innovation covariance not positive definite");
+      return OVB_ERR_NOT_SPD;
+    }
+    if (inf->nonfinite) {
+      snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: non-finite covariance entry");
+      return OVB_ERR_NONFINITE;
+    }
+    if (inf->neg_diag_index != 0x7fffffff) {
+      snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: diagonal at %d is negative", inf->neg_diag_index);
+      return OVB_ERR_NEG_DIAG;
+    }
+  }
+  return OVB_OK;
+}
+
+// UpdaterSLAM::update steps 4-5 (update/UpdaterSLAM.cpp:310-470) on the device: same per-feature kernel in its SLAM mode
+// (landmark block appended, no nullspace projection, per-class noise and gate), then the shared compress + EKF stages.
+ovb_status ovb_slam_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_landmarks *landmarks,
+                           const ovb_opts *opts, ovb_feat_out *out, double *dx, ovb_stats *stats) {
+  if (!ctx || !dx || !landmarks || !opts)
+    return OVB_ERR_ARG;
+  if (ctx->N < 1) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_slam_update: no covariance loaded (ovb_cov_set)");
+    return OVB_ERR_ARG;
+  }
+  if (opts->feat_rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_slam_update: ANCHORED_INVERSE_DEPTH_SINGLE landmarks are not supported yet");
+    return OVB_ERR_ARG;
+  }
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const int N = ctx->N;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->neg_diag_index = -1;
+  }
+  for (int i = 0; i < N; i++)
+    dx[i] = 0.0;
+  if (!feats || feats->n_feats <= 0) // UpdaterSLAM.cpp:256-257
+    return OVB_OK;
+  cudaEventRecord(ctx->ev[0], ctx->stream);
+  Packed pk;
+  ovb_status st = pack_inputs(ctx, frame, feats, opts, nullptr, &pk, landmarks);
+  if (st != OVB_OK)
+    return st;
+  const int F = pk.n_feats;
+  ctx->last_pk_valid = 0; // the replay path re-runs MSCKF updates only
+  const int r = enqueue_update(ctx, pk.n_feats, pk.bv, pk.ldH, pk.max_M, pk.m_total, pk.n_all, opts->col_order, ctx->ev, true);
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + sizeof(DevUpdateInfo) + sizeof(double) * (size_t)N;
+  cudaEventRecord(ctx->ev[6], ctx->stream);
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (out) {
+    for (int f = 0; f < F; f++) {
+      if (out->status)
+        out->status[f] = ctx->h_feat[f].status;
+      if (out->chi2)
+        out->chi2[f] = ctx->h_feat[f].chi2;
+    }
+  }
+  for (int i = 0; i < N; i++)
+    dx[i] = ctx->h_dx[i];
+  for (int s = 0; s < 5; s++)
+    cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
+  cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[0], ctx->ev[6]);
+  const DevUpdateInfo *inf = ctx->h_info;
+  if (stats) {
+    stats->n_feats_in = F;
+    stats->n_feats_used = inf->n_feats_used;
+    stats->rows_stacked = inf->rows_stacked;
+    stats->cols_stacked = inf->n_used;
+    stats->rows_update = inf->rows_stacked; // what the reference hands to EKFUpdate (it never compresses here)
     stats->neg_diag_index = (r > 0 && inf->neg_diag_index != 0x7fffffff) ? inf->neg_diag_index : -1;
     stats->ms_total = ctx->stage_ms[5];
   }

@@ -53,6 +53,11 @@ struct DevFeat {
   int sched, pad0;   // CTA i of the per-feature kernels works on feature feats[i].sched (longest tracks first)
   double p_FinA[3], p_FinG[3];
   double chi2;
+  // SLAM update only (landmark already in the state, update/UpdaterSLAM.cpp:333-341, :389-408)
+  double p_FinG_fej[3]; // Landmark::get_xyz(true) for the global representations
+  double sigma_sq;      // per-class pixel noise variance
+  double chi2_mult;     // per-class gate multiplier
+  int lm_slot, pad1;    // slot of the landmark's own 3-wide variable
 };
 
 // written by the column-map kernel; read by TSQR re-order, EKF and the host (D2H with the outputs)
@@ -165,7 +170,7 @@ void launch_triangulate(ovb_ctx *ctx, int n_feats, BlobView bv);
 // mode 0: normal (write post-nullspace rows to Hs, gate on chi²); mode 1: dump pre-nullspace dense rows to d_dump
 // mode 2: like 0 but features keep the status/p_FinG given (no triangulation ran) — used by ovb_feature_jacobians
 void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int mode, int max_M);
-void launch_column_map(ovb_ctx *ctx, int n_feats, BlobView bv);
+void launch_column_map(ovb_ctx *ctx, int n_feats, BlobView bv, int rows_drop = 3);
 // TSQR of A [m x (n+1)] (last column = residual) in place; R (n x (n+1), diag>=0) to Rout with leading dimension ldR
 void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR);
 // gather columns of Rin in the order info->col_canon (n_used of them) into Hs scratch and re-triangularise into Rout

@@ -1,0 +1,83 @@
+"""ovb_slam_update (UpdaterSLAM::update steps 4-5, update/UpdaterSLAM.cpp:310-470) on the GPU against the oracle."""
+import numpy as np
+import pytest
+
+from open_vins_b200 import capi, sim
+
+pytestmark = pytest.mark.gpu
+
+REPS = [capi.REP_GLOBAL_3D, capi.REP_GLOBAL_FULL_INVERSE_DEPTH, capi.REP_ANCHORED_3D, capi.REP_ANCHORED_FULL_INVERSE_DEPTH,
+        capi.REP_ANCHORED_MSCKF_INVERSE_DEPTH]
+
+
+def _check(eng, oracle, case, opts):
+    ref = oracle.slam_update(case.frame, case.feats, case.landmarks, opts, case.P)
+    eng.cov_set(case.P)
+    st, out, dx, stats = eng.slam_update(case.frame, case.feats, case.landmarks, opts)
+    assert st == ref["status"] == 0
+    assert np.array_equal(out.status, ref["out"].status)
+    ok = ref["out"].status == 0
+    np.testing.assert_allclose(out.chi2[ok], ref["out"].chi2[ok], rtol=1e-8)
+    assert stats.n_feats_used == ref["stats"].n_feats_used and stats.rows_stacked == ref["stats"].rows_stacked
+    assert stats.cols_stacked == ref["stats"].cols_stacked
+    Pg = eng.cov_get()
+    assert np.linalg.norm(Pg - ref["P"]) <= 1e-9 * np.linalg.norm(ref["P"])
+    assert np.linalg.norm(dx - ref["dx"]) <= 1e-9 * max(np.linalg.norm(ref["dx"]), 1e-300)
+    assert np.array_equal(Pg, Pg.T)
+    return ref, out, stats
+
+
+@pytest.mark.parametrize("rep", REPS)
+@pytest.mark.parametrize("order", [capi.COLS_REFERENCE_FIRST_SEEN, capi.COLS_CANONICAL])
+def test_slam_update_parity(oracle, rep, order):
+    case = sim.make_slam_case(n_landmarks=14, n_clones=8, n_cams=2, seed=60 + rep, rep=rep)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, feat_rep=rep, col_order=order)
+    eng = capi.Engine(max_state=256, max_feats=256, max_meas=4096)
+    ref, out, stats = _check(eng, oracle, case, opts)
+    assert stats.n_feats_used >= 8
+    eng.close()
+
+
+def test_slam_update_gate_and_no_calibration(oracle):
+    """Landmarks far from where the measurements put them are rejected by the chi² gate (per-class multiplier); the rest
+    updates the state. Mono, no calibration columns, global representation."""
+    case = sim.make_slam_case(n_landmarks=20, n_clones=6, n_cams=1, seed=5, rep=capi.REP_GLOBAL_3D, calib_ext=False, calib_intr=False)
+    lm = case.landmarks
+    val = lm.value.copy()
+    val[[2, 7, 11]] += np.array([0.8, -0.6, 0.9])  # gross landmark errors
+    case.landmarks = capi.LandmarkArrays(lm.lm_off, val, lm.value_fej, lm.anchor_cam, lm.anchor_clone, lm.sigma_pix, lm.chi2_multipler)
+    opts = capi.default_opts(feat_rep=capi.REP_GLOBAL_3D, col_order=capi.COLS_CANONICAL)
+    eng = capi.Engine(max_state=256, max_feats=256, max_meas=4096)
+    ref, out, stats = _check(eng, oracle, case, opts)
+    assert (out.status[[2, 7, 11]] == capi.FEAT_CHI2).all() and 10 <= stats.n_feats_used <= 17
+    eng.close()
+
+
+def test_msckf_then_slam_on_the_resident_covariance(oracle):
+    """VioManager order (core/VioManager.cpp:525-547): MSCKF update, then the SLAM update, P staying on the device."""
+    rep = capi.REP_GLOBAL_3D
+    sl = sim.make_slam_case(n_landmarks=10, n_clones=8, n_cams=2, seed=9, rep=rep)
+    ms = sim.make_update_case(n_feats=40, n_clones=8, n_cams=2, seed=9, calib_ext=True, calib_intr=True)
+    assert np.array_equal(ms.frame.clone_R, sl.frame.clone_R)  # same window (same seed): the landmarks extend the state
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, feat_rep=rep, col_order=capi.COLS_CANONICAL)
+    eng = capi.Engine(max_state=256, max_feats=256, max_meas=4096)
+    eng.cov_set(sl.P)
+    st, out, dx, stats = eng.msckf_update(ms.frame, ms.feats, opts)
+    r1 = oracle.msckf_update(ms.frame, ms.feats, opts, sl.P, dumps=False)
+    assert st == 0 and np.array_equal(out.status, r1["out"].status)
+    st, out2, dx2, stats2 = eng.slam_update(sl.frame, sl.feats, sl.landmarks, opts)
+    r2 = oracle.slam_update(sl.frame, sl.feats, sl.landmarks, opts, r1["P"])
+    assert st == 0 and np.array_equal(out2.status, r2["out"].status)
+    assert np.linalg.norm(eng.cov_get() - r2["P"]) <= 1e-9 * np.linalg.norm(r2["P"])
+    assert np.linalg.norm(dx2 - r2["dx"]) <= 1e-9 * np.linalg.norm(r2["dx"])
+    eng.close()
+
+
+def test_slam_update_argument_errors():
+    case = sim.make_slam_case(n_landmarks=4, n_clones=5, n_cams=1, seed=1, rep=0, calib_ext=False, calib_intr=False)
+    eng = capi.Engine(max_state=256, max_feats=64, max_meas=1024)
+    eng.cov_set(case.P)
+    opts = capi.default_opts(feat_rep=capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE)
+    with pytest.raises(capi.OvbError):
+        eng.slam_update(case.frame, case.feats, case.landmarks, opts)
+    eng.close()
