@@ -7,6 +7,7 @@
 //   ov_msckf::State                       ov_msckf/src/state/State.h:49-193
 //   ov_msckf::StateHelper                 ov_msckf/src/state/StateHelper.h (EKFPropagation, EKFUpdate, clone, marginalize, ...)
 //   ov_msckf::UpdaterMSCKF::update        ov_msckf/src/update/UpdaterMSCKF.cpp:58-295
+//   ov_type::Landmark, UpdaterSLAM::update ov_core/src/types/Landmark.h, ov_msckf/src/update/UpdaterSLAM.cpp:253-479
 // What differs, on purpose:
 //   * no Eigen: matrices are row-major std::vector<double>; rotations are 3x3 row-major R_GtoI / R_ItoC (JPL convention);
 //   * the covariance lives on the GPU inside the engine context (State owns an ovb_ctx instead of an Eigen _Cov);
@@ -97,6 +98,22 @@ struct Camera {
   int model = OVB_CAM_RADTAN;                      // cam/CamRadtan.h or cam/CamEqui.h
 };
 
+// ov_type::Landmark (types/Landmark.h:35-97) reduced to what UpdaterSLAM::update reads. xyz / xyz_fej are what
+// Landmark::get_xyz(false) / get_xyz(true) return (p_FinG for the global representations, p_FinA for the anchored ones);
+// the caller's Landmark keeps the representation's own parameters and applies dx to them.
+struct Landmark {
+  int id = -1; // first row/column of the 3-wide block in the covariance
+  size_t _featid = 0;
+  int _feat_representation = OVB_REP_GLOBAL_3D;
+  int _anchor_cam_id = -1;
+  double _anchor_clone_timestamp = -1;
+  double xyz[3] = {0, 0, 0};
+  double xyz_fej[3] = {0, 0, 0};
+  int update_fail_count = 0;
+  bool should_marg = false;
+  int size() const { return 3; }
+};
+
 // the StateOptions fields the path reads (state/StateOptions.h:35-176)
 struct StateOptions {
   bool do_fej = true;
@@ -105,6 +122,8 @@ struct StateOptions {
   int feat_rep_msckf = OVB_REP_GLOBAL_3D;
   int num_cameras = 1;
   int max_clone_size = 11;
+  int feat_rep_slam = OVB_REP_GLOBAL_3D;
+  int max_aruco_features = 0; // feature ids below this are ArUco tags with their own noise / gate (UpdaterSLAM.cpp:391-393)
 };
 
 // ov_msckf::State (state/State.h:49-193): the sliding window and calibration; the covariance is device-resident.
@@ -113,6 +132,7 @@ public:
   StateOptions _options;
   std::map<double, std::shared_ptr<PoseJPL>> _clones_IMU; // State.h:130
   std::vector<Camera> _cameras;                           // index = camera id
+  std::unordered_map<size_t, std::shared_ptr<Landmark>> _features_SLAM; // State.h:172
 
   State(const StateOptions &options, const ovb_config &cfg) : _options(options) {
     ovb_status st = ovb_create(&cfg, &_ctx);
@@ -395,6 +415,133 @@ public:
 
 private:
   UpdaterOptions _options;
+  FeatureInitializerOptions _init;
+};
+
+// ov_msckf::UpdaterSLAM::update (update/UpdaterSLAM.cpp:253-479): update of the landmarks that already live in the state.
+// delayed_init / change_anchors are not part of the engine yet.
+class UpdaterSLAM {
+public:
+  UpdaterSLAM(const UpdaterOptions &options_slam, const UpdaterOptions &options_aruco, const FeatureInitializerOptions &feat_init_options)
+      : _options_slam(options_slam), _options_aruco(options_aruco), _init(feat_init_options) {}
+
+  int col_order = OVB_COLS_REFERENCE_FIRST_SEEN;
+  ovb_stats last_stats{};
+
+  // Same contract as the reference: measurements are cleaned to the clone times; features without measurements are
+  // marked to_delete and dropped (:283-285); a chi² rejection bumps Landmark::update_fail_count (non-ArUco), marks the
+  // feature to_delete and erases it (:409-420); what remains in feature_vec was used (all to_delete, :452-454). Returns dx.
+  std::vector<double> update(State &state, std::vector<std::shared_ptr<Feature>> &feature_vec) {
+    std::vector<double> dx((size_t)state.max_covariance_size(), 0.0);
+    if (feature_vec.empty())
+      return dx;
+    std::vector<double> clonetimes;
+    for (const auto &c : state._clones_IMU)
+      clonetimes.push_back(c.first);
+    for (auto it = feature_vec.begin(); it != feature_vec.end();) {
+      (*it)->clean_old_measurements(clonetimes);
+      int ct_meas = 0;
+      for (const auto &pair : (*it)->timestamps)
+        ct_meas += (int)pair.second.size();
+      if (ct_meas < 1) {
+        (*it)->to_delete = true;
+        it = feature_vec.erase(it);
+      } else
+        ++it;
+    }
+    if (feature_vec.empty())
+      return dx;
+    // window + cameras (same marshalling as UpdaterMSCKF::update)
+    const int C = (int)state._clones_IMU.size(), K = (int)state._cameras.size();
+    std::vector<double> cR((size_t)9 * C), cp((size_t)3 * C), cRf((size_t)9 * C), cpf((size_t)3 * C), kR((size_t)9 * K), kp((size_t)3 * K), kin((size_t)8 * K);
+    std::vector<int> coff((size_t)C), kmodel((size_t)K), kext((size_t)K), kintr((size_t)K);
+    int ci = 0;
+    for (const auto &cl : state._clones_IMU) {
+      std::copy(cl.second->Rot, cl.second->Rot + 9, cR.begin() + 9 * ci);
+      std::copy(cl.second->pos, cl.second->pos + 3, cp.begin() + 3 * ci);
+      std::copy(cl.second->Rot_fej, cl.second->Rot_fej + 9, cRf.begin() + 9 * ci);
+      std::copy(cl.second->pos_fej, cl.second->pos_fej + 3, cpf.begin() + 3 * ci);
+      coff[(size_t)ci++] = cl.second->id;
+    }
+    for (int k = 0; k < K; k++) {
+      const Camera &cam = state._cameras[(size_t)k];
+      std::copy(cam.R_ItoC, cam.R_ItoC + 9, kR.begin() + 9 * k);
+      std::copy(cam.p_IinC, cam.p_IinC + 3, kp.begin() + 3 * k);
+      std::copy(cam.intrinsics, cam.intrinsics + 8, kin.begin() + 8 * k);
+      kmodel[(size_t)k] = cam.model;
+      kext[(size_t)k] = state._options.do_calib_camera_pose ? cam.calib_id : -1;
+      kintr[(size_t)k] = state._options.do_calib_camera_intrinsics ? cam.intrinsics_id : -1;
+    }
+    ovb_frame frame{C, K, cR.data(), cp.data(), cRf.data(), cpf.data(), coff.data(), kR.data(), kp.data(), kin.data(), kmodel.data(), kext.data(), kintr.data()};
+    // features + their landmarks
+    const int F = (int)feature_vec.size();
+    std::vector<int32_t> meas_off(1, 0), keys_off(1, 0), lm_off, acam, aclone;
+    std::vector<uint8_t> cam, keys;
+    std::vector<uint16_t> clone;
+    std::vector<float> uv, uvn;
+    std::vector<double> val, val_fej, sig, mult;
+    for (const auto &feat : feature_vec) {
+      const std::shared_ptr<Landmark> &lm = state._features_SLAM.at(feat->featid); // UpdaterSLAM.cpp:316
+      for (const auto &pair : feat->timestamps) {
+        keys.push_back((uint8_t)pair.first);
+        const auto &fuv = feat->uvs.at(pair.first);
+        const auto &fuvn = feat->uvs_norm.at(pair.first);
+        for (size_t m = 0; m < pair.second.size(); m++) {
+          cam.push_back((uint8_t)pair.first);
+          clone.push_back((uint16_t)(std::lower_bound(clonetimes.begin(), clonetimes.end(), pair.second[m]) - clonetimes.begin()));
+          uv.push_back(fuv[m][0]);
+          uv.push_back(fuv[m][1]);
+          uvn.push_back(fuvn[m][0]);
+          uvn.push_back(fuvn[m][1]);
+        }
+      }
+      meas_off.push_back((int32_t)cam.size());
+      keys_off.push_back((int32_t)keys.size());
+      lm_off.push_back(lm->id);
+      for (int k = 0; k < 3; k++) {
+        val.push_back(lm->xyz[k]);
+        val_fej.push_back(lm->xyz_fej[k]);
+      }
+      acam.push_back(lm->_anchor_cam_id);
+      aclone.push_back(lm->_anchor_cam_id >= 0
+                           ? (int32_t)(std::lower_bound(clonetimes.begin(), clonetimes.end(), lm->_anchor_clone_timestamp) - clonetimes.begin())
+                           : -1);
+      const bool aruco = (int)feat->featid < state._options.max_aruco_features;
+      sig.push_back(aruco ? _options_aruco.sigma_pix : _options_slam.sigma_pix);
+      mult.push_back(aruco ? _options_aruco.chi2_multipler : _options_slam.chi2_multipler);
+    }
+    ovb_feat_batch batch{F, (int)cam.size(), meas_off.data(), cam.data(), clone.data(), uv.data(), uvn.data(), keys_off.data(), keys.data()};
+    ovb_landmarks lms{lm_off.data(), val.data(), val_fej.data(), acam.data(), aclone.data(), sig.data(), mult.data()};
+    ovb_opts o;
+    ovb_opts_default(&o);
+    o.sigma_pix = _options_slam.sigma_pix;
+    o.chi2_multipler = _options_slam.chi2_multipler;
+    o.do_fej = state._options.do_fej;
+    o.feat_rep = state._options.feat_rep_slam;
+    o.do_calib_camera_pose = state._options.do_calib_camera_pose;
+    o.do_calib_camera_intrinsics = state._options.do_calib_camera_intrinsics;
+    o.col_order = col_order;
+    std::vector<int32_t> status((size_t)F);
+    std::vector<double> chi2((size_t)F);
+    ovb_feat_out out{status.data(), nullptr, nullptr, nullptr, nullptr, chi2.data()};
+    state.check(ovb_slam_update(state.ctx(), &frame, &batch, &lms, &o, &out, dx.data(), &last_stats), "UpdaterSLAM::update");
+    std::vector<std::shared_ptr<Feature>> used;
+    for (int f = 0; f < F; f++) {
+      Feature &feat = *feature_vec[(size_t)f];
+      feat.last_status = status[(size_t)f];
+      feat.last_chi2 = chi2[(size_t)f];
+      feat.to_delete = true;
+      if (status[(size_t)f] == OVB_FEAT_OK)
+        used.push_back(feature_vec[(size_t)f]);
+      else if ((int)feat.featid >= state._options.max_aruco_features)
+        state._features_SLAM.at(feat.featid)->update_fail_count++; // UpdaterSLAM.cpp:414
+    }
+    feature_vec.swap(used);
+    return dx;
+  }
+
+private:
+  UpdaterOptions _options_slam, _options_aruco;
   FeatureInitializerOptions _init;
 };
 

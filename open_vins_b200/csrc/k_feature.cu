@@ -200,6 +200,8 @@ __device__ __forceinline__ bool rep_is_relative(int rep) {
 // mode 0: full (gate + write projected rows to Hs)   mode 1: dump pre-nullspace dense rows to `dump`
 // mode 2: SLAM update (update/UpdaterSLAM.cpp:310-447): the landmark is a state variable (block 5 = H_f, slot lm_slot),
 //         no nullspace projection (all 2M rows are kept), per-feature noise / gate multiplier, rows whitened by 1/sigma
+// The SLAM variant is a separate instantiation so that the MSCKF hot path carries none of its code or registers.
+template <bool SLAM>
 __global__ void __launch_bounds__(FT_THREADS, 2)
     k_feature_system(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, DevFeat *__restrict__ feats, int n_feats, BlobView bv,
                      const double *__restrict__ P, int ldP, const double *__restrict__ chi2_table, double *__restrict__ Hs, int ldH,
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
   const int n_slots = fr->n_slots;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n_all8 = (n_all + 7) & ~7;
-  const bool slam = (mode == 2);
+  constexpr bool slam = SLAM;
   const int r0 = slam ? 0 : 3; // rows removed by the nullspace projection
   // ---- shared memory carve-up (mirrors feature_smem_bytes)
   size_t o = 0;
@@ -923,7 +925,8 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
   bool S_in_smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, true) <= smem_limit;
   size_t smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, S_in_smem);
   if (!ctx->attr_done[1]) { // function attributes are per device: one flag per context
-    cudaFuncSetAttribute(k_feature_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    cudaFuncSetAttribute(k_feature_system<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    cudaFuncSetAttribute(k_feature_system<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     ctx->attr_done[1] = 1;
   }
   int grid = n_feats;
@@ -934,7 +937,12 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
     scratch = ctx->d_scratch;
   }
   int dump_rows = ctx->dump_rows; // rows of the current dump (set by ovb_feature_jacobians)
-  ovb_launch(ctx, k_feature_system, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv, ctx->P[ctx->cur], ctx->ldP,
-                                                            ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk,
-                                                            scratch, ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
+  if (mode == 2)
+    ovb_launch(ctx, k_feature_system<true>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv,
+               ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,
+               ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
+  else
+    ovb_launch(ctx, k_feature_system<false>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv,
+               ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,
+               ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
 }

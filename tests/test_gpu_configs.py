@@ -88,3 +88,39 @@ def test_config5_tsqr_ekf_microbench(structured):
     assert np.linalg.norm(eng.cov_get() - Pn) <= 1e-9 * np.linalg.norm(Pn)
     assert np.linalg.norm(dx2 - dxn) <= 1e-9 * np.linalg.norm(dxn)
     eng.close()
+
+
+def test_config4_window_msckf_and_slam(oracle):
+    """Config 4's window (4 cameras, 31 clone poses, tracks of up to 124 measurements: the per-feature innovation is
+    245 x 245 and lives in the kernel's global-memory scratch instead of shared memory) with online calibration, then a
+    SLAM update of 25 landmarks: 31 + 8 + 25 = 64 state variables, the engine's per-call limit. Oracle parity at a
+    feature count the CPU restatement finishes in about a second."""
+    ms = sim.make_update_case(n_feats=40, n_clones=31, n_cams=4, seed=4, calib_ext=True, calib_intr=True)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, col_order=capi.COLS_CANONICAL)
+    assert int((ms.feats.meas_off[1:] - ms.feats.meas_off[:-1]).max()) == 124
+    eng = capi.Engine(max_state=384, max_feats=256, max_meas=8192)
+    eng.cov_set(ms.P)
+    st, out, dx, stats = eng.msckf_update(ms.frame, ms.feats, opts)
+    ref = oracle.msckf_update(ms.frame, ms.feats, opts, ms.P, dumps=False)
+    assert st == ref["status"] == 0 and np.array_equal(out.status, ref["out"].status) and stats.n_feats_used > 30
+    ok = ref["out"].status == 0
+    np.testing.assert_allclose(out.chi2[ok], ref["out"].chi2[ok], rtol=1e-8)
+    assert np.linalg.norm(eng.cov_get() - ref["P"]) <= 1e-9 * np.linalg.norm(ref["P"])
+    assert np.linalg.norm(dx - ref["dx"]) <= 1e-9 * np.linalg.norm(ref["dx"])
+    sl = sim.make_slam_case(n_landmarks=25, n_clones=31, n_cams=4, seed=4, rep=capi.REP_GLOBAL_3D)
+    eng.cov_set(sl.P)
+    st, out, dx, stats = eng.slam_update(sl.frame, sl.feats, sl.landmarks, opts)
+    ref = oracle.slam_update(sl.frame, sl.feats, sl.landmarks, opts, sl.P)
+    assert st == ref["status"] == 0 and np.array_equal(out.status, ref["out"].status) and stats.n_feats_used > 15
+    assert stats.cols_stacked == ref["stats"].cols_stacked
+    assert np.linalg.norm(eng.cov_get() - ref["P"]) <= 1e-9 * np.linalg.norm(ref["P"])
+    assert np.linalg.norm(dx - ref["dx"]) <= 1e-9 * np.linalg.norm(ref["dx"])
+    # one landmark more than the limit: a clear capacity error, not a wrong answer
+    sl2 = sim.make_slam_case(n_landmarks=26, n_clones=31, n_cams=4, seed=4, rep=capi.REP_GLOBAL_3D)
+    eng2 = capi.Engine(max_state=384, max_feats=256, max_meas=8192)
+    eng2.cov_set(sl2.P)
+    with pytest.raises(capi.OvbError) as ei:
+        eng2.slam_update(sl2.frame, sl2.feats, sl2.landmarks, opts)
+    assert ei.value.code == capi.OVB_ERR_CAPACITY
+    eng.close()
+    eng2.close()

@@ -103,7 +103,7 @@ def test_cpp_host_mirror_runs_the_update(oracle, name, tmp_path):
 
 def test_host_header_compiles_standalone():
     """CPU-only: the C++ mirror is plain C++17 over the C ABI (no CUDA, no Eigen needed to compile against it)."""
-    src = "#include \"ovb200_host.hpp\"\nint main() { ovb200::UpdaterOptions o; return o.sigma_pix > 0 ? 0 : 1; }\n"
+    src = "#include \"ovb200_host.hpp\"\nint main() { ovb200::UpdaterOptions o; ovb200::FeatureInitializerOptions fo; ovb200::UpdaterSLAM us(o, o, fo); ovb200::UpdaterMSCKF um(o, fo); (void)us; (void)um; return o.sigma_pix > 0 ? 0 : 1; }\n"
     res = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-"],
                          input=src, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
