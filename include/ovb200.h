@@ -214,6 +214,16 @@ ovb_status ovb_cov_marginalize(ovb_ctx *ctx, int off, int size);
 ovb_status ovb_cov_propagate(ovb_ctx *ctx, int new_off, int p, const int *old_off, const int *old_sz, int nold,
                              const double *Phi, const double *Q);
 
+/* StateHelper::initialize + initialize_invertible (state/StateHelper.cpp:393-577): add a NEW `new_size`-wide variable (a SLAM
+ * landmark in UpdaterSLAM::delayed_init, update/UpdaterSLAM.cpp:233) at the END of the covariance from the linear system
+ *     res = H_R * dx(state variables off/sz) + H_L * dx(new) + n,   n ~ N(0, sigma2 I)      (H_R r x n, H_L r x new_size, row-major)
+ * Givens split on H_L, Mahalanobis gate of the nullspace-projected part (threshold chi2_mult * quantile95(r)), covariance
+ * augmentation from the invertible part, EKF update with the projected part. *accepted = 0: gate rejected, P unchanged.
+ * dx_new[new_size] = H_Linit^-1 res_init (the new variable's own correction); dx[ovb_cov_dim() AFTER the call] is the EKF
+ * correction of the projected part (it also moves the new variable through its cross-covariance). */
+ovb_status ovb_cov_initialize(ovb_ctx *ctx, const int *off, const int *sz, int nvar, const double *H_R, const double *H_L, const double *res,
+                              int r, int new_size, double sigma2, double chi2_mult, int *accepted, double *dx_new, double *dx);
+
 /* ---- the hot path ---- */
 /* UpdaterMSCKF::update steps 2-6 in one call (update/UpdaterMSCKF.cpp:98-285). P is updated in place on the device;
  * dx (length N = ovb_cov_dim) is the correction K·res that the host applies with Type::update

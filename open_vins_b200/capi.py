@@ -254,6 +254,8 @@ def load_library(path: str | None = None) -> C.CDLL:
                                      C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
     lib.ovb_ekf_update.argtypes = [vp, c_int_p, c_int_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_double,
                                    c_double_p, c_double_p]
+    lib.ovb_cov_initialize.argtypes = [vp, c_int_p, c_int_p, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, C.c_double,
+                                       C.c_double, c_int_p, c_double_p, c_double_p]
     lib.ovb_slam_update.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_landmarks), C.POINTER(ovb_opts),
                                     C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
     lib.ovb_triangulate.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts),
@@ -280,7 +282,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
-    "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate",
+    "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate", "ovb_cov_initialize",
     "ovb_msckf_update", "ovb_slam_update", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram",
     "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
     "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_finish",
@@ -359,6 +361,23 @@ class Engine:
         return self._check(self.lib.ovb_cov_propagate(self.h, new_off, Phi.shape[0], _ptr(old_off, c_int_p),
                                                       _ptr(old_sz, c_int_p), len(old_off), _ptr(Phi, c_double_p),
                                                       _ptr(Q, c_double_p)), allow=(OVB_ERR_NEG_DIAG,))
+
+    def cov_initialize(self, off, sz, H_R, H_L, res, sigma2=1.0, chi2_mult=1.0):
+        """StateHelper::initialize: returns (status, accepted, dx_new[k], dx[N after the call])."""
+        off = np.ascontiguousarray(off, dtype=np.int32)
+        sz = np.ascontiguousarray(sz, dtype=np.int32)
+        H_R = np.ascontiguousarray(H_R, dtype=np.float64)
+        H_L = np.ascontiguousarray(H_L, dtype=np.float64)
+        res = np.ascontiguousarray(res, dtype=np.float64)
+        r, k = H_L.shape
+        acc = np.zeros(1, dtype=np.int32)
+        dx_new = np.zeros(k)
+        dx = np.zeros(self.cov_dim() + k)
+        st = self.lib.ovb_cov_initialize(self.h, _ptr(off, c_int_p), _ptr(sz, c_int_p), len(off), _ptr(H_R, c_double_p), _ptr(H_L, c_double_p),
+                                         _ptr(res, c_double_p), r, k, float(sigma2), float(chi2_mult), _ptr(acc, c_int_p), _ptr(dx_new, c_double_p),
+                                         _ptr(dx, c_double_p))
+        self._check(st, allow=(OVB_ERR_NEG_DIAG,))
+        return st, bool(acc[0]), dx_new, dx[:self.cov_dim()]
 
     # ---- hot path
     def msckf_update(self, frame: FrameArrays, feats: FeatArrays, opts: ovb_opts, out: FeatOut | None = None):

@@ -253,8 +253,9 @@ __global__ void k_ekf_prep(DevUpdateInfo *info) {
 
 // H: r x n (row-major, ldHm), r <= n <= N (callers compress first when r > n); column j of H is state column
 // d_info->col_state[j]. Everything is enqueued on the context stream; flags land in d_info.
-void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bool sizes_from_info, double sigma2, const double *Rdiag_dev) {
-  (void)sizes_from_info;
+// gate_only: stop after the Cholesky — d_w then holds w = L^-1 res (|w|^2 = res' S^-1 res) and P is untouched
+// (the Mahalanobis test of StateHelper::initialize, StateHelper.cpp:458-470).
+void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bool gate_only, double sigma2, const double *Rdiag_dev) {
   const int N = ctx->N;
   const int ld = ctx->ldP;
   double *P = ctx->P[ctx->cur];
@@ -275,6 +276,8 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
   // the residual vector is column n of H's row (TSQR output) or a separate buffer: callers stage it in d_w
   double *invdiag = ctx->d_w + ctx->cfg.max_state; // d_w holds 4 x max_state doubles: [w | 1/diag(L) | ...]
   ovb_launch(ctx, k_ekf_chol, dim3(1), dim3(EKC_THREADS), (size_t)(use_smem ? chol_bytes : 0), ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
+  if (gate_only)
+    return;
   size_t trsm_small = sizeof(double) * ((size_t)TR_ROWS * r + r);
   size_t trsm_full = trsm_small + sizeof(double) * (size_t)r * (size_t)(r | 1);
   int L_in_smem = trsm_full <= 200 * 1024;
@@ -286,6 +289,69 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
 
 // ---------------------------------------------------------------------------------------------------------------------
 // covariance structure operations
+
+// StateHelper::initialize_invertible (StateHelper.cpp:484-577): grow P by the k-wide new variable.
+//   m = P[:, cols] Hx'            (N x k)     Hx = invertible part's state Jacobian (k x n), cols from info->col_state
+//   M = Hx P[cols, cols] Hx' + s2 I (k x k, upper triangle mirrored like selfadjointView<Upper>)
+//   P[0:N, N:N+k] = -m Hinv',  P[N:N+k, 0:N] = its transpose,  P[N:N+k, N:N+k] = Hinv M Hinv'
+// Single CTA (N <= a few hundred rows, k <= 3): the step is a serial point in the reference as well.
+__global__ void k_cov_init_augment(double *__restrict__ P, int ld, int N, int k, int n, const DevUpdateInfo *__restrict__ info,
+                                   const double *__restrict__ Hx, const double *__restrict__ Hinv, double sigma2) {
+  extern __shared__ double ism[]; // m[N][k], then M[k][k]
+  double *m = ism, *M = ism + (size_t)N * k;
+  const int tid = threadIdx.x;
+  for (int a = tid; a < N; a += blockDim.x) {
+    for (int i = 0; i < k; i++) {
+      double acc = 0.0;
+      for (int j = 0; j < n; j++)
+        acc += P[(size_t)a * ld + info->col_state[j]] * Hx[i * n + j];
+      m[a * k + i] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < k * k) {
+    const int i = tid / k, i2 = tid % k;
+    double acc = 0.0;
+    for (int j = 0; j < n; j++)
+      acc += Hx[i * n + j] * m[info->col_state[j] * k + i2];
+    M[i * k + i2] = acc + (i == i2 ? sigma2 : 0.0);
+  }
+  __syncthreads();
+  if (tid < k * k) {
+    const int i = tid / k, i2 = tid % k;
+    if (i2 < i)
+      M[i * k + i2] = M[i2 * k + i]; // selfadjointView<Upper>
+  }
+  __syncthreads();
+  for (int a = tid; a < N; a += blockDim.x) {
+    for (int q = 0; q < k; q++) {
+      double acc = 0.0;
+      for (int i = 0; i < k; i++)
+        acc += m[a * k + i] * Hinv[q * k + i];
+      P[(size_t)a * ld + N + q] = -acc;
+      P[(size_t)(N + q) * ld + a] = -acc;
+    }
+  }
+  if (tid < k * k) {
+    const int q = tid / k, q2 = tid % k;
+    double acc = 0.0;
+    for (int i = 0; i < k; i++)
+      for (int i2 = 0; i2 < k; i2++)
+        acc += Hinv[q * k + i] * M[i * k + i2] * Hinv[q2 * k + i2];
+    // the reference's dense product leaves P_LL symmetric only to rounding; write the upper entry to both places so the
+    // resident covariance stays exactly symmetric
+    if (q <= q2) {
+      P[(size_t)(N + q) * ld + N + q2] = acc;
+      P[(size_t)(N + q2) * ld + N + q] = acc;
+    }
+  }
+}
+
+void launch_cov_init_augment(ovb_ctx *ctx, int k, int n, const double *Hx_dev, const double *Hinv_dev, double sigma2) {
+  const int N = ctx->N;
+  size_t smem = sizeof(double) * ((size_t)N * k + (size_t)k * k);
+  k_cov_init_augment<<<1, 256, smem, ctx->stream>>>(ctx->P[ctx->cur], ctx->ldP, N, k, n, ctx->d_info, Hx_dev, Hinv_dev, sigma2);
+}
 
 // StateHelper::clone: append a copy of the `size`-wide variable at old_off (StateHelper.cpp:371-373)
 __global__ void k_cov_clone(double *P, int ld, int N, int old_off, int size) {

@@ -1258,4 +1258,201 @@ ovb_status ovb_ekf_update(ovb_ctx *ctx, const int *off, const int *sz, int nvar,
   return OVB_OK;
 }
 
+// StateHelper::initialize on the device-resident covariance. The Givens split of the (tiny) system and the 3x3 inverse are
+// host work in the reference's operation order; the gate, the augmentation and the update run on the GPU.
+ovb_status ovb_cov_initialize(ovb_ctx *ctx, const int *off, const int *sz, int nvar, const double *H_R_in, const double *H_L_in,
+                              const double *res_in, int r, int k, double sigma2, double chi2_mult, int *accepted, double *dx_new, double *dx) {
+  if (!ctx || !off || !sz || !H_R_in || !H_L_in || !res_in || !accepted || !dx_new || !dx || nvar < 1 || k < 1 || k > 3 || r < k)
+    return OVB_ERR_ARG;
+  if (ctx->N < 1 || !(sigma2 > 0.0))
+    return OVB_ERR_ARG;
+  const int N = ctx->N;
+  int n = 0;
+  for (int i = 0; i < nvar; i++) {
+    if (off[i] < 0 || sz[i] < 1 || off[i] + sz[i] > N)
+      return OVB_ERR_ARG;
+    n += sz[i];
+  }
+  if (n > OVB_MAX_COLS || n > ctx->cfg.max_state)
+    return OVB_ERR_CAPACITY;
+  if (N + k > ctx->ldP) {
+    snprintf(ctx->err, sizeof(ctx->err), "initialize: covariance would grow to %d (max_state %d)", N + k, ctx->ldP);
+    return OVB_ERR_CAPACITY;
+  }
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  *accepted = 0;
+  // ---- Givens split (StateHelper.cpp:429-440), row-major copies
+  std::vector<double> HR(H_R_in, H_R_in + (size_t)r * n), HL(H_L_in, H_L_in + (size_t)r * k), res(res_in, res_in + r);
+  auto rot = [](double c, double s, double &x, double &y) { // applyOnTheLeft(0, 1, G.adjoint()) on the pair (x, y)
+    const double x0 = x, y0 = y;
+    x = c * x0 - s * y0;
+    y = s * x0 + c * y0;
+  };
+  for (int c0 = 0; c0 < k; ++c0) {
+    for (int m = r - 1; m > c0; m--) {
+      // JacobiRotation::makeGivens(p, q) (Eigen/src/Jacobi/Jacobi.h, real branch): G' [p; q] = [r; 0], r >= 0
+      const double p = HL[(size_t)(m - 1) * k + c0], q = HL[(size_t)m * k + c0];
+      double gc, gs;
+      if (q == 0.0) {
+        gc = p < 0.0 ? -1.0 : 1.0;
+        gs = 0.0;
+      } else if (p == 0.0) {
+        gc = 0.0;
+        gs = q < 0.0 ? 1.0 : -1.0;
+      } else if (std::fabs(p) > std::fabs(q)) {
+        const double t = q / p;
+        double u = std::sqrt(1.0 + t * t);
+        if (p < 0.0)
+          u = -u;
+        gc = 1.0 / u;
+        gs = -t * gc;
+      } else {
+        const double t = p / q;
+        double u = std::sqrt(1.0 + t * t);
+        if (q < 0.0)
+          u = -u;
+        gs = -1.0 / u;
+        gc = -t * gs;
+      }
+      for (int j = c0; j < k; j++)
+        rot(gc, gs, HL[(size_t)(m - 1) * k + j], HL[(size_t)m * k + j]);
+      rot(gc, gs, res[m - 1], res[m]);
+      for (int j = 0; j < n; j++)
+        rot(gc, gs, HR[(size_t)(m - 1) * n + j], HR[(size_t)m * n + j]);
+    }
+  }
+  // ---- H_L^-1 of the invertible k x k block (Gauss-Jordan, partial pivoting)
+  double A[9], Inv[9];
+  for (int i = 0; i < k; i++)
+    for (int j = 0; j < k; j++) {
+      A[i * k + j] = HL[(size_t)i * k + j];
+      Inv[i * k + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c0 = 0; c0 < k; c0++) {
+    int piv = c0;
+    for (int i = c0 + 1; i < k; i++)
+      if (std::fabs(A[i * k + c0]) > std::fabs(A[piv * k + c0]))
+        piv = i;
+    if (!(std::fabs(A[piv * k + c0]) > 0.0)) {
+      snprintf(ctx->err, sizeof(ctx->err), "initialize: H_L is rank deficient");
+      return OVB_ERR_ARG;
+    }
+    if (piv != c0)
+      for (int j = 0; j < k; j++) {
+        std::swap(A[c0 * k + j], A[piv * k + j]);
+        std::swap(Inv[c0 * k + j], Inv[piv * k + j]);
+      }
+    const double d = A[c0 * k + c0];
+    for (int j = 0; j < k; j++) {
+      A[c0 * k + j] /= d;
+      Inv[c0 * k + j] /= d;
+    }
+    for (int i = 0; i < k; i++) {
+      if (i == c0)
+        continue;
+      const double f = A[i * k + c0];
+      for (int j = 0; j < k; j++) {
+        A[i * k + j] -= f * A[c0 * k + j];
+        Inv[i * k + j] -= f * Inv[c0 * k + j];
+      }
+    }
+  }
+  // ---- columns of the measuring variables
+  DevUpdateInfo *hi = ctx->h_info;
+  memset(hi, 0, sizeof(*hi));
+  {
+    int c = 0;
+    for (int i = 0; i < nvar; i++)
+      for (int q = 0; q < sz[i]; q++)
+        hi->col_state[c++] = off[i] + q;
+  }
+  const int rup = r - k;
+  const double *Hdev = nullptr;
+  int ld = 0, rr = 0;
+  if (rup > 0) {
+    // ---- gate on the projected part: chi2 = resup' (Hup P Hup' + s2 I)^-1 resup (StateHelper.cpp:458-470)
+    ovb_status st = stage_dense(ctx, HR.data() + (size_t)k * n, rup, n, res.data() + k, nullptr, &ld);
+    if (st != OVB_OK)
+      return st;
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_info, hi, sizeof(DevUpdateInfo), cudaMemcpyHostToDevice, ctx->stream));
+    Hdev = ctx->d_Hs;
+    rr = rup;
+    double res2 = 0.0;
+    for (int i = k; i < r; i++)
+      res2 += res[i] * res[i];
+    const bool compressed = rup > n;
+    if (compressed) { // orthogonal compression keeps S's relevant block; the dropped rows add |z2|^2 / s2 to chi2
+      launch_tsqr(ctx, ctx->d_Hs, rup, n, ld, ctx->d_R, ld);
+      Hdev = ctx->d_R;
+      rr = n;
+    }
+    ovb_launch(ctx, k_take_z, dim3((rr + 127) / 128), dim3(128), (size_t)(0), Hdev, ld, rr, n, ctx->d_w);
+    std::vector<double> zh((size_t)rr), wh((size_t)rr);
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(zh.data(), ctx->d_w, sizeof(double) * (size_t)rr, cudaMemcpyDeviceToHost, ctx->stream));
+    launch_ekf_update(ctx, Hdev, ld, rr, n, true, sigma2, nullptr);
+    OVB_CUDA_CHECK(ctx, cudaGetLastError());
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(wh.data(), ctx->d_w, sizeof(double) * (size_t)rr, cudaMemcpyDeviceToHost, ctx->stream));
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    double chi2 = 0.0, z2 = 0.0;
+    for (int i = 0; i < rr; i++) {
+      chi2 += wh[(size_t)i] * wh[(size_t)i];
+      z2 += zh[(size_t)i] * zh[(size_t)i];
+    }
+    if (compressed)
+      chi2 += std::max(0.0, res2 - z2) / sigma2;
+    if (ctx->h_info->not_spd)
+      chi2 = NAN;
+    const double chi2_check = g_chi2_table[std::min(r, OVB_CHI2_TABLE_LEN - 1)];
+    if (!(chi2 <= chi2_mult * chi2_check))
+      return OVB_OK; // rejected: nothing was modified
+  } else {
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_info, hi, sizeof(DevUpdateInfo), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // ---- initialize_invertible: augment P (StateHelper.cpp:484-577); Hxinit | Inv staged in the free d_Y buffer
+  {
+    std::vector<double> stage((size_t)k * n + (size_t)k * k);
+    for (int i = 0; i < k; i++)
+      for (int j = 0; j < n; j++)
+        stage[(size_t)i * n + j] = HR[(size_t)i * n + j];
+    for (int i = 0; i < k * k; i++)
+      stage[(size_t)k * n + i] = Inv[i];
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_Y, stage.data(), sizeof(double) * stage.size(), cudaMemcpyHostToDevice, ctx->stream));
+    launch_cov_init_augment(ctx, k, n, ctx->d_Y, ctx->d_Y + (size_t)k * n, sigma2);
+    OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // `stage` is pageable host memory owned by this scope
+  }
+  ctx->N = N + k;
+  for (int q = 0; q < k; q++) {
+    double acc = 0.0;
+    for (int i = 0; i < k; i++)
+      acc += Inv[q * k + i] * res[i];
+    dx_new[q] = acc;
+  }
+  *accepted = 1;
+  for (int i = 0; i < N + k; i++)
+    dx[i] = 0.0;
+  if (rup > 0) {
+    // ---- EKFUpdate with the projected part on the augmented covariance (StateHelper.cpp:476-479)
+    ovb_launch(ctx, k_take_z, dim3((rr + 127) / 128), dim3(128), (size_t)(0), Hdev, ld, rr, n, ctx->d_w);
+    launch_ekf_update(ctx, Hdev, ld, rr, n, false, sigma2, nullptr);
+    OVB_CUDA_CHECK(ctx, cudaGetLastError());
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)(N + k), cudaMemcpyDeviceToHost, ctx->stream));
+    OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < N + k; i++)
+      dx[i] = ctx->h_dx[i];
+    if (ctx->h_info->not_spd) {
+      snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: innovation covariance not positive definite");
+      return OVB_ERR_NOT_SPD;
+    }
+    if (ctx->h_info->nonfinite)
+      return OVB_ERR_NONFINITE;
+    if (ctx->h_info->neg_diag_index != 0x7fffffff) {
+      snprintf(ctx->err, sizeof(ctx->err), "EKFUpdate: diagonal at %d is negative", ctx->h_info->neg_diag_index);
+      return OVB_ERR_NEG_DIAG;
+    }
+  }
+  return OVB_OK;
+}
+
 } // extern "C"

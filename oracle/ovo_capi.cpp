@@ -181,6 +181,27 @@ int ovo_slam_update(const ovb_frame *fr, const ovb_feat_batch *fb, const ovb_lan
   return st;
 }
 
+// StateHelper::initialize: H_R r x n, H_L r x k (row-major). Pout (N+k)^2.
+int ovo_cov_initialize(const double *P, int N, const int *off, const int *sz, int nvar, const double *H_R, const double *H_L, const double *res,
+                       int r, int k, double sigma2, double chi2_mult, const double *chi2_table, double *Pout, int *accepted, double *dx_new,
+                       double *dx) {
+  std::vector<Var> order;
+  int n = 0;
+  for (int i = 0; i < nvar; i++) {
+    order.push_back(Var{off[i], sz[i]});
+    n += sz[i];
+  }
+  Mat HR(r, n), HL(r, k);
+  for (int i = 0; i < r; i++) {
+    for (int j = 0; j < n; j++)
+      HR(i, j) = H_R[(size_t)i * n + j];
+    for (int j = 0; j < k; j++)
+      HL(i, j) = H_L[(size_t)i * k + j];
+  }
+  std::vector<double> rv(res, res + r);
+  return cov_initialize(P, N, order, HR, HL, rv, sigma2, chi2_mult, chi2_table, Pout, accepted, dx_new, dx);
+}
+
 // measurement_compress_inplace on a row-major H (m x n); outputs R (min(m,n) x n row-major) and z.
 int ovo_compress(const double *H, int m, int n, const double *res, double *R_out, double *z_out) {
   Mat Hc(m, n);

@@ -1264,4 +1264,140 @@ inline int slam_update(const ovb_frame &fr, const ovb_feat_batch &fb, const ovb_
   return st;
 }
 
+// StateHelper::initialize + initialize_invertible (state/StateHelper.cpp:393-577): add a new k-wide variable (k = H_L.c)
+// at the END of the covariance from  res = H_R dx + H_L dx_new + n,  n ~ N(0, sigma2 I).
+// Pout must hold (N+k)^2 doubles (row-major, leading dimension N+k); it is written only when *accepted = 1.
+inline int cov_initialize(const double *P, int N, const std::vector<Var> &H_order, Mat H_R, Mat H_L, std::vector<double> res, double sigma2,
+                          double chi2_mult, const double *chi2_table, double *Pout, int *accepted, double *dx_new, double *dx) {
+  const int r = H_L.r, k = H_L.c, n = H_R.c;
+  *accepted = 0;
+  // Givens split (:429-440): top k rows depend on the new variable, the rest does not
+  for (int c = 0; c < k; ++c) {
+    for (int m = r - 1; m > c; m--) {
+      Givens g = make_givens(H_L(m - 1, c), H_L(m, c));
+      for (int j = c; j < k; j++)
+        apply_givens(g, H_L(m - 1, j), H_L(m, j));
+      apply_givens(g, res[m - 1], res[m]);
+      for (int j = 0; j < n; j++)
+        apply_givens(g, H_R(m - 1, j), H_R(m, j));
+    }
+  }
+  Mat Hxinit(k, n), H_finit(k, k), Hup(r - k, n);
+  std::vector<double> resinit(k), resup(r - k);
+  for (int i = 0; i < k; i++) {
+    for (int j = 0; j < n; j++)
+      Hxinit(i, j) = H_R(i, j);
+    for (int j = 0; j < k; j++)
+      H_finit(i, j) = H_L(i, j);
+    resinit[i] = res[i];
+  }
+  for (int i = k; i < r; i++) {
+    for (int j = 0; j < n; j++)
+      Hup(i - k, j) = H_R(i, j);
+    resup[i - k] = res[i];
+  }
+  // Mahalanobis gate on the update portion (:458-470); threshold from chi2(res.rows())
+  if (r - k > 0) {
+    FeatJac J;
+    J.rows = r - k;
+    J.order = H_order;
+    J.Hx = Hup;
+    J.res = resup;
+    bool spd = true;
+    double chi2 = feature_chi2(P, N, J, sigma2, &spd);
+    double chi2_check = chi2_table[std::min(r, OVB_CHI2_TABLE_LEN - 1)];
+    if (!(chi2 <= chi2_mult * chi2_check))
+      return OVB_OK;
+  }
+  // ---- initialize_invertible (:484-577)
+  std::vector<int> cols;
+  for (const Var &v : H_order)
+    for (int q = 0; q < v.size; q++)
+      cols.push_back(v.off + q);
+  Mat M_a(N, k); // P[:, cols] * Hxinit'
+  for (int a = 0; a < N; a++)
+    for (int i = 0; i < k; i++) {
+      double acc = 0.0;
+      for (int j = 0; j < n; j++)
+        acc += P[(size_t)a * N + cols[j]] * Hxinit(i, j);
+      M_a(a, i) = acc;
+    }
+  Mat M(k, k); // Hxinit P_small Hxinit' + R
+  for (int i = 0; i < k; i++)
+    for (int i2 = 0; i2 < k; i2++) {
+      double acc = 0.0;
+      for (int j = 0; j < n; j++)
+        acc += Hxinit(i, j) * M_a(cols[j], i2);
+      M(i, i2) = acc + (i == i2 ? sigma2 : 0.0);
+    }
+  for (int i = 0; i < k; i++) // selfadjointView<Upper>
+    for (int i2 = 0; i2 < i; i2++)
+      M(i, i2) = M(i2, i);
+  // H_L^-1 by Gauss-Jordan with partial pivoting (Eigen: PartialPivLU for dynamic sizes)
+  Mat A = H_finit, Inv(k, k);
+  for (int i = 0; i < k; i++)
+    Inv(i, i) = 1.0;
+  for (int c = 0; c < k; c++) {
+    int piv = c;
+    for (int i = c + 1; i < k; i++)
+      if (std::fabs(A(i, c)) > std::fabs(A(piv, c)))
+        piv = i;
+    if (piv != c)
+      for (int j = 0; j < k; j++) {
+        std::swap(A(c, j), A(piv, j));
+        std::swap(Inv(c, j), Inv(piv, j));
+      }
+    double d = A(c, c);
+    for (int j = 0; j < k; j++) {
+      A(c, j) /= d;
+      Inv(c, j) /= d;
+    }
+    for (int i = 0; i < k; i++) {
+      if (i == c)
+        continue;
+      double f = A(i, c);
+      for (int j = 0; j < k; j++) {
+        A(i, j) -= f * A(c, j);
+        Inv(i, j) -= f * Inv(c, j);
+      }
+    }
+  }
+  const int N2 = N + k;
+  for (int a = 0; a < N; a++)
+    for (int b = 0; b < N; b++)
+      Pout[(size_t)a * N2 + b] = P[(size_t)a * N + b];
+  for (int a = 0; a < N; a++)
+    for (int q = 0; q < k; q++) {
+      double acc = 0.0;
+      for (int i = 0; i < k; i++)
+        acc += M_a(a, i) * Inv(q, i); // -M_a * H_Linv'
+      Pout[(size_t)a * N2 + N + q] = -acc;
+      Pout[(size_t)(N + q) * N2 + a] = -acc;
+    }
+  for (int q = 0; q < k; q++)
+    for (int q2 = 0; q2 < k; q2++) {
+      double acc = 0.0;
+      for (int i = 0; i < k; i++)
+        for (int i2 = 0; i2 < k; i2++)
+          acc += Inv(q, i) * M(i, i2) * Inv(q2, i2);
+      Pout[(size_t)(N + q) * N2 + N + q2] = acc;
+    }
+  for (int q = 0; q < k; q++) {
+    double acc = 0.0;
+    for (int i = 0; i < k; i++)
+      acc += Inv(q, i) * resinit[i];
+    dx_new[q] = acc; // new_variable->update(H_Linv * res)
+  }
+  *accepted = 1;
+  for (int i = 0; i < N2; i++)
+    dx[i] = 0.0;
+  // update with the nullspace-projected portion (:476-479)
+  if (r - k > 0) {
+    std::vector<double> Rdiag(r - k, sigma2);
+    int neg = -1;
+    return ekf_update(Pout, N2, H_order, Hup, resup, Rdiag, dx, &neg);
+  }
+  return OVB_OK;
+}
+
 } // namespace ovo

@@ -81,3 +81,29 @@ def test_slam_update_argument_errors():
     with pytest.raises(capi.OvbError):
         eng.slam_update(case.frame, case.feats, case.landmarks, opts)
     eng.close()
+
+
+@pytest.mark.parametrize("seed,r,mult", [(1, 20, 1e9), (2, 7, 1e9), (3, 3, 1e9), (4, 60, 1e9), (6, 120, 1e9), (5, 30, 1.0)])
+def test_cov_initialize_parity(oracle, seed, r, mult):
+    """ovb_cov_initialize (StateHelper::initialize, StateHelper.cpp:393-577): rows < / = / > columns (the last two compress the
+    projected part first), plus a rejected system that must leave P untouched."""
+    from tests.test_slam_cpu import _init_case
+    P, off, sz, H_R, H_L, res = _init_case(seed, r=r)
+    if mult == 1.0:
+        res = res + 3.0
+    s2 = 0.05 ** 2
+    st_r, acc_r, P_r, dxn_r, dx_r = oracle.cov_initialize(P, off, sz, H_R, H_L, res, sigma2=s2, chi2_mult=mult)
+    eng = capi.Engine(max_state=128, max_feats=16, max_meas=256, max_rows=256)
+    eng.cov_set(P)
+    st, acc, dxn, dx = eng.cov_initialize(off, sz, H_R, H_L, res, sigma2=s2, chi2_mult=mult)
+    assert st == st_r == 0 and acc == acc_r
+    Pg = eng.cov_get()
+    assert Pg.shape == P_r.shape
+    if not acc:
+        assert np.array_equal(Pg, P)
+    else:
+        assert np.linalg.norm(Pg - P_r) <= 1e-9 * np.linalg.norm(P_r)
+        assert np.linalg.norm(dxn - dxn_r) <= 1e-9 * np.linalg.norm(dxn_r)
+        assert np.linalg.norm(dx - dx_r) <= 1e-9 * max(np.linalg.norm(dx_r), 1e-300)
+        assert np.array_equal(Pg, Pg.T)
+    eng.close()

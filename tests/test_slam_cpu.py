@@ -75,3 +75,45 @@ def test_landmark_columns_by_finite_differences(oracle, rep):
             an = r0["H_big"][row:row + m, j]
             assert np.abs(fd - an).max() <= 2e-3 * max(np.abs(an).max(), 1.0), (f, k)
         row += m
+
+
+def _init_case(seed, N=60, r=20, k=3, noise=0.05):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((N, N))
+    P = A @ A.T / N + 1e-2 * np.eye(N)
+    off, sz = [9, 27, 45, 33], [6, 6, 6, 8]
+    n = sum(sz)
+    H_R = rng.standard_normal((r, n))
+    H_L = rng.standard_normal((r, k))
+    res = H_L @ (0.1 * rng.standard_normal(k)) + noise * rng.standard_normal(r)
+    return P, off, sz, H_R, H_L, res
+
+
+@pytest.mark.parametrize("seed,r", [(1, 20), (2, 7), (3, 3), (4, 60)])
+def test_initialize_equals_the_joint_posterior_with_no_prior_on_the_new_variable(oracle, seed, r):
+    """StateHelper::initialize (Givens split + initialize_invertible + EKFUpdate, StateHelper.cpp:393-577) must equal the
+    information-form posterior of the augmented state with zero prior information on the new variable."""
+    P, off, sz, H_R, H_L, res = _init_case(seed, r=r)
+    s2 = 0.05 ** 2
+    st, acc, Po, dxn, dx = oracle.cov_initialize(P, off, sz, H_R, H_L, res, sigma2=s2, chi2_mult=1e9)
+    assert st == 0 and acc and Po.shape[0] == P.shape[0] + 3
+    N, k = P.shape[0], 3
+    cols = np.concatenate([np.arange(o, o + s) for o, s in zip(off, sz)] + [np.arange(N, N + k)])
+    Hf = np.zeros((len(res), N + k))
+    Hf[:, cols] = np.hstack([H_R, H_L])
+    Lam = np.zeros((N + k, N + k))
+    Lam[:N, :N] = np.linalg.inv(P)
+    Lam += Hf.T @ Hf / s2
+    Pn = np.linalg.inv(Lam)
+    assert np.linalg.norm(Pn - Po) <= 1e-7 * np.linalg.norm(Po)  # numpy's inverse of the information matrix is the looser side
+    dxa = Pn @ Hf.T @ res / s2
+    tot = dx.copy()
+    tot[N:] += dxn  # the new variable moves by H_Linv res_init and then by the update's cross-covariance term
+    assert np.linalg.norm(dxa - tot) <= 1e-7 * np.linalg.norm(dxa)
+
+
+def test_initialize_gate_rejects_inconsistent_systems(oracle):
+    P, off, sz, H_R, H_L, res = _init_case(5, r=30)
+    res = res + 3.0  # residuals far beyond what P and the noise explain
+    st, acc, Po, dxn, dx = oracle.cov_initialize(P, off, sz, H_R, H_L, res, sigma2=0.05 ** 2, chi2_mult=1.0)
+    assert st == 0 and not acc and np.array_equal(Po, P)
