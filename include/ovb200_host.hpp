@@ -226,6 +226,29 @@ struct StateHelper {
     state.check(ovb_cov_clone(state.ctx(), variable_to_clone.first, variable_to_clone.second, dnc_dt, dt_id), "clone");
     return new_id;
   }
+  // StateHelper::initialize (StateHelper.cpp:393-482): add `new_variable` (id assigned here = old covariance size) from
+  // res = H_R dx(H_order) + H_L dx(new) + n, n ~ N(0, sigma2 I). Returns false when the Mahalanobis gate rejects (state
+  // untouched). dx_new = the new variable's own correction, dx = EKF correction of the projected part (length = new size).
+  static bool initialize(State &state, Var &new_variable, const std::vector<Var> &H_order, const std::vector<double> &H_R,
+                         const std::vector<double> &H_L, const std::vector<double> &res, double sigma2, double chi_2_mult,
+                         std::vector<double> &dx_new, std::vector<double> &dx) {
+    std::vector<int> off, sz;
+    for (auto &v : H_order) {
+      off.push_back(v.first);
+      sz.push_back(v.second);
+    }
+    const int k = new_variable.second, old_size = state.max_covariance_size();
+    int accepted = 0;
+    dx_new.assign((size_t)k, 0.0);
+    dx.assign((size_t)(old_size + k), 0.0);
+    state.check(ovb_cov_initialize(state.ctx(), off.data(), sz.data(), (int)off.size(), H_R.data(), H_L.data(), res.data(), (int)res.size(), k,
+                                   sigma2, chi_2_mult, &accepted, dx_new.data(), dx.data()),
+                "initialize");
+    if (!accepted)
+      return false;
+    new_variable.first = old_size; // new_variable->set_local_id(oldSize) (StateHelper.cpp:571)
+    return true;
+  }
   // StateHelper::marginalize (StateHelper.cpp:271-339). The caller shifts the ids of the variables behind the removed one
   // exactly as the reference does (:318-326); marginalize_old_clone below does it for the clone window.
   static void marginalize(State &state, const Var &marg) { state.check(ovb_cov_marginalize(state.ctx(), marg.first, marg.second), "marginalize"); }

@@ -107,3 +107,53 @@ def test_cov_initialize_parity(oracle, seed, r, mult):
         assert np.linalg.norm(dx - dx_r) <= 1e-9 * max(np.linalg.norm(dx_r), 1e-300)
         assert np.array_equal(Pg, Pg.T)
     eng.close()
+
+
+def test_delayed_init_composition(oracle):
+    """UpdaterSLAM::delayed_init (update/UpdaterSLAM.cpp:68-251) composed from the ABI: triangulate the new tracks, take each
+    feature's full (pre-nullspace) Jacobians, StateHelper::initialize them one after the other on the resident covariance.
+    The oracle runs the same composition with its own triangulation / Jacobians / initialize."""
+    case = sim.make_update_case(n_feats=8, n_clones=8, n_cams=2, seed=21, calib_ext=True, calib_intr=True, outlier_frac=0.0,
+                                degenerate_frac=0.0)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1)
+    eng = capi.Engine(max_state=256, max_feats=64, max_meas=2048)
+    eng.cov_set(case.P)
+    tri_g = eng.triangulate(case.frame, case.feats, opts)
+    tri_r, _ = oracle.triangulate(case.frame, case.feats, opts)
+    assert np.array_equal(tri_g.status, tri_r.status)
+    P_r = case.P.copy()
+    n_init = 0
+    # the state mean is not moved between the initialisations here (the caller's Type::update does that), so the later
+    # tracks look inconsistent with the shrinking P: a wide gate keeps most of them, the first one uses the reference's
+    mult = 1.0
+    for f in np.flatnonzero(tri_r.status == 0)[:5]:
+        one = case.feats.subset([f])
+
+        def pick(src):
+            o = capi.FeatOut(1)
+            o.status[:] = 0
+            o.p_FinA[0], o.p_FinG[0] = src.p_FinA[f], src.p_FinG[f]
+            o.anchor_cam[0], o.anchor_clone[0] = src.anchor_cam[f], src.anchor_clone[f]
+            return o
+
+        Hf_g, Hx_g, res_g, _, col_g = eng.feature_jacobians(case.frame, one, opts, pick(tri_g), stage=0)
+        Hf_r, Hx_r, res_r, _ = oracle.feature_jacobians(case.frame, one, opts, pick(tri_r), 0, col_g)
+        # H_order = the variables this feature touches, as (offset, size) runs of the dump's columns
+        used = np.flatnonzero(np.abs(Hx_r).sum(axis=0) > 0)
+        cols = col_g[used]
+        starts = [0] + [i for i in range(1, len(cols)) if cols[i] != cols[i - 1] + 1] + [len(cols)]
+        off = [int(cols[a]) for a in starts[:-1]]
+        sz = [int(b - a) for a, b in zip(starts[:-1], starts[1:])]
+        st_r, acc_r, P_r, dxn_r, dx_r = oracle.cov_initialize(P_r, off, sz, Hx_r[:, used], Hf_r, res_r, sigma2=1.0, chi2_mult=mult)
+        st_g, acc_g, dxn_g, dx_g = eng.cov_initialize(off, sz, Hx_g[:, used], Hf_g, res_g, sigma2=1.0, chi2_mult=mult)
+        assert st_g == st_r == 0 and acc_g == acc_r
+        Pg = eng.cov_get()
+        assert Pg.shape == P_r.shape
+        assert np.linalg.norm(Pg - P_r) <= 1e-9 * np.linalg.norm(P_r)
+        mult = 200.0
+        if acc_r:
+            n_init += 1
+            assert np.linalg.norm(dxn_g - dxn_r) <= 1e-8 * max(np.linalg.norm(dxn_r), 1e-12)
+            assert np.linalg.norm(dx_g - dx_r) <= 1e-9 * max(np.linalg.norm(dx_r), 1e-300)
+    assert n_init >= 3 and eng.cov_dim() == case.P.shape[0] + 3 * n_init
+    eng.close()
