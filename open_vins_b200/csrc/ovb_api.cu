@@ -130,9 +130,12 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
   ctx->h_blob = ctx->h_arena + ctx->off_blob;
   CK(cudaMalloc(&ctx->d_cc, sizeof(DevCamPoses)));
   CK(cudaMalloc(&ctx->d_feat_order, (size_t)ctx->cfg.max_feats * (OVB_MAX_VARS + 1)));
-  CK(cudaMalloc(&ctx->d_info, sizeof(DevUpdateInfo)));
-  CK(cudaMallocHost(&ctx->h_info, sizeof(DevUpdateInfo)));
-  CK(cudaMallocHost(&ctx->h_dx, sizeof(double) * (size_t)ms));
+  // update info + dx live in ONE device block and ONE pinned host block: a single D2H copy returns both
+  ctx->info_bytes = align_up(sizeof(DevUpdateInfo), 256);
+  CK(cudaMalloc(&ctx->d_info, ctx->info_bytes + sizeof(double) * (size_t)ms));
+  ctx->d_dx = (double *)((char *)ctx->d_info + ctx->info_bytes);
+  CK(cudaMallocHost(&ctx->h_info, ctx->info_bytes + sizeof(double) * (size_t)ms));
+  ctx->h_dx = (double *)((char *)ctx->h_info + ctx->info_bytes);
   CK(cudaMalloc(&ctx->d_chi2_table, sizeof(g_chi2_table)));
   CK(cudaMemcpy(ctx->d_chi2_table, g_chi2_table, sizeof(g_chi2_table), cudaMemcpyHostToDevice));
   // stacked staging matrix
@@ -154,7 +157,6 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
   CK(cudaMalloc(&ctx->d_S, sizeof(double) * (size_t)(ms + 1) * ms));
   CK(cudaMalloc(&ctx->d_Y, sizeof(double) * (size_t)ms * ms));
   CK(cudaMalloc(&ctx->d_w, sizeof(double) * (size_t)ms * 4));
-  CK(cudaMalloc(&ctx->d_dx, sizeof(double) * (size_t)ms));
   ctx->scratch_per_cta = (size_t)(2 * OVB_MAX_MEAS_PER_FEAT + 1) * (2 * OVB_MAX_MEAS_PER_FEAT + 1);
   ctx->scratch_ctas = 2 * ctx->sm_count;
   CK(cudaMalloc(&ctx->d_scratch, sizeof(double) * ctx->scratch_per_cta * ctx->scratch_ctas));
@@ -172,12 +174,12 @@ void ovb_destroy(ovb_ctx *ctx) {
   if (ctx->stream)
     cudaStreamSynchronize(ctx->stream);
   void *dev[] = {ctx->P[0],   ctx->P[1], ctx->d_arena, ctx->d_cc, ctx->d_feat_order, ctx->d_info, ctx->d_chi2_table, ctx->d_Hs, ctx->d_W[0],
-                 ctx->d_W[1], ctx->d_R,  ctx->d_R2,    ctx->d_M,  ctx->d_S,          ctx->d_Y,    ctx->d_w,          ctx->d_dx, ctx->d_scratch,
+                 ctx->d_W[1], ctx->d_R,  ctx->d_R2,    ctx->d_M,  ctx->d_S,          ctx->d_Y,    ctx->d_w,          ctx->d_scratch,
                  ctx->d_dump, ctx->P_snap, ctx->d_flush, ctx->d_Gpart, ctx->d_G};
   for (void *p : dev)
     if (p)
       cudaFree(p);
-  void *host[] = {ctx->h_arena, ctx->h_info, ctx->h_dx, ctx->h_stage};
+  void *host[] = {ctx->h_arena, ctx->h_info, ctx->h_stage};
   for (void *p : host)
     if (p)
       cudaFreeHost(p);
@@ -865,9 +867,9 @@ ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat
   const int r = enqueue_update(ctx, pk.n_feats, pk.bv, pk.ldH, pk.max_M, pk.m_total, pk.n_all, opts->col_order, ctx->ev);
   OVB_CUDA_CHECK(ctx, cudaGetLastError());
   OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
-  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
-  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + sizeof(DevUpdateInfo) + sizeof(double) * (size_t)N;
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, ctx->info_bytes + sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost,
+                                      ctx->stream)); // info + dx in one copy
+  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + ctx->info_bytes + sizeof(double) * (size_t)N;
   cudaEventRecord(ctx->ev[6], ctx->stream);
   OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   unpack_feats(ctx, F, out);
@@ -937,9 +939,9 @@ ovb_status ovb_slam_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_
   const int r = enqueue_update(ctx, pk.n_feats, pk.bv, pk.ldH, pk.max_M, pk.m_total, pk.n_all, opts->col_order, ctx->ev, true);
   OVB_CUDA_CHECK(ctx, cudaGetLastError());
   OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
-  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
-  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + sizeof(DevUpdateInfo) + sizeof(double) * (size_t)N;
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, ctx->info_bytes + sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost,
+                                      ctx->stream)); // info + dx in one copy
+  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + ctx->info_bytes + sizeof(double) * (size_t)N;
   cudaEventRecord(ctx->ev[6], ctx->stream);
   OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   if (out) {
@@ -1060,9 +1062,9 @@ ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_block
   cudaEventRecord(ctx->ev[5], ctx->stream);
   OVB_CUDA_CHECK(ctx, cudaGetLastError());
   OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_feat, ctx->d_feat, sizeof(DevFeat) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
-  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(DevUpdateInfo), cudaMemcpyDeviceToHost, ctx->stream));
-  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_dx, ctx->d_dx, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + sizeof(DevUpdateInfo) + sizeof(double) * (size_t)N;
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, ctx->info_bytes + sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost,
+                                      ctx->stream)); // info + dx in one copy
+  ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + ctx->info_bytes + sizeof(double) * (size_t)N;
   cudaEventRecord(ctx->ev[6], ctx->stream);
   OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   unpack_feats(ctx, F, out);

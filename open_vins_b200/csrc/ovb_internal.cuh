@@ -137,6 +137,7 @@ struct ovb_ctx {
   int dump_rows;
   int max_rows;
   int sm_count;
+  size_t info_bytes; // DevUpdateInfo rounded up: d_dx / h_dx start right behind d_info / h_info
   int attr_done[4]; // per-context (= per-device) one-time cudaFuncSetAttribute flags: 0 tsqr, 1 feature, 2 ekf, 3 gram
   int tsqr_pdl;     // programmatic dependent launch between the TSQR level kernels (OVB_TSQR_PDL=0 disables: A/B timing only)
   int tsqr_cluster; // upper TSQR levels as one thread-block cluster (OVB_TSQR_CLUSTER=0 disables: A/B timing only)
