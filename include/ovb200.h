@@ -233,10 +233,11 @@ ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat
 
 /* ---- SLAM landmarks: features that already live in the state (ov_type::Landmark, types/Landmark.h; State::_features_SLAM) ----
  * One entry per feature of the batch handed to ovb_slam_update. All landmarks of one call share the representation
- * ovb_opts.feat_rep (feat_rep_slam); ANCHORED_INVERSE_DEPTH_SINGLE (the one case where the reference nullspace-projects
- * inside the SLAM update, update/UpdaterSLAM.cpp:344-353) is not supported yet and returns OVB_ERR_ARG. */
+ * ovb_opts.feat_rep (feat_rep_slam). With ANCHORED_INVERSE_DEPTH_SINGLE the landmark variable is 1 wide (the inverse depth):
+ * its column is dz/drho and the two bearing columns of H_f are nullspace-projected out (update/UpdaterSLAM.cpp:344-353),
+ * such features need at least two measurements (:278-281). */
 typedef struct {
-  const int32_t *lm_off;         /* [n_feats] covariance id of the 3-wide landmark variable (Type::id()) */
+  const int32_t *lm_off;         /* [n_feats] covariance id of the landmark variable (Type::id(); 3 wide, 1 for the SINGLE rep) */
   const double *value;           /* [n_feats][3] Landmark::get_xyz(false): p_FinG (global reps) / p_FinA (anchored reps) */
   const double *value_fej;       /* [n_feats][3] Landmark::get_xyz(true) */
   const int32_t *anchor_cam;     /* [n_feats] Landmark::_anchor_cam_id            (anchored reps; else ignored) */

@@ -111,7 +111,7 @@ struct Landmark {
   double xyz_fej[3] = {0, 0, 0};
   int update_fail_count = 0;
   bool should_marg = false;
-  int size() const { return 3; }
+  int size() const { return _feat_representation == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE ? 1 : 3; }
 };
 
 // the StateOptions fields the path reads (state/StateOptions.h:35-176)
@@ -466,8 +466,12 @@ public:
       int ct_meas = 0;
       for (const auto &pair : (*it)->timestamps)
         ct_meas += (int)pair.second.size();
+      // the single-depth representation projects the bearing out and needs two measurements (UpdaterSLAM.cpp:278-290)
+      const int required_meas = (state._options.feat_rep_slam == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE) ? 2 : 1;
       if (ct_meas < 1) {
         (*it)->to_delete = true;
+        it = feature_vec.erase(it);
+      } else if (ct_meas < required_meas) {
         it = feature_vec.erase(it);
       } else
         ++it;

@@ -215,7 +215,12 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n_all8 = (n_all + 7) & ~7;
   constexpr bool slam = SLAM;
-  const int r0 = slam ? 0 : 3; // rows removed by the nullspace projection
+  // SLAM landmarks kept as a single inverse depth (ANCHORED_INVERSE_DEPTH_SINGLE, UpdaterSLAM.cpp:344-353): the landmark
+  // variable is 1 wide (the depth column of H_f) and the two bearing columns are projected out like an MSCKF feature's three
+  const bool single = slam && (op.feat_rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE);
+  const int nproj = slam ? (single ? 2 : 0) : 3; // columns of H_f that are projected out = rows removed
+  const int r0 = nproj;
+  const int lmw = single ? 1 : 3;                // width of the landmark block (block 5)
   // ---- shared memory carve-up (mirrors feature_smem_bytes)
   size_t o = 0;
   MeasView mv;
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       if (status_in != OVB_FEAT_OK || M < 2 || M > maxM)
         continue;
     } else {
-      if (M < (slam ? 1 : 2))
+      if (M < ((slam && !single) ? 1 : 2))
         continue; // no rows reserved
       if (status_in != OVB_FEAT_OK || M > maxM) {
         // rows reserved for this feature are zero (they are harmless in the QR)
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
         for (int r = 0; r < 2; r++)
 #pragma unroll
           for (int k = 0; k < 3; k++)
-            B5[8 * r + k] = mHf[3 * r + k];
+            B5[8 * r + k] = single ? mHf[3 * r + 2] : mHf[3 * r + k]; // single: only entry 0 (the depth column) is read
         sl[5] = F->lm_slot;
       }
       sl[0] = mcs[tid];
@@ -584,13 +589,15 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
     double tau[3] = {0.0, 0.0, 0.0};
     double *rowk = red + FT_WARPS * 3; // 3 doubles: the pivot row's values
-    if (slam) { // no projection: Q = I (tau = 0, V = 0 make every sweep below a no-op)
+    if (nproj < 3) { // fewer (or no) reflectors: the unused ones are tau = 0, V = 0, which makes their sweeps no-ops
       if (tid < rows)
         V[3 * tid] = V[3 * tid + 1] = V[3 * tid + 2] = 0.0;
       __syncthreads();
     }
 #pragma unroll
-    for (int k = 0; k < 3 && !slam; k++) {
+    for (int k = 0; k < 3; k++) {
+      if (k >= nproj)
+        break;
       const double ak = a[k];
       const bool below = (tid > k && tid < rows);
       // g[j] = sum over rows below the pivot of a_k a_j  (g[k] = squared norm of the sub-column)
@@ -636,7 +643,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
     // Gram of the reflectors: G10 = v1'v0, G20 = v2'v0, G21 = v2'v1
     double G10 = 0, G20 = 0, G21 = 0;
-    if (tid < rows && !slam) {
+    if (tid < rows && nproj > 0) {
       double v0 = V[3 * tid], v1 = V[3 * tid + 1], v2 = V[3 * tid + 2];
       G10 = v1 * v0;
       G20 = v2 * v0;
@@ -746,7 +753,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
               continue;
             const double *B = mv.blk(I, b);
             const double *Pb = P + (size_t)fslot_off[sb] * ldP + pc;
-            const int wb = blk_w(b);
+            const int wb = (b == 5) ? lmw : blk_w(b);
             double pw[6];
 #pragma unroll
             for (int k = 0; k < 6; k++)
@@ -775,7 +782,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
           if (sb < 0)
             continue;
           const double *B = mv.blk(J, b);
-          int wb = blk_w(b);
+          int wb = (b == 5) ? lmw : blk_w(b);
           int c0 = slot2l[sb];
           for (int k = 0; k < wb; k++) {
             double ta = Tmy[c0 + k], tb = Tmy[n_all + c0 + k];
@@ -804,7 +811,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     __syncthreads();
 
     // ---- S <- Q' S Q (both sides), only rows/cols 3.. are used afterwards
-    for (int pass = 0; pass < 2 && !slam; pass++) {
+    for (int pass = 0; pass < 2 && nproj > 0; pass++) {
       for (int j = tid; j < rows; j += FT_THREADS) {
         // pass 0: vector = column j (stride ldS); pass 1: vector = row j (stride 1)
         const int st = (pass == 0) ? ldS : 1;

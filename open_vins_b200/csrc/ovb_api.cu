@@ -371,9 +371,10 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
   }; // kind 0 clone, 1 ext, 2 intr, 3 landmark
   std::vector<SlotRec> slots;
   std::vector<int> lm_slot_of((size_t)(lm ? fb->n_feats : 0), -1);
+  const bool lm_single = lm && op->feat_rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE; // 1-wide landmark (inverse depth only)
   if (lm)
     for (int f = 0; f < fb->n_feats; f++)
-      slots.push_back({lm->lm_off[f], 3, 3, f});
+      slots.push_back({lm->lm_off[f], lm_single ? 1 : 3, 3, f});
   for (int k = 0; k < fr->n_cams; k++) {
     hf->cam_ext_slot[k] = hf->cam_intr_slot[k] = -1;
     if (op->do_calib_camera_pose) {
@@ -464,7 +465,7 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
     maxM = std::max(maxM, Mf);
     d.row0 = row;
     if (lm)
-      row += 2 * Mf; // UpdaterSLAM.cpp:365-387: H_xf = [H_x, H_f], all 2M rows kept
+      row += lm_single ? (Mf >= 2 ? 2 * Mf - 2 : 0) : 2 * Mf; // UpdaterSLAM.cpp:344-387: all 2M rows kept (SINGLE: 2 projected out)
     else
       row += Mf >= 2 ? 2 * Mf - 3 : 0;
     d.key0 = (int)nkeys;
@@ -500,7 +501,7 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
       d.p_FinG_fej[k] = NAN;
     if (lm) {
       d.lm_slot = lm_slot_of[(size_t)f];
-      d.status = Mf >= 1 ? OVB_FEAT_OK : OVB_FEAT_FEW_MEAS; // UpdaterSLAM.cpp:283-285
+      d.status = Mf >= (lm_single ? 2 : 1) ? OVB_FEAT_OK : OVB_FEAT_FEW_MEAS; // UpdaterSLAM.cpp:278-290
       const bool rel = op->feat_rep >= OVB_REP_ANCHORED_3D;
       d.anchor_cam = rel && lm->anchor_cam ? lm->anchor_cam[f] : -1;
       d.anchor_clone = rel && lm->anchor_clone ? lm->anchor_clone[f] : -1;
@@ -723,7 +724,7 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
     cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = ctx->side_stream;
-    launch_column_map(ctx, F, bv, slam ? 0 : 3);
+    launch_column_map(ctx, F, bv, slam ? (ctx->h_opts->o.feat_rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE ? 2 : 0) : 3);
     ctx->stream = main_stream;
     cudaEventRecord(ctx->ev_join, ctx->side_stream);
   }
@@ -913,10 +914,6 @@ ovb_status ovb_slam_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_
     return OVB_ERR_ARG;
   if (ctx->N < 1) {
     snprintf(ctx->err, sizeof(ctx->err), "ovb_slam_update: no covariance loaded (ovb_cov_set)");
-    return OVB_ERR_ARG;
-  }
-  if (opts->feat_rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE) {
-    snprintf(ctx->err, sizeof(ctx->err), "ovb_slam_update: ANCHORED_INVERSE_DEPTH_SINGLE landmarks are not supported yet");
     return OVB_ERR_ARG;
   }
   OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));

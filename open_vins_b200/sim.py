@@ -308,9 +308,10 @@ def make_slam_case(n_landmarks=12, n_clones=8, n_cams=2, seed=0, rep=0, calib_ex
                             full_track_frac=1.0, outlier_frac=0.0, degenerate_frac=0.0)
     lay, fr = base.layout, base.frame
     N0 = lay.N
-    N = N0 + 3 * n_landmarks
-    lm_off = N0 + 3 * np.arange(n_landmarks)
-    sig = np.concatenate([lay.sigmas(), 0.05 * np.ones(3 * n_landmarks)])
+    lm_size = 1 if rep == 5 else 3  # ANCHORED_INVERSE_DEPTH_SINGLE keeps only the inverse depth in the state
+    N = N0 + lm_size * n_landmarks
+    lm_off = N0 + lm_size * np.arange(n_landmarks)
+    sig = np.concatenate([lay.sigmas(), (0.01 if rep == 5 else 0.05) * np.ones(lm_size * n_landmarks)])
     U = rng.standard_normal((N, 12))
     Cn = 0.6 * np.eye(N) + 0.4 * (U @ U.T) / 12
     P = (sig[:, None] * Cn) * sig[None, :]
@@ -320,7 +321,7 @@ def make_slam_case(n_landmarks=12, n_clones=8, n_cams=2, seed=0, rep=0, calib_ex
     keep, meas_off = [], [0]
     first_clone = []
     for f in range(n_landmarks):
-        L = int(rng.integers(track_len[0], track_len[1] + 1))
+        L = int(rng.integers(max(track_len[0], 2 if rep == 5 else 1), track_len[1] + 1))
         idx = [i for i in range(fa.meas_off[f], fa.meas_off[f + 1]) if fa.clone[i] >= n_clones - L]
         keep += idx
         meas_off.append(meas_off[-1] + len(idx))

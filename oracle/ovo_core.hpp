@@ -1137,14 +1137,17 @@ inline int msckf_update(const ovb_frame &fr, const ovb_feat_batch &fb, const ovb
 }
 
 // Steps 4-5 of UpdaterSLAM::update (update/UpdaterSLAM.cpp:310-470). Landmarks live in the state: value / FEJ value
-// come from `lm` (Landmark::get_xyz), H_xf = [H_x, H_f], no nullspace projection (the SINGLE representation, :344-353,
-// is not restated), no compression, ONE EKFUpdate with the block-scaled identity R_big (:444). P updated in place.
+// come from `lm` (Landmark::get_xyz), H_xf = [H_x, H_f], no nullspace projection — except for ANCHORED_INVERSE_DEPTH_SINGLE,
+// whose landmark is the 1-wide depth: H_xf = [H_x, dz/drho] and the two bearing columns are projected out (:344-353) —,
+// no compression, ONE EKFUpdate with the block-scaled identity R_big (:444). P updated in place.
 inline int slam_update(const ovb_frame &fr, const ovb_feat_batch &fb, const ovb_landmarks &lm, const ovb_opts &op, const double *chi2_table,
                        double *P, int N, ovb_feat_out *out, double *dx, ovb_stats *stats, UpdateDump *dump) {
   const int F = fb.n_feats;
   int rep = op.feat_rep;
-  if (rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE)
-    return OVB_ERR_ARG;
+  const bool single = (rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE);
+  if (single)
+    rep = OVB_REP_ANCHORED_MSCKF_INVERSE_DEPTH; // :327-329
+  const int lm_size = single ? 1 : 3;
   std::vector<int> status(F, OVB_FEAT_OK);
   std::vector<double> chi2s(F, std::nan(""));
   size_t max_meas_size = 0;
@@ -1156,7 +1159,7 @@ inline int slam_update(const ovb_frame &fr, const ovb_feat_batch &fb, const ovb_
   int ct_jacob = 0, ct_meas = 0, used = 0;
   double T0 = now_s();
   for (int f = 0; f < F; f++) {
-    if (fb.meas_off[f + 1] - fb.meas_off[f] < 1) { // :283-285 (ct_meas < 1: dropped before the update)
+    if (fb.meas_off[f + 1] - fb.meas_off[f] < (single ? 2 : 1)) { // :278-290 (too few measurements: dropped before the update)
       status[f] = OVB_FEAT_FEW_MEAS;
       continue;
     }
@@ -1175,14 +1178,22 @@ inline int slam_update(const ovb_frame &fr, const ovb_feat_batch &fb, const ovb_
     FeatJac Jxf;
     Jxf.rows = J.rows;
     Jxf.order = J.order;
-    Jxf.order.push_back(Var{lm.lm_off[f], 3});
+    Jxf.order.push_back(Var{lm.lm_off[f], lm_size});
     Jxf.res = J.res;
-    Jxf.Hx.resize_zero(J.rows, J.Hx.c + 3);
+    Jxf.Hx.resize_zero(J.rows, J.Hx.c + lm_size);
     for (int i = 0; i < J.rows; i++) {
       for (int k = 0; k < J.Hx.c; k++)
         Jxf.Hx(i, k) = J.Hx(i, k);
-      for (int k = 0; k < 3; k++)
-        Jxf.Hx(i, J.Hx.c + k) = J.Hf(i, k);
+      for (int k = 0; k < lm_size; k++)
+        Jxf.Hx(i, J.Hx.c + k) = J.Hf(i, single ? 2 : k);
+    }
+    if (single) { // :344-353 — project the bearing portion (the first two columns of H_f) out of [H_x, dz/drho] and res
+      Jxf.nf = 2;
+      Jxf.Hf.resize_zero(J.rows, 2);
+      for (int i = 0; i < J.rows; i++)
+        for (int k = 0; k < 2; k++)
+          Jxf.Hf(i, k) = J.Hf(i, k);
+      nullspace_project_inplace(Jxf);
     }
     // :389-420 — chi² gate with the per-class noise and multiplier
     const double sigma_pix = lm.sigma_pix ? lm.sigma_pix[f] : op.sigma_pix;

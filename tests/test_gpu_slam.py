@@ -7,7 +7,7 @@ from open_vins_b200 import capi, sim
 pytestmark = pytest.mark.gpu
 
 REPS = [capi.REP_GLOBAL_3D, capi.REP_GLOBAL_FULL_INVERSE_DEPTH, capi.REP_ANCHORED_3D, capi.REP_ANCHORED_FULL_INVERSE_DEPTH,
-        capi.REP_ANCHORED_MSCKF_INVERSE_DEPTH]
+        capi.REP_ANCHORED_MSCKF_INVERSE_DEPTH, capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE]
 
 
 def _check(eng, oracle, case, opts):
@@ -77,9 +77,11 @@ def test_slam_update_argument_errors():
     case = sim.make_slam_case(n_landmarks=4, n_clones=5, n_cams=1, seed=1, rep=0, calib_ext=False, calib_intr=False)
     eng = capi.Engine(max_state=256, max_feats=64, max_meas=1024)
     eng.cov_set(case.P)
-    opts = capi.default_opts(feat_rep=capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE)
-    with pytest.raises(capi.OvbError):
+    # an anchored representation without anchors is an argument error, not a silent wrong answer
+    opts = capi.default_opts(feat_rep=capi.REP_ANCHORED_3D)
+    with pytest.raises(capi.OvbError) as ei:
         eng.slam_update(case.frame, case.feats, case.landmarks, opts)
+    assert ei.value.code == capi.OVB_ERR_ARG
     eng.close()
 
 

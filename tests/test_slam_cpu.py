@@ -10,8 +10,11 @@ def _cols(order_off, order_sz):
 
 
 @pytest.mark.parametrize("rep", [capi.REP_GLOBAL_3D, capi.REP_GLOBAL_FULL_INVERSE_DEPTH, capi.REP_ANCHORED_3D,
-                                 capi.REP_ANCHORED_FULL_INVERSE_DEPTH, capi.REP_ANCHORED_MSCKF_INVERSE_DEPTH])
+                                 capi.REP_ANCHORED_FULL_INVERSE_DEPTH, capi.REP_ANCHORED_MSCKF_INVERSE_DEPTH,
+                                 capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE])
 def test_slam_update_is_the_textbook_update_of_its_stacked_system(oracle, rep):
+    single = rep == capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE  # 1-wide landmark, the two bearing columns projected out
+    lmw, drop = (1, 2) if single else (3, 0)
     case = sim.make_slam_case(n_landmarks=14, n_clones=8, n_cams=2, seed=40 + rep, rep=rep)
     opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, feat_rep=rep)
     r = oracle.slam_update(case.frame, case.feats, case.landmarks, opts, case.P)
@@ -23,8 +26,8 @@ def test_slam_update_is_the_textbook_update_of_its_stacked_system(oracle, rep):
     used = np.flatnonzero(r["out"].status == 0)
     row = 0
     for f in used:
-        m = 2 * int(case.feats.meas_off[f + 1] - case.feats.meas_off[f])
-        j = [int(np.flatnonzero(c == case.lm_off[f] + k)[0]) for k in range(3)]
+        m = 2 * int(case.feats.meas_off[f + 1] - case.feats.meas_off[f]) - drop
+        j = [int(np.flatnonzero(c == case.lm_off[f] + k)[0]) for k in range(lmw)]
         assert np.abs(H[row:row + m, j]).max() > 0
         mask = np.ones(H.shape[0], dtype=bool)
         mask[row:row + m] = False
@@ -43,7 +46,7 @@ def test_slam_update_is_the_textbook_update_of_its_stacked_system(oracle, rep):
     # the gate of every feature: chi2 = res' (H_xf P_marg H_xf' + s2 I)^-1 res on its own rows
     row = 0
     for f in used:
-        m = 2 * int(case.feats.meas_off[f + 1] - case.feats.meas_off[f])
+        m = 2 * int(case.feats.meas_off[f + 1] - case.feats.meas_off[f]) - drop
         Sf = S[row:row + m, row:row + m]
         chi2 = res[row:row + m] @ np.linalg.solve(Sf, res[row:row + m])
         assert abs(chi2 - r["out"].chi2[f]) <= 1e-9 * chi2
