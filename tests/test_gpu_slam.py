@@ -159,3 +159,32 @@ def test_delayed_init_composition(oracle):
             assert np.linalg.norm(dx_g - dx_r) <= 1e-9 * max(np.linalg.norm(dx_r), 1e-300)
     assert n_init >= 3 and eng.cov_dim() == case.P.shape[0] + 3 * n_init
     eng.close()
+
+
+def test_anchor_change_propagation_shape(oracle):
+    """UpdaterSLAM::perform_anchor_change (update/UpdaterSLAM.cpp:574-647) ends in StateHelper::EKFPropagation with a 3-wide
+    new block (the landmark itself) and Phi over (landmark, old anchor clone, new anchor clone[, extrinsics]), Q = 0:
+    ovb_cov_propagate covers that shape on the resident covariance."""
+    rng = np.random.default_rng(3)
+    N = 90
+    A = rng.standard_normal((N, N))
+    P = A @ A.T / N + 1e-3 * np.eye(N)
+    lm_off, old_clone, new_clone, ext = 84, 30, 66, 15
+    old_off, old_sz = [lm_off, old_clone, new_clone, ext], [3, 6, 6, 6]
+    Phi = np.hstack([np.eye(3) + 0.1 * rng.standard_normal((3, 3)), 0.3 * rng.standard_normal((3, 18))])
+    Q = np.zeros((3, 3))
+    st_r, P_r = oracle.cov_propagate(P, lm_off, Phi, Q, old_off, old_sz)
+    eng = capi.Engine(max_state=128, max_feats=16, max_meas=256)
+    eng.cov_set(P)
+    st_g = eng.cov_propagate(lm_off, Phi, Q, old_off, old_sz)
+    assert st_g == st_r == 0
+    Pg = eng.cov_get()
+    assert np.linalg.norm(Pg - P_r) <= 1e-12 * np.linalg.norm(P_r)
+    # textbook: P' = J P J' with J = identity except the landmark rows
+    J = np.eye(N)
+    J[lm_off:lm_off + 3] = 0.0
+    cols = np.concatenate([np.arange(o, o + s) for o, s in zip(old_off, old_sz)])
+    J[lm_off:lm_off + 3, cols] = Phi
+    Pt = J @ P @ J.T
+    assert np.linalg.norm(Pg - Pt) <= 1e-12 * np.linalg.norm(Pt)
+    eng.close()
