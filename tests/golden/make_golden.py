@@ -53,7 +53,40 @@ def build(name):
     return d
 
 
+SLAM_CASES = {
+    # name: (sim.make_slam_case kwargs, option kwargs)
+    "slam_global3d": (dict(n_landmarks=12, n_clones=8, n_cams=2, seed=31, rep=capi.REP_GLOBAL_3D),
+                      dict(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, feat_rep=capi.REP_GLOBAL_3D)),
+    "slam_single_depth": (dict(n_landmarks=12, n_clones=8, n_cams=2, seed=32, rep=capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE),
+                          dict(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, feat_rep=capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE)),
+}
+LM_FIELDS = ["lm_off", "value", "value_fej", "anchor_cam", "anchor_clone", "sigma_pix", "chi2_multipler"]
+
+
+def build_slam(name):
+    skw, okw = SLAM_CASES[name]
+    case = sim.make_slam_case(**skw)
+    opts = capi.default_opts(**okw)
+    ref = oracle.slam_update(case.frame, case.feats, case.landmarks, opts, case.P)
+    assert ref["status"] == 0
+    d = {"P": case.P, "opt_keys": np.array(sorted(okw.keys())), "opt_vals": np.array([okw[k] for k in sorted(okw.keys())], dtype=np.int64)}
+    for k in FRAME_FIELDS:
+        d["frame_" + k] = getattr(case.frame, k)
+    for k in FEAT_FIELDS:
+        d["feat_" + k] = getattr(case.feats, k)
+    for k in LM_FIELDS:
+        d["lm_" + k] = getattr(case.landmarks, k)
+    d.update(out_status=ref["out"].status, out_chi2=ref["out"].chi2, dx=ref["dx"], P_post=ref["P"], H_big=ref["H_big"], res_big=ref["res_big"],
+             Rdiag_big=ref["Rdiag_big"], order_off=ref["order_off"], order_sz=ref["order_sz"], n_used=np.int64(ref["stats"].n_feats_used))
+    return d
+
+
 def main():
+    for name in SLAM_CASES:
+        d = build_slam(name)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **d)
+        print(name, os.path.getsize(path), "bytes; used", int(d["n_used"]), "of", len(d["out_status"]))
     for name in CASES:
         d = build(name)
         path = os.path.join(HERE, name + ".npz")

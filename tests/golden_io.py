@@ -12,8 +12,26 @@ FRAME_FIELDS = ["clone_R", "clone_p", "clone_R_fej", "clone_p_fej", "clone_off",
 FEAT_FIELDS = ["meas_off", "cam", "clone", "uv", "uvn"]
 
 
-def names():
+LM_FIELDS = ["lm_off", "value", "value_fej", "anchor_cam", "anchor_clone", "sigma_pix", "chi2_multipler"]
+
+
+def _all():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def names():
+    """MSCKF update cases."""
+    return [n for n in _all() if not n.startswith("slam_")]
+
+
+def slam_names():
+    return [n for n in _all() if n.startswith("slam_")]
+
+
+def load_slam(name):
+    d, frame, feats, opts = load(name)
+    lms = capi.LandmarkArrays(*[d["lm_" + k] for k in LM_FIELDS])
+    return d, frame, feats, lms, opts
 
 
 def load(name):

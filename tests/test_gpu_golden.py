@@ -26,3 +26,17 @@ def test_engine_matches_golden(name):
     Pg = eng.cov_get()
     assert np.linalg.norm(Pg - d["P_post"]) <= 1e-9 * np.linalg.norm(d["P_post"])
     eng.close()
+
+
+@pytest.mark.parametrize("name", golden_io.slam_names())
+def test_engine_matches_slam_golden(name):
+    d, frame, feats, lms, opts = golden_io.load_slam(name)
+    eng = capi.Engine(max_state=256, max_feats=256, max_meas=8192)
+    eng.cov_set(d["P"])
+    st, out, dx, stats = eng.slam_update(frame, feats, lms, opts)
+    assert st == 0 and np.array_equal(out.status, d["out_status"]) and stats.n_feats_used == int(d["n_used"])
+    ok = d["out_status"] == 0
+    np.testing.assert_allclose(out.chi2[ok], d["out_chi2"][ok], rtol=1e-8)
+    assert np.linalg.norm(dx - d["dx"]) <= 1e-9 * np.linalg.norm(d["dx"])
+    assert np.linalg.norm(eng.cov_get() - d["P_post"]) <= 1e-9 * np.linalg.norm(d["P_post"])
+    eng.close()
