@@ -54,4 +54,5 @@ def test_compression_invariants_against_50_digit_arithmetic(oracle, seed, m, n):
     g = _np(Hm.T * rm, (n, 1)).ravel()
     assert np.linalg.norm(R.T @ R - G) <= 5e-15 * np.linalg.norm(G) * n
     assert np.linalg.norm(R.T @ z - g) <= 5e-15 * np.linalg.norm(H) * np.linalg.norm(res) * n
-    assert (np.diag(R) >= 0).all() and np.allclose(np.tril(R, -1), 0.0, atol=0)
+    # the rotated-away entries are computed, not set: they are zero to rounding, exactly as in the reference's Givens sweep
+    assert (np.diag(R) >= 0).all() and np.abs(np.tril(R, -1)).max() <= 1e-14 * np.abs(R).max()
