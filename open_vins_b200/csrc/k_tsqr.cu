@@ -160,19 +160,20 @@ __global__ void __launch_bounds__(QR_THREADS)
   // step k is slot 0 of group 0 and every register index is static, so the loop stays rolled (one copy in the I-cache).
   double *Bp = &sm.At[0][0]; // staging [j][t][g], pitch 257: conflict-free both ways (aliases the tile buffer)
   {
+    // 8-byte cp.async straight into the transposed staging layout: every load of the CTA is in flight at once
+    // (zero-filled beyond the chunk's rows / the panel's columns)
     const int lj = tid & 15, rr = tid >> 4;
 #pragma unroll 4
     for (int pass = 0; pass < QR_CR / 16; pass++) {
       const int r = pass * 16 + rr;
-      double v = 0.0;
-      if (r < rows_i && lj < nbp) {
-        if (level == 0)
-          v = A[(size_t)(c0 + chunk * crl + r) * ldA + c0 + lj];
-        else
-          v = Win[(size_t)(chunk * QR_CR + r) * QR_NB + lj];
-      }
-      Bp[lj * 257 + (r & 15) * 16 + (r >> 4)] = v;
+      const bool ok = (r < rows_i) && (lj < nbp);
+      const double *src = A;
+      if (ok)
+        src = (level == 0) ? A + (size_t)(c0 + chunk * crl + r) * ldA + c0 + lj : Win + (size_t)(chunk * QR_CR + r) * QR_NB + lj;
+      cp_async8(smem_u32(&Bp[lj * 257 + (r & 15) * 16 + (r >> 4)]), src, ok ? 8u : 0u);
     }
+    cp_async_commit();
+    cp_async_wait_all();
   }
   __syncthreads();
   TPROBE(1);
@@ -498,17 +499,21 @@ __global__ void __launch_bounds__(QR_THREADS)
         for (int kq = 0; kq < 4; kq++)
           va[kq] = sm.Vs[r][(4 * kq + fk) ^ sw];
         double c[4][2];
+        // a ragged last tile (ncol < 32) only pays for the 8-column sub-tiles it has
 #pragma unroll
         for (int ct = 0; ct < 4; ct++) {
-          const double2 cc = *reinterpret_cast<const double2 *>(&At[r][8 * ct + 2 * fk]);
-          c[ct][0] = cc.x;
-          c[ct][1] = cc.y;
+          if (8 * ct < ncol) {
+            const double2 cc = *reinterpret_cast<const double2 *>(&At[r][8 * ct + 2 * fk]);
+            c[ct][0] = cc.x;
+            c[ct][1] = cc.y;
+          }
         }
 #pragma unroll
         for (int kq = 0; kq < 4; kq++)
 #pragma unroll
           for (int ct = 0; ct < 4; ct++)
-            dmma884(c[ct][0], c[ct][1], va[kq], sm.Zs[4 * kq + fk][8 * ct + fr]);
+            if (8 * ct < ncol)
+              dmma884(c[ct][0], c[ct][1], va[kq], sm.Zs[4 * kq + fk][8 * ct + fr]);
         if (r < rows_i) {
           double *dst = A + (size_t)sm.rowidx[r] * ldA + col0;
 #pragma unroll
