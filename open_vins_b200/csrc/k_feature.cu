@@ -203,7 +203,8 @@ __device__ __forceinline__ bool rep_is_relative(int rep) {
 // The SLAM variant is a separate instantiation so that the MSCKF hot path carries none of its code or registers.
 template <bool SLAM>
 __global__ void __launch_bounds__(FT_THREADS, 2)
-    k_feature_system(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, DevFeat *__restrict__ feats, int n_feats, BlobView bv,
+    k_feature_system(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, DevFeat *__restrict__ feats, int sched_lo, int n_feats,
+                     BlobView bv,
                      const double *__restrict__ P, int ldP, const double *__restrict__ chi2_table, double *__restrict__ Hs, int ldH,
                      unsigned char *__restrict__ feat_order, int mode, int maxM, int nblk, double *__restrict__ scratch,
                      size_t scratch_per_cta, double *__restrict__ dump, int ld_dump, int dump_rows) {
@@ -278,7 +279,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
   }
 
-  for (int fi = blockIdx.x; fi < n_feats; fi += gridDim.x) {
+  // this launch works on entries [sched_lo, n_feats) of the longest-first schedule (one size class, see the launcher)
+  for (int fi = sched_lo + blockIdx.x; fi < n_feats; fi += gridDim.x) {
     const int f = feats[fi].sched; // longest tracks first: the short ones fill the tail of the last wave
     DevFeat *F = &feats[f];
     const int m0 = F->m0, M = F->m1 - F->m0;
@@ -936,6 +938,45 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
     cudaFuncSetAttribute(k_feature_system<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     ctx->attr_done[1] = 1;
   }
+  int dump_rows = ctx->dump_rows; // rows of the current dump (set by ovb_feature_jacobians)
+  // ---- size classes. Shared memory per CTA grows with the square of the track length, and one launch must size it for
+  // its longest track: a single launch runs 2 CTAs/SM for everybody and the short tracks wait for a second wave. Three
+  // launches (tracks > 32, 17..32, <= 16 measurements; the schedule is already sorted longest-first, so classes are
+  // contiguous ranges) on three streams let 3-5 short-track CTAs share an SM next to the long ones.
+  if (mode == 0 && S_in_smem && ctx->feat_classes && n_feats > ctx->sm_count) {
+    const int thr[2] = {32, 16};
+    int bound[4] = {0, n_feats, n_feats, n_feats};
+    for (int i = 0, c = 0; i < n_feats && c < 2; i++) {
+      const DevFeat &d = ctx->h_feat[ctx->h_feat[i].sched];
+      while (c < 2 && d.m1 - d.m0 <= thr[c])
+        bound[++c] = i;
+    }
+    cudaStream_t main_stream = ctx->stream;
+    cudaStream_t side[3] = {main_stream, ctx->side_stream, ctx->side_stream2};
+    cudaEvent_t joined[3] = {nullptr, ctx->ev_join, ctx->ev_join2};
+    cudaEventRecord(ctx->ev_fork, main_stream);
+    for (int c = 0; c < 3; c++) {
+      const int lo = bound[c], hi = bound[c + 1];
+      if (hi <= lo)
+        continue;
+      const DevFeat &longest = ctx->h_feat[ctx->h_feat[lo].sched];
+      int cM = longest.m1 - longest.m0;
+      cM = cM < 2 ? 2 : (cM > maxM ? maxM : cM);
+      const size_t csmem = feature_smem_bytes(cM, n_all, n_slots, nblk, true);
+      if (c > 0)
+        cudaStreamWaitEvent(side[c], ctx->ev_fork, 0);
+      ctx->stream = side[c];
+      ovb_launch(ctx, k_feature_system<false>, dim3(hi - lo), dim3(FT_THREADS), csmem, ctx->d_frame, ctx->d_opts, ctx->d_feat, lo, hi, bv,
+                 ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, cM, nblk, (double *)nullptr,
+                 ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
+      ctx->stream = main_stream;
+      if (c > 0) {
+        cudaEventRecord(joined[c], side[c]);
+        cudaStreamWaitEvent(main_stream, joined[c], 0);
+      }
+    }
+    return;
+  }
   int grid = n_feats;
   double *scratch = nullptr;
   if (!S_in_smem) {
@@ -943,13 +984,12 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
       grid = ctx->scratch_ctas;
     scratch = ctx->d_scratch;
   }
-  int dump_rows = ctx->dump_rows; // rows of the current dump (set by ovb_feature_jacobians)
   if (mode == 2)
-    ovb_launch(ctx, k_feature_system<true>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv,
+    ovb_launch(ctx, k_feature_system<true>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, 0, n_feats, bv,
                ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,
                ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
   else
-    ovb_launch(ctx, k_feature_system<false>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, n_feats, bv,
+    ovb_launch(ctx, k_feature_system<false>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, 0, n_feats, bv,
                ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,
                ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
 }

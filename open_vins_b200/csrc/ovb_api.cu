@@ -96,10 +96,14 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
     ctx->tsqr_cluster = e ? atoi(e) : 1;
     const char *e2 = getenv("OVB_TSQR_PDL");
     ctx->tsqr_pdl = e2 ? atoi(e2) : 1;
+    const char *e3 = getenv("OVB_FEAT_CLASSES");
+    ctx->feat_classes = e3 ? atoi(e3) : 1;
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = 1;
   CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->side_stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++)
@@ -190,6 +194,10 @@ void ovb_destroy(ovb_ctx *ctx) {
     cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join)
     cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_join2)
+    cudaEventDestroy(ctx->ev_join2);
+  if (ctx->side_stream2)
+    cudaStreamDestroy(ctx->side_stream2);
   if (ctx->side_stream)
     cudaStreamDestroy(ctx->side_stream);
   if (ctx->stream && ctx->own_stream)

@@ -89,7 +89,9 @@ struct ovb_ctx {
   cudaStream_t stream;
   int own_stream;
   cudaStream_t side_stream;      // column bookkeeping runs here, concurrently with the compression
-  cudaEvent_t ev_fork, ev_join;
+  cudaStream_t side_stream2;     // with side_stream: the per-feature kernel's size classes run side by side
+  cudaEvent_t ev_fork, ev_join, ev_join2;
+  int feat_classes;              // split the per-feature kernel into size classes (OVB_FEAT_CLASSES=0 disables: A/B timing only)
   cudaEvent_t ev[8];
   char err[256];
   // covariance (double buffered for clone/marginalize), row-major with leading dimension ldP
