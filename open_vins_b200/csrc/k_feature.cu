@@ -970,6 +970,7 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
                  ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, cM, nblk, (double *)nullptr,
                  ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
       ctx->stream = main_stream;
+      ctx->n_launch++;
       if (c > 0) {
         cudaEventRecord(joined[c], side[c]);
         cudaStreamWaitEvent(main_stream, joined[c], 0);
@@ -984,6 +985,7 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
       grid = ctx->scratch_ctas;
     scratch = ctx->d_scratch;
   }
+  ctx->n_launch++;
   if (mode == 2)
     ovb_launch(ctx, k_feature_system<true>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, 0, n_feats, bv,
                ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,

@@ -719,7 +719,7 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
     launch_triangulate(ctx, F, bv);
     ctx->n_launch += 2;
   }
-  ctx->n_launch += 2; // feature systems, column map
+  ctx->n_launch += 1; // column map (the per-feature kernel counts its own launches: one, or one per size class)
   if (ev)
     cudaEventRecord(ev[1], ctx->stream);
   launch_feature_system(ctx, F, bv, ldH, slam ? 2 : 0, max_M);
@@ -1041,7 +1041,7 @@ ovb_status ovb_msckf_shard_compress(ovb_ctx *ctx, const ovb_frame *frame, const 
   launch_triangulate(ctx, pk.n_feats, pk.bv);
   launch_feature_system(ctx, pk.n_feats, pk.bv, pk.ldH, 0, pk.max_M);
   launch_column_map(ctx, pk.n_feats, pk.bv);
-  ctx->n_launch += 4;
+  ctx->n_launch += 3; // cam poses, triangulate, column map (+ the per-feature kernel's own count)
   if (pk.m_total > 0)
     launch_tsqr(ctx, ctx->d_Hs, pk.m_total, pk.n_all, pk.ldH, R_dev, pk.ldH);
   else
