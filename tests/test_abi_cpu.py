@@ -62,3 +62,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "ovo_" not in txt and "libovoracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_abi_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: include/ovb200.h must compile as pedantic C99 (no C++ in the signatures) and link
+    against the library from a C translation unit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "c_check.c"
+    src.write_text('#include "ovb200.h"\n#include <stdio.h>\n'
+                   'int main(void) { ovb_opts o; ovb_opts_default(&o); printf("%d %d\\n", ovb_abi_version(), o.max_runs); return 0; }\n')
+    exe = tmp_path / "c_check"
+    libdir = os.path.join(root, "open_vins_b200")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                          "-L", libdir, "-lovb200", "-Wl,-rpath," + libdir, "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["1", "5"], (out.stdout, out.stderr)
