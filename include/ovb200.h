@@ -255,6 +255,16 @@ typedef struct {
 ovb_status ovb_slam_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_landmarks *landmarks,
                            const ovb_opts *opts, ovb_feat_out *out, double *dx, ovb_stats *stats);
 
+/* UpdaterSLAM::perform_anchor_change (update/UpdaterSLAM.cpp:506-647), host math only (no context, no GPU work): re-express an
+ * anchored landmark (ovb_opts.feat_rep = one of the ANCHORED_* representations) in a new anchor camera/clone and return
+ *   new_value / new_value_fej [3]  the landmark's xyz in the new anchor frame (Landmark::set_from_xyz),
+ *   order_off/order_sz[*n_order]   phi_order_OLD: old anchor clone [, its extrinsics], new anchor clone [, its extrinsics], landmark
+ *   Phi [phisize x *n_cols]        row-major, phisize = 3 (1 for ANCHORED_INVERSE_DEPTH_SINGLE); capacity 3 x 27 doubles.
+ * The covariance step is then  ovb_cov_propagate(ctx, lm_off, phisize, order_off, order_sz, *n_order, Phi, Q = 0). */
+ovb_status ovb_slam_anchor_change(const ovb_frame *frame, const ovb_opts *opts, int lm_off, const double *value, const double *value_fej,
+                                  int old_cam, int old_clone, int new_cam, int new_clone, double *new_value, double *new_value_fej,
+                                  double *Phi, int32_t *order_off, int32_t *order_sz, int32_t *n_order, int32_t *n_cols);
+
 /* StateHelper::EKFUpdate with R = sigma2·I (UpdaterMSCKF.cpp:282) or R = diag(Rdiag) (UpdaterSLAM.cpp:444).
  * H is r×n row-major, n = Σ sz.                                                   state/StateHelper.cpp:116-197 */
 ovb_status ovb_ekf_update(ovb_ctx *ctx, const int *off, const int *sz, int nvar, const double *H, int r, const double *res,

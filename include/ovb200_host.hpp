@@ -442,7 +442,7 @@ private:
 };
 
 // ov_msckf::UpdaterSLAM::update (update/UpdaterSLAM.cpp:253-479): update of the landmarks that already live in the state.
-// delayed_init / change_anchors are not part of the engine yet.
+// delayed_init composes from ovb_triangulate + ovb_feature_jacobians + StateHelper::initialize.
 class UpdaterSLAM {
 public:
   UpdaterSLAM(const UpdaterOptions &options_slam, const UpdaterOptions &options_aruco, const FeatureInitializerOptions &feat_init_options)
@@ -565,6 +565,70 @@ public:
     }
     feature_vec.swap(used);
     return dx;
+  }
+
+  // UpdaterSLAM::change_anchors (update/UpdaterSLAM.cpp:481-504): before the oldest clone is marginalised, every landmark
+  // anchored in it moves to the newest clone (same camera). The host math is ovb_slam_anchor_change, the covariance step
+  // StateHelper::EKFPropagation with the 3-wide (1-wide) landmark block and Q = 0.
+  void change_anchors(State &state) {
+    if ((int)state._clones_IMU.size() <= state._options.max_clone_size)
+      return;
+    const double marg_timestep = state._clones_IMU.begin()->first; // State::margtimestep(): the oldest clone
+    const double new_timestep = state._clones_IMU.rbegin()->first; // state->_timestamp: the newest clone
+    std::vector<double> clonetimes;
+    for (const auto &c : state._clones_IMU)
+      clonetimes.push_back(c.first);
+    auto clone_index = [&](double t) { return (int)(std::lower_bound(clonetimes.begin(), clonetimes.end(), t) - clonetimes.begin()); };
+    for (auto &f : state._features_SLAM) {
+      Landmark &lm = *f.second;
+      if (lm._feat_representation == OVB_REP_GLOBAL_3D || lm._feat_representation == OVB_REP_GLOBAL_FULL_INVERSE_DEPTH)
+        continue;
+      if (lm._anchor_clone_timestamp != marg_timestep)
+        continue;
+      perform_anchor_change(state, lm, clone_index(marg_timestep), clone_index(new_timestep), new_timestep, lm._anchor_cam_id);
+    }
+  }
+
+  // UpdaterSLAM::perform_anchor_change (update/UpdaterSLAM.cpp:506-647)
+  void perform_anchor_change(State &state, Landmark &lm, int old_clone, int new_clone, double new_anchor_timestamp, int new_cam_id) {
+    const int C = (int)state._clones_IMU.size(), K = (int)state._cameras.size();
+    std::vector<double> cR((size_t)9 * C), cp((size_t)3 * C), cRf((size_t)9 * C), cpf((size_t)3 * C), kR((size_t)9 * K), kp((size_t)3 * K), kin((size_t)8 * K);
+    std::vector<int> coff((size_t)C), kmodel((size_t)K), kext((size_t)K), kintr((size_t)K, -1);
+    int ci = 0;
+    for (const auto &cl : state._clones_IMU) {
+      std::copy(cl.second->Rot, cl.second->Rot + 9, cR.begin() + 9 * ci);
+      std::copy(cl.second->pos, cl.second->pos + 3, cp.begin() + 3 * ci);
+      std::copy(cl.second->Rot_fej, cl.second->Rot_fej + 9, cRf.begin() + 9 * ci);
+      std::copy(cl.second->pos_fej, cl.second->pos_fej + 3, cpf.begin() + 3 * ci);
+      coff[(size_t)ci++] = cl.second->id;
+    }
+    for (int k = 0; k < K; k++) {
+      const Camera &cam = state._cameras[(size_t)k];
+      std::copy(cam.R_ItoC, cam.R_ItoC + 9, kR.begin() + 9 * k);
+      std::copy(cam.p_IinC, cam.p_IinC + 3, kp.begin() + 3 * k);
+      std::copy(cam.intrinsics, cam.intrinsics + 8, kin.begin() + 8 * k);
+      kmodel[(size_t)k] = cam.model;
+      kext[(size_t)k] = state._options.do_calib_camera_pose ? cam.calib_id : -1;
+    }
+    ovb_frame frame{C, K, cR.data(), cp.data(), cRf.data(), cpf.data(), coff.data(), kR.data(), kp.data(), kin.data(), kmodel.data(), kext.data(), kintr.data()};
+    ovb_opts o;
+    ovb_opts_default(&o);
+    o.do_fej = state._options.do_fej;
+    o.feat_rep = lm._feat_representation;
+    o.do_calib_camera_pose = state._options.do_calib_camera_pose;
+    double nv[3], nvf[3], Phi[3 * 27];
+    int32_t off[8], sz[8], n_order = 0, n_cols = 0;
+    ovb_status st = ovb_slam_anchor_change(&frame, &o, lm.id, lm.xyz, lm.xyz_fej, lm._anchor_cam_id, old_clone, new_cam_id, new_clone, nv, nvf, Phi,
+                                           off, sz, &n_order, &n_cols);
+    if (st != OVB_OK)
+      throw Error(st, "perform_anchor_change: invalid anchor");
+    const int phisize = sz[n_order - 1];
+    std::vector<double> Q((size_t)phisize * phisize, 0.0);
+    state.check(ovb_cov_propagate(state.ctx(), lm.id, phisize, off, sz, n_order, Phi, Q.data()), "perform_anchor_change");
+    std::copy(nv, nv + 3, lm.xyz);
+    std::copy(nvf, nvf + 3, lm.xyz_fej);
+    lm._anchor_cam_id = new_cam_id;
+    lm._anchor_clone_timestamp = new_anchor_timestamp;
   }
 
 private:

@@ -25,6 +25,7 @@ UNITS = [
     ("k_gram.cu", []),
     ("k_ekf.cu", []),
     ("ovb_api.cu", []),
+    ("anchor_change.cu", []),  # host-only math (UpdaterSLAM::perform_anchor_change)
 ]
 HEADERS = ["ovb_internal.cuh", "geom.cuh", "chol.cuh", "chi2_table.inc", os.path.join("..", "..", "include", "ovb200.h")]
 

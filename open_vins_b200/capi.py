@@ -256,6 +256,8 @@ def load_library(path: str | None = None) -> C.CDLL:
                                    c_double_p, c_double_p]
     lib.ovb_cov_initialize.argtypes = [vp, c_int_p, c_int_p, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, C.c_double,
                                        C.c_double, c_int_p, c_double_p, c_double_p]
+    lib.ovb_slam_anchor_change.argtypes = [C.POINTER(ovb_frame), C.POINTER(ovb_opts), C.c_int, c_double_p, c_double_p, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p, c_int_p]
     lib.ovb_slam_update.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_landmarks), C.POINTER(ovb_opts),
                                     C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
     lib.ovb_triangulate.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts),
@@ -283,10 +285,30 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate", "ovb_cov_initialize",
-    "ovb_msckf_update", "ovb_slam_update", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram",
+    "ovb_msckf_update", "ovb_slam_update", "ovb_slam_anchor_change", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram",
     "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
     "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_finish",
 ]
+
+
+def slam_anchor_change(frame: "FrameArrays", opts: ovb_opts, lm_off, value, value_fej, old_cam, old_clone, new_cam, new_clone, lib=None):
+    """UpdaterSLAM::perform_anchor_change host math (no context, no GPU). Returns (new_value, new_value_fej, off, sz, Phi)."""
+    lib = lib or load_library()
+    value = np.ascontiguousarray(value, dtype=np.float64)
+    value_fej = np.ascontiguousarray(value_fej, dtype=np.float64)
+    nv, nvf = np.zeros(3), np.zeros(3)
+    Phi = np.zeros(3 * 27)
+    off, sz = np.zeros(8, dtype=np.int32), np.zeros(8, dtype=np.int32)
+    n_order, n_cols = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+    fs = frame.struct()
+    st = lib.ovb_slam_anchor_change(C.byref(fs), C.byref(opts), int(lm_off), _ptr(value, c_double_p), _ptr(value_fej, c_double_p), int(old_cam),
+                                    int(old_clone), int(new_cam), int(new_clone), _ptr(nv, c_double_p), _ptr(nvf, c_double_p), _ptr(Phi, c_double_p),
+                                    _ptr(off, c_int_p), _ptr(sz, c_int_p), _ptr(n_order, c_int_p), _ptr(n_cols, c_int_p))
+    if st != OVB_OK:
+        raise OvbError(st, "ovb_slam_anchor_change: invalid arguments")
+    no, nc = int(n_order[0]), int(n_cols[0])
+    phisize = int(sz[no - 1])
+    return nv, nvf, off[:no].copy(), sz[:no].copy(), Phi[:phisize * nc].reshape(phisize, nc).copy()
 
 
 class OvbError(RuntimeError):

@@ -202,6 +202,28 @@ int ovo_cov_initialize(const double *P, int N, const int *off, const int *sz, in
   return cov_initialize(P, N, order, HR, HL, rv, sigma2, chi2_mult, chi2_table, Pout, accepted, dx_new, dx);
 }
 
+// UpdaterSLAM::perform_anchor_change host math. Phi_out: phisize x 27 capacity (row-major, leading dimension *ncols).
+int ovo_anchor_change(const ovb_frame *fr, const ovb_opts *op, int lm_off, const double *value, const double *value_fej, int old_cam, int old_clone,
+                      int new_cam, int new_clone, double *new_value, double *new_value_fej, double *Phi_out, int32_t *order_off, int32_t *order_sz,
+                      int32_t *n_order, int32_t *ncols) {
+  AnchorChange a = anchor_change(*fr, *op, op->feat_rep, lm_off, v3(value[0], value[1], value[2]), v3(value_fej[0], value_fej[1], value_fej[2]),
+                                 old_cam, old_clone, new_cam, new_clone);
+  for (int k = 0; k < 3; k++) {
+    new_value[k] = a.value(k);
+    new_value_fej[k] = a.value_fej(k);
+  }
+  *n_order = (int)a.order.size();
+  for (size_t i = 0; i < a.order.size(); i++) {
+    order_off[i] = a.order[i].off;
+    order_sz[i] = a.order[i].size;
+  }
+  *ncols = a.Phi.c;
+  for (int i = 0; i < a.Phi.r; i++)
+    for (int j = 0; j < a.Phi.c; j++)
+      Phi_out[(size_t)i * a.Phi.c + j] = a.Phi(i, j);
+  return OVB_OK;
+}
+
 // measurement_compress_inplace on a row-major H (m x n); outputs R (min(m,n) x n row-major) and z.
 int ovo_compress(const double *H, int m, int n, const double *res, double *R_out, double *z_out) {
   Mat Hc(m, n);

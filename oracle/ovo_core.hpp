@@ -1411,4 +1411,103 @@ inline int cov_initialize(const double *P, int N, const std::vector<Var> &H_orde
   return OVB_OK;
 }
 
+// UpdaterSLAM::perform_anchor_change (update/UpdaterSLAM.cpp:506-647), the host math in front of its EKFPropagation:
+// the landmark re-expressed in the new anchor (value and FEJ value), the variable order phi_order_OLD and Phi.
+struct AnchorChange {
+  V3 value, value_fej;
+  std::vector<Var> order; // phi_order_OLD: x_order_old (+ new ones from x_order_new), then the landmark
+  Mat Phi;                // phisize x sum(order sizes)
+};
+inline AnchorChange anchor_change(const ovb_frame &fr, const ovb_opts &op, int rep, int lm_off, const V3 &value, const V3 &value_fej,
+                                  int old_cam, int old_clone, int new_cam, int new_clone) {
+  AnchorChange out;
+  Mat Hf_old, Hf_new;
+  std::vector<Mat> Hx_old, Hx_new;
+  std::vector<Var> xo_old, xo_new;
+  jacobian_representation(fr, op, rep, value, value_fej, value, old_cam, old_clone, Hf_old, Hx_old, xo_old);
+  auto cam_pose = [&](int cam, int cl, bool fej, M3 &R_GtoC, V3 &p_CinG) {
+    M3 R_GtoI = load_m3((fej ? fr.clone_R_fej : fr.clone_R) + 9 * cl);
+    V3 p_IinG = load_v3((fej ? fr.clone_p_fej : fr.clone_p) + 3 * cl);
+    R_GtoC = m3mul(load_m3(fr.cam_R + 9 * cam), R_GtoI);
+    p_CinG = vsub(p_IinG, m3Tv(R_GtoC, load_v3(fr.cam_p + 3 * cam)));
+  };
+  auto transfer = [&](bool fej, const V3 &p_old) {
+    M3 R_GtoOLD, R_GtoNEW;
+    V3 p_OLDinG, p_NEWinG;
+    cam_pose(old_cam, old_clone, fej, R_GtoOLD, p_OLDinG);
+    cam_pose(new_cam, new_clone, fej, R_GtoNEW, p_NEWinG);
+    M3 R_OLDtoNEW = m3mul(R_GtoNEW, m3T(R_GtoOLD));
+    V3 p_OLDinNEW = m3v(R_GtoNEW, vsub(p_OLDinG, p_NEWinG));
+    return vadd(m3v(R_OLDtoNEW, p_old), p_OLDinNEW);
+  };
+  out.value = transfer(false, value);
+  out.value_fej = transfer(true, value_fej);
+  jacobian_representation(fr, op, rep, out.value, out.value_fej, out.value, new_cam, new_clone, Hf_new, Hx_new, xo_new);
+  // phi_order_OLD (:600-617)
+  std::vector<int> col_old(xo_old.size()), col_new(xo_new.size());
+  int cur = 0;
+  auto place = [&](const Var &v) {
+    int c = find_var(out.order, v.off);
+    if (c < 0) {
+      c = cur;
+      out.order.push_back(v);
+      cur += v.size;
+    }
+    return c;
+  };
+  for (size_t i = 0; i < xo_old.size(); i++)
+    col_old[i] = place(xo_old[i]);
+  for (size_t i = 0; i < xo_new.size(); i++)
+    col_new[i] = place(xo_new[i]);
+  const int phisize = (rep != OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE) ? 3 : 1;
+  const int col_lm = cur;
+  out.order.push_back(Var{lm_off, phisize});
+  cur += phisize;
+  out.Phi.resize_zero(phisize, cur);
+  // H_f_new^-1 (:624-629)
+  Mat Inv(phisize, 3);
+  if (phisize == 1) {
+    double n2 = 0;
+    for (int i = 0; i < 3; i++)
+      n2 += Hf_new(i, 0) * Hf_new(i, 0);
+    for (int i = 0; i < 3; i++)
+      Inv(0, i) = 1.0 / n2 * Hf_new(i, 0);
+  } else {
+    M3 A;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        A(i, j) = Hf_new(i, j);
+    for (int c = 0; c < 3; c++) { // colPivHouseholderQr().solve(Identity), column by column
+      V3 e = v3(c == 0, c == 1, c == 2);
+      V3 x = colpiv_qr_solve3(A, e);
+      for (int i = 0; i < 3; i++)
+        Inv(i, c) = x(i);
+    }
+  }
+  auto add_block = [&](int col, const Mat &B, double sign) { // Phi[:, col:col+B.c] += sign * Inv * B
+    for (int i = 0; i < phisize; i++)
+      for (int j = 0; j < B.c; j++) {
+        double acc = 0.0;
+        for (int k = 0; k < 3; k++)
+          acc += Inv(i, k) * B(k, j);
+        out.Phi(i, col + j) += sign * acc;
+      }
+  };
+  for (size_t i = 0; i < Hx_old.size(); i++)
+    add_block(col_old[i], Hx_old[i], 1.0);
+  {
+    Mat blk(phisize, phisize);
+    for (int i = 0; i < phisize; i++)
+      for (int j = 0; j < phisize; j++) {
+        double acc = 0.0;
+        for (int k = 0; k < 3; k++)
+          acc += Inv(i, k) * Hf_old(k, j);
+        out.Phi(i, col_lm + j) = acc;
+      }
+  }
+  for (size_t i = 0; i < Hx_new.size(); i++)
+    add_block(col_new[i], Hx_new[i], -1.0);
+  return out;
+}
+
 } // namespace ovo

@@ -120,3 +120,71 @@ def test_initialize_gate_rejects_inconsistent_systems(oracle):
     res = res + 3.0  # residuals far beyond what P and the noise explain
     st, acc, Po, dxn, dx = oracle.cov_initialize(P, off, sz, H_R, H_L, res, sigma2=0.05 ** 2, chi2_mult=1.0)
     assert st == 0 and not acc and np.array_equal(Po, P)
+
+
+ANCHORED = [capi.REP_ANCHORED_3D, capi.REP_ANCHORED_FULL_INVERSE_DEPTH, capi.REP_ANCHORED_MSCKF_INVERSE_DEPTH,
+            capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE]
+
+
+def _global_point(fr, cam, cl, pA, fej=False):
+    R = (fr.clone_R_fej if fej else fr.clone_R)[cl]
+    p = (fr.clone_p_fej if fej else fr.clone_p)[cl]
+    return R.T @ (fr.cam_R[cam].T @ (pA - fr.cam_p[cam])) + p
+
+
+@pytest.mark.parametrize("rep", ANCHORED)
+@pytest.mark.parametrize("ext,fej", [(1, 1), (0, 1), (1, 0)])
+def test_anchor_change_matches_oracle_and_keeps_the_point(oracle, rep, ext, fej):
+    """ovb_slam_anchor_change (host math of UpdaterSLAM::perform_anchor_change, UpdaterSLAM.cpp:506-647; no GPU involved) against
+    the oracle restatement, plus the geometric invariant: the landmark's global position does not move."""
+    case = sim.make_slam_case(n_landmarks=6, n_clones=7, n_cams=2, seed=90 + rep, rep=rep)
+    fr, lm = case.frame, case.landmarks
+    opts = capi.default_opts(do_calib_camera_pose=ext, do_calib_camera_intrinsics=0, feat_rep=rep, do_fej=fej)
+    for f, (new_cam, new_clone) in enumerate([(0, 6), (1, 6), (0, 5), (1, 3), (0, 6), (1, 4)]):
+        old_cam, old_clone = int(lm.anchor_cam[f]), int(lm.anchor_clone[f])
+        got = capi.slam_anchor_change(fr, opts, lm.lm_off[f], lm.value[f], lm.value_fej[f], old_cam, old_clone, new_cam, new_clone)
+        ref = oracle.anchor_change(fr, opts, lm.lm_off[f], lm.value[f], lm.value_fej[f], old_cam, old_clone, new_cam, new_clone)
+        nv, nvf, off, sz, Phi = got
+        assert np.array_equal(off, ref[2]) and np.array_equal(sz, ref[3])
+        assert sz[-1] == (1 if rep == capi.REP_ANCHORED_INVERSE_DEPTH_SINGLE else 3) and off[-1] == lm.lm_off[f]
+        np.testing.assert_allclose(nv, ref[0], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(nvf, ref[1], rtol=1e-13, atol=1e-15)
+        assert np.linalg.norm(Phi - ref[4]) <= 1e-11 * np.linalg.norm(ref[4])
+        # same point in the global frame before and after (current estimates, and FEJ estimates for the FEJ value)
+        np.testing.assert_allclose(_global_point(fr, new_cam, new_clone, nv), _global_point(fr, old_cam, old_clone, lm.value[f]), atol=1e-12)
+        np.testing.assert_allclose(_global_point(fr, new_cam, new_clone, nvf, True), _global_point(fr, old_cam, old_clone, lm.value_fej[f], True),
+                                   atol=1e-12)
+
+
+def test_anchor_change_phi_by_finite_differences(oracle):
+    """ANCHORED_3D, FEJ off: Phi's landmark and position blocks are plain derivatives of
+    p_new = R_OLDtoNEW p_old + p_OLDinNEW with respect to p_old and the two clone positions."""
+    rep = capi.REP_ANCHORED_3D
+    case = sim.make_slam_case(n_landmarks=3, n_clones=6, n_cams=2, seed=17, rep=rep)
+    fr, lm = case.frame, case.landmarks
+    opts = capi.default_opts(do_calib_camera_pose=0, feat_rep=rep, do_fej=0)
+    f, new_cam, new_clone = 1, 1, 5
+    old_cam, old_clone = int(lm.anchor_cam[f]), int(lm.anchor_clone[f])
+    nv, nvf, off, sz, Phi = capi.slam_anchor_change(fr, opts, lm.lm_off[f], lm.value[f], lm.value[f], old_cam, old_clone, new_cam, new_clone)
+    cols = np.concatenate([[0], np.cumsum(sz)])
+    h = 1e-6
+
+    def new_value(val, dp_old=np.zeros(3), dp_new=np.zeros(3)):
+        fr2 = capi.FrameArrays(fr.clone_R, fr.clone_p.copy(), fr.clone_R, fr.clone_p.copy(), fr.clone_off, fr.cam_R, fr.cam_p, fr.cam_intr,
+                               fr.cam_model, fr.cam_ext_off, fr.cam_intr_off)
+        fr2.clone_p[old_clone] += dp_old
+        fr2.clone_p[new_clone] += dp_new
+        fr2.clone_p_fej[:] = fr2.clone_p
+        return capi.slam_anchor_change(fr2, opts, lm.lm_off[f], val, val, old_cam, old_clone, new_cam, new_clone)[0]
+
+    for k in range(3):
+        e = np.zeros(3)
+        e[k] = h
+        fd_lm = (new_value(lm.value[f] + e) - new_value(lm.value[f] - e)) / (2 * h)
+        np.testing.assert_allclose(Phi[:, cols[-2] + k], fd_lm, atol=1e-7)                 # d p_new / d p_old
+        i_old = int(np.flatnonzero(off == fr.clone_off[old_clone])[0])
+        i_new = int(np.flatnonzero(off == fr.clone_off[new_clone])[0])
+        fd_old = (new_value(lm.value[f], dp_old=e) - new_value(lm.value[f], dp_old=-e)) / (2 * h)
+        fd_new = (new_value(lm.value[f], dp_new=e) - new_value(lm.value[f], dp_new=-e)) / (2 * h)
+        np.testing.assert_allclose(Phi[:, cols[i_old] + 3 + k], fd_old, atol=1e-7)        # position part of the old anchor clone
+        np.testing.assert_allclose(Phi[:, cols[i_new] + 3 + k], fd_new, atol=1e-7)        # position part of the new anchor clone
