@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compress", default="cholqr2", choices=["tsqr", "gram", "cholqr2"],
+                    help="measurement compression: cholqr2 (default, csrc/k_cholqr.cu), tsqr (Householder), gram (one-pass normal equations)")
     ap.add_argument("--features", type=int, default=WORKLOAD["n_feats"],
                     help="features per update (default: BASELINE config 2 = 400; 4096 = the config-3 sweep point, for scaling studies)")
     args = ap.parse_args()
@@ -208,7 +210,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     case = sim.make_update_case(**WORKLOAD)
-    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, col_order=capi.COLS_CANONICAL)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, col_order=capi.COLS_CANONICAL,
+                             compress={"tsqr": capi.COMPRESS_HOUSEHOLDER_TSQR, "gram": capi.COMPRESS_NORMAL_EQUATIONS,
+                                       "cholqr2": capi.COMPRESS_CHOLQR2}[args.compress])
     F = case.feats.n_feats
     if world > 1:
         from open_vins_b200 import multigpu

@@ -83,10 +83,14 @@ typedef enum {
 typedef enum {
   OVB_COMPRESS_HOUSEHOLDER_TSQR = 0, /* default. blocked Householder TSQR; R equals the reference's Givens R row for row
                                         (diag >= 0); post-update P/x within 1e-9 of the reference in every tested setup */
-  OVB_COMPRESS_NORMAL_EQUATIONS = 1  /* opt-in fast mode: [R z] = chol([H r]'[H r]), one streaming pass, ~4x faster.
+  OVB_COMPRESS_NORMAL_EQUATIONS = 1, /* opt-in fast mode: [R z] = chol([H r]'[H r]), one streaming pass, ~4x faster.
                                         Squares the condition number: with weakly observable calibration states in the
                                         update (online intrinsics/extrinsics) the posterior of those states is only good to
                                         ~1e-6 relative, so it misses the 1e-9 parity bar there (tests/test_gpu_gram.py) */
+  OVB_COMPRESS_CHOLQR2 = 2           /* shifted CholeskyQR2 on the FP64 tensor-core path (csrc/k_cholqr.cu): two Gram +
+                                        Cholesky passes with a row-wise triangular solve in between. No condition-number
+                                        loss in R'R / R'z; systems wider than 159 columns fall back to the
+                                        Householder TSQR */
 } ovb_compress_mode;
 
 /* ---- context ---- */
@@ -294,6 +298,9 @@ ovb_status ovb_compress(ovb_ctx *ctx, const double *H, int m, int n, const doubl
 /* Same contract through the normal equations (OVB_COMPRESS_NORMAL_EQUATIONS): R upper triangular with diag >= 0,
  * rows whose pivot is at round-off level are zero. */
 ovb_status ovb_compress_gram(ovb_ctx *ctx, const double *H, int m, int n, const double *res, double *R_out, double *z_out);
+
+/* Same contract through the shifted CholeskyQR2 (OVB_COMPRESS_CHOLQR2); n <= 159, else OVB_ERR_CAPACITY. */
+ovb_status ovb_compress_cholqr2(ovb_ctx *ctx, const double *H, int m, int n, const double *res, double *R_out, double *z_out);
 
 /* chi² 0.95 quantile table used by the gate (boost::math::quantile in the reference, UpdaterMSCKF.cpp:52-55). */
 double ovb_chi2_quantile95(int dof);

@@ -23,6 +23,7 @@ UNITS = [
     ("k_feature.cu", ["-fmad=false"]),
     ("k_tsqr.cu", []),
     ("k_gram.cu", []),
+    ("k_cholqr.cu", []),
     ("k_ekf.cu", []),
     ("ovb_api.cu", []),
     ("anchor_change.cu", []),  # host-only math (UpdaterSLAM::perform_anchor_change)

@@ -28,7 +28,7 @@ OVB_OK, OVB_ERR_NEG_DIAG, OVB_ERR_NONFINITE, OVB_ERR_CAPACITY, OVB_ERR_CUDA, OVB
  REP_ANCHORED_MSCKF_INVERSE_DEPTH, REP_ANCHORED_INVERSE_DEPTH_SINGLE) = range(6)
 CAM_RADTAN, CAM_EQUI = 0, 1
 COLS_REFERENCE_FIRST_SEEN, COLS_CANONICAL = 0, 1
-COMPRESS_HOUSEHOLDER_TSQR, COMPRESS_NORMAL_EQUATIONS = 0, 1
+COMPRESS_HOUSEHOLDER_TSQR, COMPRESS_NORMAL_EQUATIONS, COMPRESS_CHOLQR2 = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)
@@ -267,6 +267,7 @@ def load_library(path: str | None = None) -> C.CDLL:
                                           c_int_p, c_int_p, c_int_p, C.c_int]
     lib.ovb_compress.argtypes = [vp, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
     lib.ovb_compress_gram.argtypes = [vp, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
+    lib.ovb_compress_cholqr2.argtypes = [vp, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
     lib.ovb_chi2_quantile95.argtypes = [C.c_int]
     lib.ovb_chi2_quantile95.restype = C.c_double
     lib.ovb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 6)]
@@ -285,7 +286,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate", "ovb_cov_initialize",
-    "ovb_msckf_update", "ovb_slam_update", "ovb_slam_anchor_change", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram",
+    "ovb_msckf_update", "ovb_slam_update", "ovb_slam_anchor_change", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram", "ovb_compress_cholqr2",
     "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
     "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_finish",
 ]
@@ -452,11 +453,12 @@ class Engine:
         m, n = H.shape
         R = np.zeros((n, n))
         z = np.zeros(n)
-        fn = self.lib.ovb_compress if mode == COMPRESS_HOUSEHOLDER_TSQR else self.lib.ovb_compress_gram
+        fn = {COMPRESS_HOUSEHOLDER_TSQR: self.lib.ovb_compress, COMPRESS_NORMAL_EQUATIONS: self.lib.ovb_compress_gram,
+              COMPRESS_CHOLQR2: self.lib.ovb_compress_cholqr2}[mode]
         self._check(fn(self.h, _ptr(H, c_double_p), m, n, _ptr(res, c_double_p), _ptr(R, c_double_p), _ptr(z, c_double_p)))
         return R, z
 
-    def ekf_update(self, off, sz, H, res, sigma2=1.0, Rdiag=None):
+    def ekf_update(self, off, sz, H, res, sigma2=1.0, Rdiag=None, allow=()):
         off = np.ascontiguousarray(off, dtype=np.int32)
         sz = np.ascontiguousarray(sz, dtype=np.int32)
         H = np.ascontiguousarray(H, dtype=np.float64)
@@ -466,7 +468,7 @@ class Engine:
         st = self.lib.ovb_ekf_update(self.h, _ptr(off, c_int_p), _ptr(sz, c_int_p), len(off), _ptr(H, c_double_p),
                                      H.shape[0], _ptr(res, c_double_p), float(sigma2), _ptr(Rd, c_double_p),
                                      _ptr(dx, c_double_p))
-        self._check(st, allow=(OVB_ERR_NEG_DIAG,))
+        self._check(st, allow=(OVB_ERR_NEG_DIAG,) + tuple(allow))
         return st, dx
 
     # ---- multi-GPU staged calls (device pointers are raw ints, e.g. torch.Tensor.data_ptr())

@@ -23,16 +23,17 @@ __device__ __forceinline__ void stage_lower_async(double *dst, int ldd, const do
 
 #define EKC_THREADS 512 // threads of the single-CTA Cholesky kernels (16 warps: cheaper barriers, 128 registers per thread)
 
-// 1/sqrt(d) from a float seed refined to full double precision; the library sqrt/divide pair costs several
-// hundred cycles on a single dependent chain, and every Cholesky pivot sits on the critical path of the whole CTA.
+// 1/sqrt(d) from the hardware's double-precision seed (MUFU.RSQ64H, ~2^-20 relative, no float round trip) refined by
+// one third-order (Halley) step to full double precision: ~80 cycles on the dependent chain instead of ~170 for the
+// float-seeded variant and several hundred for the library sqrt/divide pair (tools/ubench/cholqr_bench.cu). Every
+// Cholesky pivot sits on the critical path of its whole CTA.
 __device__ __forceinline__ double fast_rsqrt(double d) {
-  if (d > 1e-30 && d < 1e30) {
-    // one third-order (Halley) step: 22 -> ~66 bits
-    double y = (double)rsqrtf((float)d);
-    const double e = 1.0 - d * y * y;
-    return y + y * (e * (0.5 + 0.375 * e));
-  }
-  return 1.0 / sqrt(d);
+  // branch free (a taken branch on the pivot chain costs more than the arithmetic): valid for normal positive d; the
+  // callers select the result away for d <= 0, and pivots are >= sigma^2 or a shift, far from the subnormal range
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = 1.0 - d * y * y;
+  return y + y * (e * (0.5 + 0.375 * e));
 }
 
 // 8x8 diagonal block of the blocked Cholesky, factored in registers by one warp: lane i (< nbk) holds row i and the

@@ -1,0 +1,908 @@
+// k_cholqr.cu — measurement compression as a shifted CholeskyQR2 on the FP64 tensor-core path (DMMA), plus the
+// single-CTA DMMA Cholesky shared with the EKF update.
+// Replaces UpdaterHelper::measurement_compress_inplace (ov_msckf/src/update/UpdaterHelper.cpp:456-487: a Givens sweep of
+// 3mn² flops with stride-m accesses) for stacked systems of up to CQ_MAXN columns (residual included).
+//
+//   pass 1   G1 = [H r]'[H r]                      k_cq_gram (DMMA, row slabs over all SMs) + k_cq_reduce (fixed order)
+//            R1'R1 = G1 + s1 I                      k_cq_chol (one CTA, matrix tile-packed in shared memory, DMMA trailing update)
+//            Q1 = [H r] R1^-1   (in place)          k_cq_trsm (row groups in registers, right-looking, DMMA)
+//   pass 2   G2 = Q1'Q1,  R2'R2 = G2 + s2 I         the same two kernels
+//            [R z] = rows 0..n-1 of R2 R1           k_cq_trmm
+//
+// Why two passes are enough for the filter: StateHelper::EKFUpdate (state/StateHelper.cpp:116-197) sees
+// the compressed system only through R'R = H'H and R'z = H'r. With Q1 = A R1^-1 computed by row-wise backward-stable
+// substitution (A + dA = Q1 R1, |dA| <= c u |Q1||R1|, the same column-wise backward error a Householder QR commits),
+//   R'R = R1'(Q1'Q1 + E) R1 = (A+dA)'(A+dA) + R1' E R1,     -eps I <= E <= eps I  (Gram rounding + s2, |Q1 e_j| <= 1)
+// and R1'E R1 is bounded IN THE POSITIVE-SEMIDEFINITE ORDER by eps (G1 + s1 I): a relative perturbation eps of the
+// information the measurements carry plus an absolute eps*s1 ~ 1e-24 |A|² — no condition-number factor, whatever R1
+// was (R1 only has to keep |Q1| <= ~1, which the shift s1 guarantees). A single pass (k_gram.cu) has the kappa² loss
+// that failed the 1e-9 bar with weakly observable calibration columns; the second pass removes it. The shifts make the
+// factorisations total on the rank-deficient MSCKF system (gauge nullspace).
+//
+// Everything is deterministic (no atomics, fixed reduction order): replicas on different GPUs stay bitwise equal.
+#include "chol.cuh"
+#include "ovb_internal.cuh"
+#include <math.h>
+#include <cstdio>
+
+#define CQ_MAXN 160      // columns incl. the residual that the single-CTA Cholesky / register TRSM take
+#define CQ_MAXB 20       // CQ_MAXN / 8
+#define CQ_MAXRB 22      // row blocks of the Cholesky (n + extra right-hand-side rows <= 176)
+#define CQ_GRAM_T 512    // threads of k_cq_gram (16 warps, one 32x32 output tile each)
+#define CQ_KB 32         // rows per staged chunk in k_cq_gram
+#define CQ_CHOL_T 384
+#define CQ_CHOL_NA 4     // look-ahead warps of the Cholesky
+#define CQ_XP 12         // pitch of the panel buffer (conflict-free 8x4 fragments)
+#define CQ_TRSM_T 640
+
+namespace {
+
+// D(8x8) += A(8x4) B(4x8), FP64 tensor-core path. a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], d0/d1 = D[lane>>2][2*(lane&3)+{0,1}]
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned s_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cpa16(unsigned dst, const void *src, unsigned bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cpa8(unsigned dst, const void *src, unsigned bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bar_group(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ int tri(int b) { return (b * (b + 1)) >> 1; }
+
+// Output tile owned by warp w of Gram block blk. The Gram matrix is cut into blocks of BW x BW warp tiles (32 x 32 each);
+// only blocks bI <= bJ exist; a diagonal block keeps its upper warp tiles only. Returns false for an idle warp.
+__device__ __forceinline__ bool cq_tile_origin(int blk, int w, int BW, int nblk_side, int &ci, int &cj, int &offI, int &offJ, bool &diag) {
+  int bI = 0, t = blk;
+  while (t >= nblk_side - bI) {
+    t -= nblk_side - bI;
+    bI++;
+  }
+  const int bJ = bI + t;
+  diag = (bI == bJ);
+  int a, b;
+  if (diag) {
+    a = 0;
+    int u = w;
+    while (a < BW && u >= BW - a) {
+      u -= BW - a;
+      a++;
+    }
+    if (a >= BW)
+      return false;
+    b = a + u;
+  } else {
+    if (w >= BW * BW)
+      return false;
+    a = w / BW;
+    b = w % BW;
+  }
+  offI = a * 32;
+  offJ = (diag ? 0 : BW * 32) + b * 32;
+  ci = (bI * BW + a) * 32;
+  cj = (bJ * BW + b) * 32;
+  return true;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------------ Gram
+// Partial Gram matrix of one row slab: Gpart[slab][blk][warp][32x32] = A[slab rows, I cols]' A[slab rows, J cols].
+// The slab streams through shared memory in chunks of CQ_KB rows (cp.async, double buffered, zero fill past the edges);
+// both DMMA operands are the SAME fragment pattern X[k0 + (lane&3)][c0 + (lane>>2)] of the staged rows, so one staged
+// chunk feeds the row- and the column-side of every tile. grid = (upper blocks, slabs).
+__global__ void __launch_bounds__(CQ_GRAM_T) k_cq_gram(const double *__restrict__ A, int ldA, int m, int nt, int slab_rows, int BW, int nblk_side,
+                                                      double *__restrict__ Gpart) {
+  OVB_PDL_ENTER();
+  extern __shared__ __align__(16) double gsm[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
+  int ci, cj, offI, offJ;
+  bool diag;
+  const bool active = cq_tile_origin(blockIdx.x, wid, BW, nblk_side, ci, cj, offI, offJ, diag);
+  // column ranges staged per row: [I range (BW*32)] then, for off-diagonal blocks, [J range (BW*32)]
+  int bI = 0, tt = blockIdx.x;
+  while (tt >= nblk_side - bI) {
+    tt -= nblk_side - bI;
+    bI++;
+  }
+  const int bJ = bI + tt;
+  const int WI = BW * 32;
+  const int nrng = (bI == bJ) ? 1 : 2;
+  const int pitch = nrng * WI + 4; // = 4 mod 16: conflict-free fragment loads
+  const int cI0 = bI * WI, cJ0 = bJ * WI;
+  const int r0 = blockIdx.y * slab_rows, r1 = min(m, r0 + slab_rows);
+  const int nchunks = (r1 > r0) ? (r1 - r0 + CQ_KB - 1) / CQ_KB : 0;
+  const int units_per_row = nrng * WI / 2;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+      acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  auto issue = [&](int c) {
+    double *buf = gsm + (size_t)(c & 1) * CQ_KB * pitch;
+    const int rc = r0 + c * CQ_KB;
+    for (int e = tid; e < CQ_KB * units_per_row; e += CQ_GRAM_T) {
+      const int k = e / units_per_row, u = e - k * units_per_row;
+      const int r = rc + k;
+      int col, dcol;
+      if (2 * u < WI) {
+        col = cI0 + 2 * u;
+        dcol = 2 * u;
+      } else {
+        col = cJ0 + (2 * u - WI);
+        dcol = 2 * u;
+      }
+      unsigned bytes = 0;
+      if (r < r1)
+        bytes = (col + 1 < nt) ? 16u : (col < nt ? 8u : 0u);
+      const double *src = bytes ? (A + (size_t)r * ldA + col) : A;
+      cpa16(s_u32(buf + (size_t)k * pitch + dcol), src, bytes);
+    }
+    cpa_commit();
+  };
+  if (nchunks > 0)
+    issue(0);
+  for (int c = 0; c < nchunks; c++) {
+    if (c + 1 < nchunks) {
+      issue(c + 1);
+      cpa_wait<1>();
+    } else {
+      cpa_wait<0>();
+    }
+    __syncthreads();
+    if (active) {
+      const double *buf = gsm + (size_t)(c & 1) * CQ_KB * pitch;
+#pragma unroll
+      for (int ks = 0; ks < CQ_KB / 4; ks++) {
+        const double *row = buf + (size_t)(4 * ks + q) * pitch + g;
+        double fa[4], fb[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          fa[b] = row[offI + 8 * b];
+        if (diag && offI == offJ) {
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+            fb[b] = fa[b];
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+            fb[b] = row[offJ + 8 * b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+            dmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    double *dst = Gpart + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + wid) * 1024;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        *reinterpret_cast<double2 *>(dst + (8 * a + g) * 32 + 8 * b + 2 * q) = make_double2(acc[a][b][0], acc[a][b][1]);
+  }
+}
+
+// G[i][j] = sum over slabs in a FIXED order (bitwise reproducible), for i <= j, mirrored. grid = (16 warp tiles x 8 chunks
+// of 128 elements, blocks); the 1024 threads of a CTA are 128 elements x 8 slab groups (group g sums slabs g, g+8, ...),
+// the eight partial sums meet in shared memory and are added as a balanced tree.
+#define CQ_RED_T 1024
+#define CQ_RED_CH 8
+#define CQ_RED_GX (16 * CQ_RED_CH)
+__global__ void __launch_bounds__(CQ_RED_T) k_cq_reduce(const double *__restrict__ Gpart, int nslab, int nblk, int BW, int nblk_side, int nt,
+                                                       double *__restrict__ G, int ldG) {
+  OVB_PDL_ENTER();
+  __shared__ double red[8][128];
+  int ci, cj, offI, offJ;
+  bool diag;
+  const int w = blockIdx.x / CQ_RED_CH, ch = blockIdx.x % CQ_RED_CH, blk = blockIdx.y;
+  if (!cq_tile_origin(blk, w, BW, nblk_side, ci, cj, offI, offJ, diag))
+    return;
+  if (ci >= nt || cj >= nt)
+    return;
+  const int el = threadIdx.x & 127, sg = threadIdx.x >> 7;
+  const int e = ch * 128 + el;
+  const double *src = Gpart + ((size_t)blk * 16 + w) * 1024 + e;
+  const size_t stride = (size_t)nblk * 16 * 1024;
+  double s0 = 0.0, s1 = 0.0;
+  int sl = sg;
+  for (; sl + 8 < nslab; sl += 16) {
+    s0 += src[(size_t)sl * stride];
+    s1 += src[(size_t)(sl + 8) * stride];
+  }
+  if (sl < nslab)
+    s0 += src[(size_t)sl * stride];
+  red[sg][el] = s0 + s1;
+  __syncthreads();
+  if (sg == 0) {
+    const int i = ci + (e >> 5), j = cj + (e & 31);
+    if (i < nt && j < nt && i <= j) {
+      const double s = ((red[0][el] + red[1][el]) + (red[2][el] + red[3][el])) + ((red[4][el] + red[5][el]) + (red[6][el] + red[7][el]));
+      G[(size_t)i * ldG + j] = s;
+      G[(size_t)j * ldG + i] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------ Cholesky
+// Single-CTA Cholesky of an n x n SPD matrix (n <= CQ_MAXN) with `extra` right-hand-side rows appended as rows n.. .
+// The lower triangle lives in shared memory as packed 8x8 tiles (tile (bi,bj), bj <= bi, at (bi(bi+1)/2 + bj)*64,
+// row-major inside): a tile IS the DMMA accumulator fragment (lane reads its two doubles at 2*lane: conflict free), and
+// the whole 160 x 160 triangle is 107 KB. Right-looking, 8-wide block steps:
+//   trailing update  S[bi][bj] -= X[bi] X[bj]'  : two DMMAs per tile, operands from the panel buffer Xp (pitch 12),
+//                    two tiles in flight per warp
+//   look-ahead       warps 0..4 update block column k+1 first, warp 0 factors its diagonal tile — every lane holds the
+//                    whole 8x8 triangle in registers and runs the same 8-pivot chain (no shuffles, no divergence;
+//                    MUFU.RSQ64H-seeded reciprocal square roots) — then the five warps solve panel k+1, all while warps
+//                    5..15 finish the rest of trailing update k. One CTA barrier per block step.
+// Measured chain per block step (tools/ubench/cholqr_bench.cu): DMMA 26 cycles dependent, DFMA 8, rsqrt ~80.
+struct CqCholSmem {
+  double T[(CQ_MAXRB * (CQ_MAXRB + 1) / 2) * 64];
+  double Xp[2][CQ_MAXRB * 8 * CQ_XP];
+  double invd[CQ_MAXRB * 8];
+  double red[32];
+  int flag;
+};
+
+// The factor as the other kernels consume it (written by the Cholesky kernel as a straight copy of its shared memory):
+//   [tile-packed lower triangle of L = R', tile (bi,bj) at (bi(bi+1)/2 + bj)*64, row-major 8x8] [reciprocal pivots 1/L_jj]
+// Entries past n are zero (the solve treats the padded diagonal as 1).
+#define CQ_PK_INV ((CQ_MAXB * (CQ_MAXB + 1) / 2) * 64)
+#define CQ_PK_DOUBLES (CQ_PK_INV + CQ_MAXB * 8)
+
+namespace {
+
+// Factor the diagonal tile (row-major 8x8, lower) — all lanes of the calling warp compute the same thing in registers;
+// rows >= nbk of the tile are left untouched. strict: a pivot <= 0 (or NaN) raises *flag; else pivots are floored at
+// floor_d (semidefinite input) and a zero pivot empties its column.
+__device__ __forceinline__ void cq_diag8(double *tile, int nbk, double *invd, bool strict, double floor_d, int *flag) {
+  const int lane = threadIdx.x & 31;
+  double a[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+#pragma unroll
+    for (int j2 = 0; j2 < 4; j2++) {
+      if (2 * j2 <= i) {
+        const double2 v = *reinterpret_cast<const double2 *>(tile + i * 8 + 2 * j2);
+        a[i][2 * j2] = v.x;
+        a[i][2 * j2 + 1] = v.y;
+      }
+    }
+  }
+  double inv[8];
+  bool bad = false;
+  const double inv_floor = (floor_d > 0.0) ? fast_rsqrt(floor_d) : 0.0; // off the chain: known before the first pivot
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const double d0 = a[j][j];
+    const double y = fast_rsqrt(d0); // unconditional; the comparisons below run beside it and only select
+    const bool in = j < nbk;
+    double d, iv;
+    if (strict) {
+      const bool pos = d0 > 0.0;
+      bad = bad || (in && !pos);
+      d = d0;
+      iv = (in && pos) ? y : 0.0;
+    } else {
+      const bool above = d0 > floor_d; // NaN falls to the floor as well; it survives elsewhere in the row
+      d = above ? d0 : floor_d;
+      iv = in ? (above ? y : inv_floor) : 0.0; // floor 0 (all-zero system): the column empties
+    }
+    inv[j] = iv;
+    a[j][j] = d * iv;
+#pragma unroll
+    for (int i = j + 1; i < 8; i++)
+      a[i][j] *= iv;
+#pragma unroll
+    for (int i = j + 1; i < 8; i++)
+#pragma unroll
+      for (int c = j + 1; c <= i; c++)
+        a[i][c] -= a[i][j] * a[c][j];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (lane == i && i < nbk) {
+#pragma unroll
+      for (int c = 0; c <= i; c++)
+        tile[i * 8 + c] = a[i][c];
+    }
+  }
+  if (lane == 8) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      invd[j] = inv[j];
+    if (bad)
+      *flag = 1;
+  }
+}
+
+// rows i0, i0+stride, ... of panel k: x L_kk' = S[i][kb..kb+8); writes x in place and into the panel buffer (zero past nbk).
+// L_kk and the reciprocal pivots go to registers first so that the substitution chain never waits for shared memory.
+__device__ __forceinline__ void cq_panel_rows(double *T, double *Xp, const double *invd, int i0, int stride, int nrows, int k, int nbk) {
+  if (i0 >= nrows)
+    return;
+  const double *Lk = T + (size_t)(tri(k) + k) * 64;
+  double L[8][8], iv[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    iv[c] = (c < nbk) ? invd[8 * k + c] : 0.0;
+#pragma unroll
+    for (int t2 = 0; t2 < 4; t2++) {
+      if (2 * t2 < c) {
+        const double2 v = *reinterpret_cast<const double2 *>(Lk + c * 8 + 2 * t2);
+        L[c][2 * t2] = v.x;
+        L[c][2 * t2 + 1] = v.y;
+      }
+    }
+  }
+  for (int i = i0; i < nrows; i += stride) {
+    double *src = T + (size_t)(tri(i >> 3) + k) * 64 + (i & 7) * 8;
+    double v[8], x[8];
+    {
+      const double2 v01 = *reinterpret_cast<const double2 *>(src), v23 = *reinterpret_cast<const double2 *>(src + 2);
+      const double2 v45 = *reinterpret_cast<const double2 *>(src + 4), v67 = *reinterpret_cast<const double2 *>(src + 6);
+      v[0] = v01.x, v[1] = v01.y, v[2] = v23.x, v[3] = v23.y, v[4] = v45.x, v[5] = v45.y, v[6] = v67.x, v[7] = v67.y;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      double s = v[c];
+#pragma unroll
+      for (int t = 0; t < 8; t++)
+        if (t < c)
+          s -= x[t] * L[c][t];
+      x[c] = (c < nbk) ? s * iv[c] : 0.0;
+    }
+    if (nbk == 8) {
+      *reinterpret_cast<double2 *>(src) = make_double2(x[0], x[1]);
+      *reinterpret_cast<double2 *>(src + 2) = make_double2(x[2], x[3]);
+      *reinterpret_cast<double2 *>(src + 4) = make_double2(x[4], x[5]);
+      *reinterpret_cast<double2 *>(src + 6) = make_double2(x[6], x[7]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        if (c < nbk)
+          src[c] = x[c];
+    }
+    double *xp = Xp + (size_t)i * CQ_XP;
+    *reinterpret_cast<double2 *>(xp) = make_double2(x[0], x[1]);
+    *reinterpret_cast<double2 *>(xp + 2) = make_double2(x[2], x[3]);
+    *reinterpret_cast<double2 *>(xp + 4) = make_double2(x[4], x[5]);
+    *reinterpret_cast<double2 *>(xp + 6) = make_double2(x[6], x[7]);
+  }
+}
+
+struct CqTileOps {
+  double a0, a1, b0, b1;
+  double2 c;
+  double2 *cp;
+};
+__device__ __forceinline__ void cq_tile_load(CqTileOps &o, double *T, const double *Xp, int bi, int bj, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const double *xa = Xp + (size_t)(8 * bi + g) * CQ_XP + q;
+  const double *xb = Xp + (size_t)(8 * bj + g) * CQ_XP + q;
+  o.cp = reinterpret_cast<double2 *>(T + (size_t)(tri(bi) + bj) * 64 + 2 * lane);
+  o.a0 = -xa[0];
+  o.a1 = -xa[4];
+  o.b0 = xb[0];
+  o.b1 = xb[4];
+  o.c = *o.cp;
+}
+__device__ __forceinline__ void cq_tile_mma_store(CqTileOps &o) {
+  dmma(o.c.x, o.c.y, o.a0, o.b0);
+  dmma(o.c.x, o.c.y, o.a1, o.b1);
+  *o.cp = o.c;
+}
+
+#ifdef CQ_PROBE
+#define CQ_PROBE_T(v) v = clock64()
+#else
+#define CQ_PROBE_T(v) do { } while (0)
+#endif
+
+// The factorisation proper, on a tile-packed lower triangle already in shared memory. n columns, nrows = n + extra rows.
+__device__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, bool strict, double floor_d) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // look-ahead group = the warps of sub-partition 0 (wid % 4 == 0): the pivot chain then never queues behind the other
+  // warps' DMMAs in the FP64 pipe of its sub-partition
+  constexpr int NW = CQ_CHOL_T / 32, NA = NW / 4, NBW = NW - NA;
+  const bool inA = (wid & 3) == 0;
+  const int widA = wid >> 2, tidA = widA * 32 + lane;  // rank inside the look-ahead group
+  const int widB = wid - (wid >> 2) - 1;               // rank among the other warps
+#ifdef CQ_PROBE
+  long long p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0;
+#endif
+  const int NB = (n + 7) >> 3, NRB = (nrows + 7) >> 3;
+  if (wid == 0)
+    cq_diag8(sm.T, min(8, n), sm.invd, strict, floor_d, &sm.flag);
+  __syncthreads();
+  cq_panel_rows(sm.T, sm.Xp[0], sm.invd, min(8, n) + tid, CQ_CHOL_T, nrows, 0, min(8, n));
+  __syncthreads();
+  for (int k = 0; k + 1 < NB; k++) {
+    const int par = k & 1;
+    const double *Xk = sm.Xp[par];
+    CQ_PROBE_T(p0);
+    if (inA) {
+      const int k1 = k + 1;
+      const int nbk1 = min(8, n - 8 * k1);
+      // block column k+1 (warp 0 takes the diagonal tile first), two tiles in flight
+      for (int bi = k1 + widA; bi < NRB; bi += 2 * NA) {
+        CqTileOps o0, o1;
+        cq_tile_load(o0, sm.T, Xk, bi, k1, lane);
+        const bool two = bi + NA < NRB;
+        if (two)
+          cq_tile_load(o1, sm.T, Xk, bi + NA, k1, lane);
+        cq_tile_mma_store(o0);
+        if (two)
+          cq_tile_mma_store(o1);
+      }
+      CQ_PROBE_T(p1);
+      bar_group(1, NA * 32);
+      CQ_PROBE_T(p2);
+      if (wid == 0)
+        cq_diag8(sm.T + (size_t)(tri(k1) + k1) * 64, nbk1, sm.invd + 8 * k1, strict, floor_d, &sm.flag);
+      CQ_PROBE_T(p3);
+      bar_group(1, NA * 32);
+      CQ_PROBE_T(p4);
+      cq_panel_rows(sm.T, sm.Xp[par ^ 1], sm.invd, 8 * k1 + nbk1 + tidA, NA * 32, nrows, k1, nbk1);
+      CQ_PROBE_T(p5);
+    } else {
+      // tiles (bi, bj) with k+2 <= bj <= bi < NRB, bj < NB, flattened row by row over the remaining warps; the flat index
+      // advances by the warp count, the (row, column) pair follows incrementally
+      const int R = NRB - (k + 2);
+      const int TB = (R * (R + 1)) >> 1;
+      int r = 0, c = widB;
+      while (c > r) {
+        c -= r + 1;
+        r++;
+      }
+      for (int t = widB; t < TB; t += 2 * NBW) {
+        const int bi0 = k + 2 + r, bj0 = k + 2 + c;
+        c += NBW;
+        while (c > r) {
+          c -= r + 1;
+          r++;
+        }
+        const int bi1 = k + 2 + r, bj1 = k + 2 + c;
+        const bool two = t + NBW < TB;
+        c += NBW;
+        while (c > r) {
+          c -= r + 1;
+          r++;
+        }
+        CqTileOps o0, o1;
+        const bool v0 = bj0 < NB, v1 = two && bj1 < NB;
+        if (v0)
+          cq_tile_load(o0, sm.T, Xk, bi0, bj0, lane);
+        if (v1)
+          cq_tile_load(o1, sm.T, Xk, bi1, bj1, lane);
+        if (v0)
+          cq_tile_mma_store(o0);
+        if (v1)
+          cq_tile_mma_store(o1);
+      }
+      CQ_PROBE_T(p1);
+    }
+    __syncthreads();
+    CQ_PROBE_T(p6);
+#ifdef CQ_PROBE
+    if ((k == 0 || k == 8 || k == 16) && (tid == 0 || tid == 32 || tid == 128 || tid == CQ_CHOL_T - 32)) {
+      if (inA)
+        printf("chol k=%d tid=%d A: tiles %lld bar %lld diag %lld bar %lld panel %lld wait %lld | step %lld\n", k, tid, p1 - p0, p2 - p1, p3 - p2, p4 - p3,
+               p5 - p4, p6 - p5, p6 - p0);
+      else
+        printf("chol k=%d tid=%d B: tiles %lld wait %lld | step %lld\n", k, tid, p1 - p0, p6 - p1, p6 - p0);
+    }
+#endif
+  }
+}
+
+// stage the lower triangle of a row-major global matrix (rows < nrows, cols < n; rows >= n come from `rhs` when given)
+// into the tile-packed layout with 16-byte cp.async (one warp per row, every load of the CTA in flight at once); whole
+// diagonal tiles are fetched, everything past the edges is zero-filled. ldG must be even (16-byte aligned row starts).
+__device__ void cq_load_tiles(CqCholSmem &sm, const double *__restrict__ G, size_t ldG, int n, int nrows, const double *__restrict__ rhs, int ld_rhs) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int NB = (n + 7) >> 3, NRB = (nrows + 7) >> 3;
+  for (int i = wid; i < 8 * NRB; i += CQ_CHOL_T / 32) {
+    const double *row = (i >= n && rhs != nullptr) ? rhs + (size_t)(i - n) * ld_rhs : G + (size_t)i * ldG;
+    const int jmax = min(i | 7, 8 * NB - 1);
+    double *dst = sm.T + (size_t)tri(i >> 3) * 64 + (i & 7) * 8;
+    for (int j = 2 * lane; j <= jmax; j += 64) {
+      unsigned bytes = 0;
+      if (i < nrows)
+        bytes = (j + 1 < n) ? 16u : (j < n ? 8u : 0u);
+      cpa16(s_u32(dst + (size_t)(j >> 3) * 64 + (j & 7)), bytes ? (const void *)(row + j) : (const void *)G, bytes);
+    }
+  }
+  cpa_commit();
+  for (int e = tid; e < 2 * CQ_MAXRB * 8 * CQ_XP; e += CQ_CHOL_T)
+    (&sm.Xp[0][0])[e] = 0.0;
+  if (tid == 0)
+    sm.flag = 0;
+  cpa_wait<0>();
+}
+
+__device__ __forceinline__ double cq_el(const double *T, int i, int j) { return T[(size_t)(tri(i >> 3) + (j >> 3)) * 64 + (i & 7) * 8 + (j & 7)]; }
+
+} // namespace
+
+// Gram mode: L L' = G + shift_rel * max(diag G) * I; writes L (= R') in the packed layout above to Lpk. ldG even.
+__global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_gram(const double *__restrict__ G, int ldG, int n, double shift_rel, double *__restrict__ Lpk) {
+  OVB_PDL_ENTER();
+  extern __shared__ __align__(16) unsigned char cq_raw[];
+  CqCholSmem &sm = *reinterpret_cast<CqCholSmem *>(cq_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#ifdef CQ_PROBE
+  const long long q0 = clock64();
+#endif
+  cq_load_tiles(sm, G, (size_t)ldG, n, n, nullptr, 0);
+  __syncthreads();
+  // largest diagonal entry -> shift
+  double mx = 0.0;
+  for (int i = tid; i < n; i += CQ_CHOL_T) {
+    const double d = sm.T[(size_t)(tri(i >> 3) + (i >> 3)) * 64 + (i & 7) * 9];
+    mx = (d > mx) ? d : mx;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double y = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = (y > mx) ? y : mx;
+  }
+  if (lane == 0)
+    sm.red[wid] = mx;
+  __syncthreads();
+  mx = 0.0;
+  for (int w = 0; w < CQ_CHOL_T / 32; w++)
+    mx = (sm.red[w] > mx) ? sm.red[w] : mx;
+  const double shift = shift_rel * mx;
+  for (int i = tid; i < n; i += CQ_CHOL_T)
+    sm.T[(size_t)(tri(i >> 3) + (i >> 3)) * 64 + (i & 7) * 9] += shift;
+  __syncthreads();
+#ifdef CQ_PROBE
+  const long long q1 = clock64();
+#endif
+  cq_chol_tiles(sm, n, n, false, 0.25 * shift);
+#ifdef CQ_PROBE
+  const long long q2 = clock64();
+#endif
+  const int NB = (n + 7) >> 3;
+  for (int e = 2 * tid; e < tri(NB) * 64; e += 2 * CQ_CHOL_T)
+    *reinterpret_cast<double2 *>(Lpk + e) = *reinterpret_cast<const double2 *>(sm.T + e);
+  for (int e = tid; e < CQ_MAXB * 8; e += CQ_CHOL_T)
+    Lpk[CQ_PK_INV + e] = (e < n) ? sm.invd[e] : 1.0;
+#ifdef CQ_PROBE
+  if (tid == 0)
+    printf("chol_gram n=%d: load %lld factor %lld store %lld cycles\n", n, q1 - q0, q2 - q1, clock64() - q2);
+#endif
+}
+
+// EKF mode (StateHelper::EKFUpdate's LLT, state/StateHelper.cpp:160-161): S (r x r, lower triangle in global memory) with
+// the residual as right-hand-side row -> L written back over the lower triangle of S, w = L^-1 res, 1/diag(L); a
+// non-positive pivot raises info->not_spd. ldS even.
+__global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_ekf(double *__restrict__ S, int ldS, int r, const double *__restrict__ res, double *__restrict__ w,
+                                                          double *__restrict__ invdiag, DevUpdateInfo *__restrict__ info, double *__restrict__ Lpk) {
+  OVB_PDL_ENTER();
+  extern __shared__ __align__(16) unsigned char cq_raw[];
+  CqCholSmem &sm = *reinterpret_cast<CqCholSmem *>(cq_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  cq_load_tiles(sm, S, (size_t)ldS, r, r + 1, res, 0);
+  __syncthreads();
+  cq_chol_tiles(sm, r, r + 1, true, 0.0);
+  for (int i = wid; i < r; i += CQ_CHOL_T / 32)
+    for (int j = lane; j <= i; j += 32)
+      S[(size_t)i * ldS + j] = cq_el(sm.T, i, j);
+  for (int j = tid; j < r; j += CQ_CHOL_T) {
+    w[j] = cq_el(sm.T, r, j);
+    invdiag[j] = sm.invd[j];
+  }
+  if (Lpk != nullptr) { // the factor as k_cq_trsm consumes it (Y = M L^-T)
+    const int NB = (r + 7) >> 3;
+    for (int e = 2 * tid; e < tri(NB) * 64; e += 2 * CQ_CHOL_T)
+      *reinterpret_cast<double2 *>(Lpk + e) = *reinterpret_cast<const double2 *>(sm.T + e);
+    for (int e = tid; e < CQ_MAXB * 8; e += CQ_CHOL_T)
+      Lpk[CQ_PK_INV + e] = (e < r) ? sm.invd[e] : 1.0;
+  }
+  if (tid == 0 && sm.flag)
+    info->not_spd = 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------ TRSM
+// A <- A R^-1 in place, R = L' upper triangular nt x nt (nt <= CQ_MAXN). One warp owns 8 rows, whose column blocks live
+// in registers as DMMA accumulator fragments. The columns are taken in two halves of NH blocks so that a row group
+// needs 2*NH accumulator doubles per lane: 20 warps (row groups) are resident per SM and the FP64 tensor pipe always has
+// somebody's DMMAs to run while the others sit in their substitution chains. Within a half, right-looking:
+//   gather   the four lanes of a quad exchange their column pairs, so every lane holds its row's 8 entries of the block
+//   solve    x R_jj = v by substitution in registers, redundantly in the four lanes (backward stable row by row; the
+//            dependent chain is one multiply + one FMA per column, no shuffle on it)
+//   push     the solved block IS then the A-operand (register select): -X_j R[j][j+1..] goes into the later blocks of
+//            the half with independent DMMAs; the fragments are also parked in shared memory for the second half,
+//            which starts with the plain product  A[:, half 2] -= X[:, half 1] R[half 1, half 2].
+// L sits in shared memory in the Cholesky kernel's tile layout: tile (j, jb) read at g*8 + 4ks + q is exactly the
+// B-operand fragment of R[8jb.., 8j..] (conflict free).
+#define CQ_TRSM_NH 10 // column blocks per half
+#define CQ_TRSM_SMEM (sizeof(double) * ((size_t)CQ_PK_DOUBLES + (size_t)(CQ_TRSM_T / 32) * CQ_TRSM_NH * 2 * 32))
+template <int NH>
+__device__ __forceinline__ void cq_trsm_half(double (&acc)[NH][2], int b0, int nb, const double *Lt, const double *Ri, double *xs, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int jb = 0; jb < NH; jb++) {
+    if (jb < nb) {
+      const int B = b0 + jb;
+      const double *Ld = Lt + (size_t)(tri(B) + B) * 64; // R[8B+t][8B+c] = Ld[c*8 + t], t <= c
+      const double *ri = Ri + B * 8;
+      double x[8];
+#pragma unroll
+      for (int qq = 0; qq < 4; qq++) {
+        x[2 * qq] = __shfl_sync(0xffffffffu, acc[jb][0], (lane & ~3) | qq);
+        x[2 * qq + 1] = __shfl_sync(0xffffffffu, acc[jb][1], (lane & ~3) | qq);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        x[c] *= ri[c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; c2++)
+          x[c2] -= x[c] * Ld[c2 * 8 + c];
+      }
+      acc[jb][0] = (q == 0) ? x[0] : (q == 1) ? x[2] : (q == 2) ? x[4] : x[6];
+      acc[jb][1] = (q == 0) ? x[1] : (q == 1) ? x[3] : (q == 2) ? x[5] : x[7];
+      // A-operand fragments of the two k-steps: element (row g, column 4ks + q), negated
+      const double af0 = -((q == 0) ? x[0] : (q == 1) ? x[1] : (q == 2) ? x[2] : x[3]);
+      const double af1 = -((q == 0) ? x[4] : (q == 1) ? x[5] : (q == 2) ? x[6] : x[7]);
+      if (xs != nullptr) {
+        xs[(2 * jb) * 32 + lane] = af0;
+        xs[(2 * jb + 1) * 32 + lane] = af1;
+      }
+#pragma unroll
+      for (int j = 0; j < NH; j++) {
+        if (j > jb && j < nb) {
+          const double *lf = Lt + (size_t)(tri(b0 + j) + B) * 64 + g * 8 + q;
+          dmma(acc[j][0], acc[j][1], af0, lf[0]);
+          dmma(acc[j][0], acc[j][1], af1, lf[4]);
+        }
+      }
+    }
+  }
+}
+
+template <int NH>
+__device__ __forceinline__ void cq_trsm_load(double (&acc)[NH][2], const double *arow, bool row_ok, int b0, int nb, int nt, int q) {
+#pragma unroll
+  for (int jb = 0; jb < NH; jb++) {
+    const int col = 8 * (b0 + jb) + 2 * q;
+    acc[jb][0] = acc[jb][1] = 0.0;
+    if (jb < nb && row_ok) {
+      if (col + 1 < nt) {
+        const double2 v = *reinterpret_cast<const double2 *>(arow + col);
+        acc[jb][0] = v.x;
+        acc[jb][1] = v.y;
+      } else if (col < nt) {
+        acc[jb][0] = arow[col];
+      }
+    }
+  }
+}
+template <int NH>
+__device__ __forceinline__ void cq_trsm_store(const double (&acc)[NH][2], double *arow, bool row_ok, int b0, int nb, int nt, int q) {
+  if (!row_ok)
+    return;
+#pragma unroll
+  for (int jb = 0; jb < NH; jb++) {
+    const int col = 8 * (b0 + jb) + 2 * q;
+    if (jb < nb) {
+      if (col + 1 < nt)
+        *reinterpret_cast<double2 *>(arow + col) = make_double2(acc[jb][0], acc[jb][1]);
+      else if (col < nt)
+        arow[col] = acc[jb][0];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CQ_TRSM_T) k_cq_trsm(double *__restrict__ A, int ldA, int m, int nt, const double *__restrict__ Lpk) {
+  OVB_PDL_ENTER();
+  constexpr int NH = CQ_TRSM_NH;
+  extern __shared__ __align__(16) double tsm[];
+  double *Lt = tsm;
+  double *Ri = tsm + CQ_PK_INV;
+  double *Xs = tsm + CQ_PK_DOUBLES; // per warp: first-half A-operand fragments [NH][2][32]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int NB = (nt + 7) >> 3;
+  const int nb1 = min(NB, NH), nb2 = NB - nb1;
+  for (int e = 2 * tid; e < tri(NB) * 64; e += 2 * CQ_TRSM_T)
+    cpa16(s_u32(Lt + e), Lpk + e, 16u);
+  for (int e = 2 * tid; e < NB * 8; e += 2 * CQ_TRSM_T)
+    cpa16(s_u32(Ri + e), Lpk + CQ_PK_INV + e, 16u);
+  cpa_commit();
+  cpa_wait<0>();
+  __syncthreads();
+  double *xs = Xs + (size_t)wid * (NH * 2 * 32);
+  const int ngroups = (m + 7) >> 3;
+  for (int rg = blockIdx.x * (CQ_TRSM_T / 32) + wid; rg < ngroups; rg += gridDim.x * (CQ_TRSM_T / 32)) {
+    const int row = 8 * rg + g;
+    const bool row_ok = row < m;
+    double *arow = A + (size_t)row * ldA;
+    double acc[NH][2];
+    cq_trsm_load<NH>(acc, arow, row_ok, 0, nb1, nt, q);
+    cq_trsm_half<NH>(acc, 0, nb1, Lt, Ri, nb2 > 0 ? xs : nullptr, lane);
+    cq_trsm_store<NH>(acc, arow, row_ok, 0, nb1, nt, q);
+    if (nb2 > 0) {
+      cq_trsm_load<NH>(acc, arow, row_ok, nb1, nb2, nt, q);
+      __syncwarp();
+      // A[:, half 2] -= X[:, half 1] R[half 1, half 2]
+#pragma unroll 2
+      for (int jb = 0; jb < nb1; jb++) {
+        const double af0 = xs[(2 * jb) * 32 + lane], af1 = xs[(2 * jb + 1) * 32 + lane];
+#pragma unroll
+        for (int j = 0; j < NH; j++) {
+          if (j < nb2) {
+            const double *lf = Lt + (size_t)(tri(nb1 + j) + jb) * 64 + g * 8 + q;
+            dmma(acc[j][0], acc[j][1], af0, lf[0]);
+            dmma(acc[j][0], acc[j][1], af1, lf[4]);
+          }
+        }
+      }
+      cq_trsm_half<NH>(acc, nb1, nb2, Lt, Ri, nullptr, lane);
+      cq_trsm_store<NH>(acc, arow, row_ok, nb1, nb2, nt, q);
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------ R = R2 R1
+// Product of two upper-triangular nt x nt factors; rows 0..n-1 (n = nt - 1) go to Rout = [R | z], lower part zeroed.
+// both factors arrive as tile-packed L = R'. 16 x 16 output tile per CTA; the tile's whole K range (at most CQ_MAXN deep) is staged in
+// one shot, so a CTA pays one L2 round trip.
+__global__ void __launch_bounds__(256) k_cq_trmm(const double *__restrict__ L2, const double *__restrict__ L1, int nt, double *__restrict__ Rout, int ldR) {
+  OVB_PDL_ENTER();
+  __shared__ double As[16][CQ_MAXN + 1]; // R2[16ti + a][k0 + k]
+  __shared__ double Bs[CQ_MAXN][17];     // R1[k0 + k][16tj + b]
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n = nt - 1;
+  const int i = ti * 16 + ty, j = tj * 16 + tx;
+  double acc = 0.0;
+  if (tj >= ti) {
+    const int k0 = ti * 16, k1 = min(nt, tj * 16 + 16); // R2[i][k] = 0 for k < i, R1[k][j] = 0 for k > j
+    const int K = k1 - k0;
+    for (int e = tid; e < 16 * K; e += 256) {
+      const int a = e / K, k = e - a * K;
+      const int ii = ti * 16 + a, kk = k0 + k;
+      As[a][k] = (ii < nt && kk >= ii) ? L2[(size_t)(tri(kk >> 3) + (ii >> 3)) * 64 + (kk & 7) * 8 + (ii & 7)] : 0.0; // R2[ii][kk] = L2[kk][ii]
+    }
+    for (int e = tid; e < 16 * K; e += 256) {
+      const int k = e >> 4, b = e & 15;
+      const int kk = k0 + k, jj = tj * 16 + b;
+      Bs[k][b] = (jj < nt && jj >= kk) ? L1[(size_t)(tri(jj >> 3) + (kk >> 3)) * 64 + (jj & 7) * 8 + (kk & 7)] : 0.0; // R1[kk][jj] = L1[jj][kk]
+    }
+    __syncthreads();
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 3 < K; k += 4) {
+      a0 += As[ty][k] * Bs[k][tx];
+      a1 += As[ty][k + 1] * Bs[k + 1][tx];
+      a2 += As[ty][k + 2] * Bs[k + 2][tx];
+      a3 += As[ty][k + 3] * Bs[k + 3][tx];
+    }
+    for (; k < K; k++)
+      a0 += As[ty][k] * Bs[k][tx];
+    acc = (a0 + a1) + (a2 + a3);
+  }
+  if (i < n && j < nt)
+    Rout[(size_t)i * ldR + j] = (j >= i) ? acc : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------------------ launchers
+static bool cq_attrs(ovb_ctx *ctx) {
+  if (!ctx->attr_done[4]) {
+    cudaFuncSetAttribute(k_cq_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_cq_chol_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CqCholSmem));
+    cudaFuncSetAttribute(k_cq_chol_ekf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CqCholSmem));
+    cudaFuncSetAttribute(k_cq_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CQ_TRSM_SMEM);
+    ctx->attr_done[4] = 1;
+  }
+  return true;
+}
+
+int ovb_cholqr_max_cols(void) { return CQ_MAXN; }
+
+static bool cq_ensure_G(ovb_ctx *ctx) {
+  const int ldW = CQ_MAXN + 8;
+  const size_t need_G = (size_t)4 * ldW * ldW; // [G (both passes) | L1 | L2 | EKF factor]
+  if (need_G > ctx->G_cap) {
+    if (ctx->d_G)
+      cudaFree(ctx->d_G);
+    ctx->d_G = nullptr;
+    if (cudaMalloc(&ctx->d_G, sizeof(double) * need_G) != cudaSuccess)
+      return false;
+    ctx->G_cap = need_G;
+  }
+  return true;
+}
+
+// EKF Cholesky through the DMMA kernel when S (+ the residual row) fits its tile store. With one right-hand-side row the
+// last row block may spill past CQ_MAXB blocks; the packed factor (for the register solve) is only offered when it fits.
+bool launch_chol_ekf_dmma(ovb_ctx *ctx, double *S, int ldS, int r, const double *res, double *w, double *invdiag, double **Lpk_out) {
+  if (Lpk_out)
+    *Lpk_out = nullptr;
+  if (r + 1 > CQ_MAXRB * 8 || r > CQ_MAXN || (ldS & 1))
+    return false;
+  cq_attrs(ctx);
+  double *Lpk = nullptr;
+  if (cq_ensure_G(ctx)) {
+    const int ldW = CQ_MAXN + 8;
+    Lpk = ctx->d_G + (size_t)3 * ldW * ldW;
+  }
+  ovb_launch(ctx, k_cq_chol_ekf, dim3(1), dim3(CQ_CHOL_T), sizeof(CqCholSmem), S, ldS, r, res, w, invdiag, ctx->d_info, Lpk);
+  if (Lpk_out)
+    *Lpk_out = Lpk;
+  return true;
+}
+
+bool launch_trsm_rows(ovb_ctx *ctx, double *A, int ldA, int m, int nt, const double *Lpk) {
+  if (nt > CQ_MAXN || (ldA & 1) || m < 1 || Lpk == nullptr)
+    return false;
+  cq_attrs(ctx);
+  const int ngroups = (m + 7) / 8;
+  int ctas = (ngroups + 3) / 4; // short matrices (the EKF's N rows): few row groups per CTA so that the groups spread over the SMs
+  if (ctas > ctx->sm_count)
+    ctas = ctx->sm_count;
+  ovb_launch(ctx, k_cq_trsm, dim3(ctas), dim3(CQ_TRSM_T), (size_t)CQ_TRSM_SMEM, A, ldA, m, nt, Lpk);
+  return true;
+}
+
+// [R | z] <- shifted CholeskyQR2 of A [m x (n+1)] (A is overwritten by Q1). Returns the number of kernels launched, or -1
+// when the system is too wide for this path (the caller falls back to the Householder TSQR).
+int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR) {
+  const int nt = n + 1;
+  if (nt > CQ_MAXN || (ldA & 1) || m < 1)
+    return -1;
+  cq_attrs(ctx);
+  const int nT = (nt + 31) / 32; // warp tiles per side (<= 5)
+  const int BW = nT, nblk_side = 1, nblk = 1;
+  int nslab = ctx->sm_count;
+  const int max_slabs = (m + CQ_KB - 1) / CQ_KB;
+  if (nslab > max_slabs)
+    nslab = max_slabs;
+  int slab_rows = (m + nslab - 1) / nslab;
+  slab_rows = (slab_rows + 3) & ~3;
+  nslab = (m + slab_rows - 1) / slab_rows;
+  const size_t need_part = (size_t)nslab * nblk * 16 * 1024;
+  const int ldW = CQ_MAXN + 8;
+  if (!cq_ensure_G(ctx))
+    return -1;
+  if (need_part > ctx->Gpart_cap) {
+    if (ctx->d_Gpart)
+      cudaFree(ctx->d_Gpart);
+    ctx->d_Gpart = nullptr;
+    if (cudaMalloc(&ctx->d_Gpart, sizeof(double) * need_part) != cudaSuccess)
+      return -1;
+    ctx->Gpart_cap = need_part;
+  }
+  double *G = ctx->d_G, *L1 = G + (size_t)ldW * ldW, *L2 = L1 + (size_t)ldW * ldW;
+  static_assert(CQ_PK_DOUBLES <= (CQ_MAXN + 8) * (CQ_MAXN + 8), "packed factor must fit its slot");
+  const size_t gram_smem = sizeof(double) * 2 * CQ_KB * (size_t)(BW * 32 + 4);
+  const size_t trsm_smem = CQ_TRSM_SMEM;
+  const int ngroups = (m + 7) / 8;
+  int trsm_ctas = (ngroups + CQ_TRSM_T / 32 - 1) / (CQ_TRSM_T / 32);
+  if (trsm_ctas > ctx->sm_count)
+    trsm_ctas = ctx->sm_count;
+  for (int pass = 0; pass < 2; pass++) {
+    ovb_launch(ctx, k_cq_gram, dim3(nblk, nslab), dim3(CQ_GRAM_T), gram_smem, (const double *)A, ldA, m, nt, slab_rows, BW, nblk_side, ctx->d_Gpart);
+    ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, nslab, nblk, BW, nblk_side, nt, G, ldW);
+    ovb_launch(ctx, k_cq_chol_gram, dim3(1), dim3(CQ_CHOL_T), sizeof(CqCholSmem), (const double *)G, ldW, nt, pass == 0 ? 1e-11 : 1e-13,
+               pass == 0 ? L1 : L2);
+    if (pass == 0)
+      ovb_launch(ctx, k_cq_trsm, dim3(trsm_ctas), dim3(CQ_TRSM_T), trsm_smem, A, ldA, m, nt, (const double *)L1);
+  }
+  const int nT16 = (nt + 15) / 16;
+  ovb_launch(ctx, k_cq_trmm, dim3(nT16, nT16), dim3(256), (size_t)0, (const double *)L2, (const double *)L1, nt, Rout, ldR);
+  ctx->n_launch += 8;
+  return 8;
+}

@@ -122,10 +122,12 @@ __global__ void __launch_bounds__(EKC_THREADS) k_ekf_chol(double *__restrict__ S
 #define TR_ROWS 8 // rows of M (warps) per CTA
 __global__ void __launch_bounds__(32 * TR_ROWS) k_ekf_trsm(const double *__restrict__ M, int ldM, const double *__restrict__ L, int ldL,
                                                            const double *__restrict__ invdiag, int N, int r, double *__restrict__ Yout, int ldY,
-                                                           int L_in_smem) {
+                                                           int L_in_smem, const DevUpdateInfo *__restrict__ info) {
   OVB_PDL_ENTER();
   extern __shared__ __align__(16) double tsm[]; // [TR_ROWS][r] y rows, then r reciprocal pivots, then L (r x ldl) when it fits
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (info->not_spd)
+    return; // failed factor: leave P untouched (the status code is then recoverable, include/ovb200.h)
   const int ldl = r | 1;
   double *inv_s = tsm + (size_t)TR_ROWS * r;
   double *Ls = inv_s + r;
@@ -203,6 +205,11 @@ __global__ void __launch_bounds__(256) k_ekf_downdate(double *__restrict__ P, in
   if (b0 < a0)
     return;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  if (info->not_spd) { // failed factor: P stays as it was, no correction
+    if (a0 == b0 && tid < EK_T && a0 + tid < N)
+      dx[a0 + tid] = 0.0;
+    return;
+  }
   double acc[4] = {0, 0, 0, 0};
   double dxa = 0.0; // dx partial for row a0 + tid (diagonal tiles, tid < 32)
   for (int k0 = 0; k0 < r; k0 += EK_T) {
@@ -244,6 +251,128 @@ __global__ void __launch_bounds__(256) k_ekf_downdate(double *__restrict__ P, in
     dx[a0 + tid] = dxa;
 }
 
+// ---- one-shot variants for K <= EK1_KMAX (the whole inner dimension staged at once: a CTA pays ONE L2 round trip instead
+// of one per 32-wide K tile; at config-2 sizes these products are latency-, not flop-bound). Same contract as k_ekf_gemm.
+#define EK1_KMAX 160
+__global__ void __launch_bounds__(256) k_ekf_gemm1(int mode, const double *__restrict__ P, int ldP, const double *__restrict__ H, int ldH,
+                                                   const double *__restrict__ Min, int ldM, const DevUpdateInfo *__restrict__ info, int X, int Y,
+                                                   int K, double *__restrict__ Cout, int ldC, double sigma2, const double *__restrict__ Rdiag) {
+  OVB_PDL_ENTER();
+  extern __shared__ __align__(16) double g1[];
+  const int x0 = blockIdx.x * EK_T, y0 = blockIdx.y * EK_T;
+  if (mode == 1 && y0 > x0 + EK_T - 1)
+    return; // strictly upper tile of S
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int *cs = info->col_state;
+  const int pk = K | 1;
+  // mode 0: Gs[j][a] = P[cs[j]][x0+a] (K x 32, pitch 33)   Hs[i][j] = H[y0+i][j] (32 x K, pitch pk)      M[a][i]
+  // mode 1: Hs[i][j] = H[x0+i][j]      (32 x K, pitch pk)   Gs[j][k] = M[cs[j]][y0+k] (K x 32, pitch 33)   S[i][k]
+  double *Gs = g1, *Hs = g1 + (size_t)K * 33;
+  const double *Gsrc = (mode == 0) ? P : Min;
+  const int ldG = (mode == 0) ? ldP : ldM;
+  const int g0 = (mode == 0) ? x0 : y0, gmax = (mode == 0) ? X : Y;
+  const int h0 = (mode == 0) ? y0 : x0, hmax = (mode == 0) ? Y : X;
+  for (int e = tid; e < K * 32; e += 256) {
+    const int j = e >> 5, a = e & 31;
+    Gs[j * 33 + a] = (g0 + a < gmax) ? Gsrc[(size_t)cs[j] * ldG + g0 + a] : 0.0;
+  }
+  for (int i = ty; i < 32; i += 8)
+    for (int j = tx; j < K; j += 32)
+      Hs[i * pk + j] = (h0 + i < hmax) ? H[(size_t)(h0 + i) * ldH + j] : 0.0;
+  __syncthreads();
+  double acc[4] = {0, 0, 0, 0};
+  if (mode == 0) {
+    // acc[u] = sum_j Gs[j][tx] * Hs[ty + 8u][j]   -> M[x0 + tx][y0 + ty + 8u]
+    for (int j = 0; j < K; j++) {
+      const double gv = Gs[j * 33 + tx];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        acc[u] += gv * Hs[(ty + 8 * u) * pk + j];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int a = x0 + tx, i = y0 + ty + 8 * u;
+      if (a < X && i < Y)
+        Cout[(size_t)a * ldC + i] = acc[u];
+    }
+  } else {
+    // acc[u] = sum_j Hs[ty + 8u][j] * Gs[j][tx]   -> S[x0 + ty + 8u][y0 + tx]
+    for (int j = 0; j < K; j++) {
+      const double gv = Gs[j * 33 + tx];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        acc[u] += Hs[(ty + 8 * u) * pk + j] * gv;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = x0 + ty + 8 * u, k = y0 + tx;
+      if (i < X && k < Y) {
+        double v = acc[u];
+        if (i == k)
+          v += Rdiag ? Rdiag[i] : sigma2;
+        Cout[(size_t)i * ldC + k] = v;
+      }
+    }
+  }
+}
+
+// P <- sym_U(P - Y Y'), dx = Y w, r <= EK1_KMAX: both 32-row strips of Y staged at once (same contract as k_ekf_downdate)
+__global__ void __launch_bounds__(256) k_ekf_downdate1(double *__restrict__ P, int ldP, const double *__restrict__ Yin, int ldY, int N, int r,
+                                                       const double *__restrict__ w, double *__restrict__ dx, DevUpdateInfo *__restrict__ info) {
+  OVB_PDL_ENTER();
+  extern __shared__ __align__(16) double d1[];
+  const int a0 = blockIdx.x * EK_T, b0 = blockIdx.y * EK_T;
+  if (b0 < a0)
+    return;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  if (info->not_spd) { // failed factor: P stays as it was, no correction
+    if (a0 == b0 && tid < EK_T && a0 + tid < N)
+      dx[a0 + tid] = 0.0;
+    return;
+  }
+  const int pk = r | 1;
+  double *As = d1, *Bs = d1 + (size_t)32 * pk, *ws = Bs + (size_t)32 * pk;
+  for (int i = ty; i < 32; i += 8)
+    for (int k = tx; k < r; k += 32) {
+      As[i * pk + k] = (a0 + i < N) ? Yin[(size_t)(a0 + i) * ldY + k] : 0.0;
+      Bs[i * pk + k] = (b0 + i < N) ? Yin[(size_t)(b0 + i) * ldY + k] : 0.0;
+    }
+  for (int k = tid; k < r; k += 256)
+    ws[k] = w[k];
+  __syncthreads();
+  double acc[4] = {0, 0, 0, 0};
+  for (int k = 0; k < r; k++) {
+    const double bv = Bs[tx * pk + k];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      acc[u] += As[(ty + 8 * u) * pk + k] * bv;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const int a = a0 + ty + 8 * u, b = b0 + tx;
+    if (a < N && b < N && b >= a) {
+      const double v = P[(size_t)a * ldP + b] - acc[u];
+      P[(size_t)a * ldP + b] = v;
+      P[(size_t)b * ldP + a] = v;
+      if (a == b && v < 0.0)
+        atomicMin(&info->neg_diag_index, a);
+      if (!isfinite(v))
+        info->nonfinite = 1;
+    }
+  }
+  if (a0 == b0 && tid < EK_T && a0 + tid < N) {
+    double s0 = 0.0, s1 = 0.0;
+    int k = 0;
+    for (; k + 1 < r; k += 2) {
+      s0 += As[tid * pk + k] * ws[k];
+      s1 += As[tid * pk + k + 1] * ws[k + 1];
+    }
+    if (k < r)
+      s0 += As[tid * pk + k] * ws[k];
+    dx[a0 + tid] = s0 + s1;
+  }
+}
+
 __global__ void k_ekf_prep(DevUpdateInfo *info) {
   OVB_PDL_ENTER();
   info->neg_diag_index = 0x7fffffff;
@@ -262,29 +391,52 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
   ovb_launch(ctx, k_ekf_prep, dim3(1), dim3(1), (size_t)(0), ctx->d_info);
   if (r <= 0 || n <= 0)
     return;
-  dim3 g0((N + EK_T - 1) / EK_T, (r + EK_T - 1) / EK_T);
-  ovb_launch(ctx, k_ekf_gemm, dim3(g0), dim3(256), (size_t)(0), 0, P, ld, H, ldHm, nullptr, 0, ctx->d_info, N, r, n, ctx->d_M, ld, 0.0, nullptr);
-  dim3 g1((r + EK_T - 1) / EK_T, (r + EK_T - 1) / EK_T);
-  ovb_launch(ctx, k_ekf_gemm, dim3(g1), dim3(256), (size_t)(0), 1, P, ld, H, ldHm, ctx->d_M, ld, ctx->d_info, r, r, n, ctx->d_S, ld, sigma2, Rdiag_dev);
-  size_t chol_bytes = sizeof(double) * (size_t)(r + 1) * (size_t)(r | 1);
-  int use_smem = chol_bytes <= 200 * 1024;
   if (!ctx->attr_done[2]) { // function attributes are per device: one flag per context
     cudaFuncSetAttribute(k_ekf_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_ekf_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_ekf_gemm1, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_ekf_downdate1, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     ctx->attr_done[2] = 1;
   }
+  // small inner dimensions (config 2: n = r = 154): one-shot staged products, DMMA Cholesky + register solve of k_cholqr.cu
+  const bool one_shot = ctx->ekf_chol_dmma && n <= EK1_KMAX && r <= EK1_KMAX;
+  dim3 g0((N + EK_T - 1) / EK_T, (r + EK_T - 1) / EK_T);
+  dim3 g1((r + EK_T - 1) / EK_T, (r + EK_T - 1) / EK_T);
+  if (one_shot) {
+    const size_t sm01 = sizeof(double) * ((size_t)n * 33 + (size_t)32 * (n | 1));
+    ovb_launch(ctx, k_ekf_gemm1, dim3(g0), dim3(256), sm01, 0, P, ld, H, ldHm, nullptr, 0, ctx->d_info, N, r, n, ctx->d_M, ld, 0.0, nullptr);
+    ovb_launch(ctx, k_ekf_gemm1, dim3(g1), dim3(256), sm01, 1, P, ld, H, ldHm, ctx->d_M, ld, ctx->d_info, r, r, n, ctx->d_S, ld, sigma2, Rdiag_dev);
+  } else {
+    ovb_launch(ctx, k_ekf_gemm, dim3(g0), dim3(256), (size_t)(0), 0, P, ld, H, ldHm, nullptr, 0, ctx->d_info, N, r, n, ctx->d_M, ld, 0.0, nullptr);
+    ovb_launch(ctx, k_ekf_gemm, dim3(g1), dim3(256), (size_t)(0), 1, P, ld, H, ldHm, ctx->d_M, ld, ctx->d_info, r, r, n, ctx->d_S, ld, sigma2, Rdiag_dev);
+  }
+  size_t chol_bytes = sizeof(double) * (size_t)(r + 1) * (size_t)(r | 1);
+  int use_smem = chol_bytes <= 200 * 1024;
   // the residual vector is column n of H's row (TSQR output) or a separate buffer: callers stage it in d_w
   double *invdiag = ctx->d_w + ctx->cfg.max_state; // d_w holds 4 x max_state doubles: [w | 1/diag(L) | ...]
-  ovb_launch(ctx, k_ekf_chol, dim3(1), dim3(EKC_THREADS), (size_t)(use_smem ? chol_bytes : 0), ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
+  double *Lpk = nullptr; // packed factor for the register solve (only written by the DMMA Cholesky)
+  const bool dmma_chol = ctx->ekf_chol_dmma && launch_chol_ekf_dmma(ctx, ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, &Lpk);
+  if (!dmma_chol)
+    ovb_launch(ctx, k_ekf_chol, dim3(1), dim3(EKC_THREADS), (size_t)(use_smem ? chol_bytes : 0), ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
   if (gate_only)
     return;
-  size_t trsm_small = sizeof(double) * ((size_t)TR_ROWS * r + r);
-  size_t trsm_full = trsm_small + sizeof(double) * (size_t)r * (size_t)(r | 1);
-  int L_in_smem = trsm_full <= 200 * 1024;
-  ovb_launch(ctx, k_ekf_trsm, dim3((N + TR_ROWS - 1) / TR_ROWS), dim3(32 * TR_ROWS), (size_t)(L_in_smem ? trsm_full : trsm_small), ctx->d_M, ld, ctx->d_S, ld, invdiag, N,
-                                                                                                              r, ctx->d_Y, ld, L_in_smem);
+  const double *Yd = ctx->d_Y;
+  if (dmma_chol && Lpk != nullptr && launch_trsm_rows(ctx, ctx->d_M, ld, N, r, Lpk)) {
+    Yd = ctx->d_M; // Y = M L^-T in place
+  } else {
+    size_t trsm_small = sizeof(double) * ((size_t)TR_ROWS * r + r);
+    size_t trsm_full = trsm_small + sizeof(double) * (size_t)r * (size_t)(r | 1);
+    int L_in_smem = trsm_full <= 200 * 1024;
+    ovb_launch(ctx, k_ekf_trsm, dim3((N + TR_ROWS - 1) / TR_ROWS), dim3(32 * TR_ROWS), (size_t)(L_in_smem ? trsm_full : trsm_small), ctx->d_M, ld, ctx->d_S, ld, invdiag, N,
+               r, ctx->d_Y, ld, L_in_smem, ctx->d_info);
+  }
   dim3 g2((N + EK_T - 1) / EK_T, (N + EK_T - 1) / EK_T);
-  ovb_launch(ctx, k_ekf_downdate, dim3(g2), dim3(256), (size_t)(0), P, ld, ctx->d_Y, ld, N, r, ctx->d_w, ctx->d_dx, ctx->d_info);
+  if (one_shot) {
+    const size_t smd = sizeof(double) * ((size_t)64 * (r | 1) + r);
+    ovb_launch(ctx, k_ekf_downdate1, dim3(g2), dim3(256), smd, P, ld, Yd, ld, N, r, ctx->d_w, ctx->d_dx, ctx->d_info);
+  } else {
+    ovb_launch(ctx, k_ekf_downdate, dim3(g2), dim3(256), (size_t)(0), P, ld, Yd, ld, N, r, ctx->d_w, ctx->d_dx, ctx->d_info);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

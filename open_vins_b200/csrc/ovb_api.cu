@@ -98,6 +98,8 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
     ctx->tsqr_pdl = e2 ? atoi(e2) : 1;
     const char *e3 = getenv("OVB_FEAT_CLASSES");
     ctx->feat_classes = e3 ? atoi(e3) : 1;
+    const char *e4 = getenv("OVB_EKF_CHOL_DMMA");
+    ctx->ekf_chol_dmma = e4 ? atoi(e4) : 1;
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = 1;
@@ -705,6 +707,17 @@ __global__ void k_fill_zero_dx(double *dx, int N) {
     dx[i] = 0.0;
 }
 
+// measurement_compress_inplace in the requested mode; returns the number of rows of [R | z] handed to the EKF update.
+// The Cholesky-based modes always produce n rows; the Householder path leaves min(m, n).
+static int compress_system(ovb_ctx *ctx, int mode, double *A, int m, int n, int ldA, double *Rout, int ldR) {
+  if (mode == OVB_COMPRESS_CHOLQR2 && launch_compress_cholqr2(ctx, A, m, n, ldA, Rout, ldR) >= 0)
+    return n;
+  if (mode == OVB_COMPRESS_NORMAL_EQUATIONS && launch_compress_gram(ctx, A, m, n, ldA, Rout, ldR) >= 0)
+    return n;
+  launch_tsqr(ctx, A, m, n, ldA, Rout, ldR);
+  return std::min(m, n);
+}
+
 // The device pipeline of one update on inputs already in the arena: steps 2-6 of UpdaterMSCKF::update.
 // ev (optional): ev[1] after triangulation, ev[2] after the per-feature systems, ev[3] after the column map, ev[4] after
 // compression, ev[5] after the EKF update. Returns the row count handed to the EKF update.
@@ -740,11 +753,9 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
     cudaEventRecord(ev[3], ctx->stream);
   const int ldR = ldH;
   const double *Rfinal = ctx->d_R;
+  int r = 0;
   if (m_total > 0) {
-    if (ctx->h_opts->o.compress == OVB_COMPRESS_NORMAL_EQUATIONS)
-      launch_compress_gram(ctx, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
-    else
-      launch_tsqr(ctx, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
+    r = compress_system(ctx, ctx->h_opts->o.compress, ctx->d_Hs, m_total, n_all, ldH, ctx->d_R, ldR);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     if (col_order == OVB_COLS_REFERENCE_FIRST_SEEN) {
       launch_reorder_R(ctx, ctx->d_R, n_all, ldR, ctx->d_R2, ldR);
@@ -755,8 +766,6 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
   if (ev)
     cudaEventRecord(ev[4], ctx->stream);
-  // the Householder path leaves min(m, n) non-zero rows; the Cholesky factor of the Gram matrix is always n x n
-  const int r = (ctx->h_opts->o.compress == OVB_COMPRESS_NORMAL_EQUATIONS && m_total > 0) ? n_all : std::min(m_total, n_all);
   if (r > 0) {
     ovb_launch(ctx, k_take_z, dim3((r + 127) / 128), dim3(128), (size_t)(0), Rfinal, ldR, r, n_all, ctx->d_w);
     launch_ekf_update(ctx, Rfinal, ldR, r, n_all, false, slam ? 1.0 : ctx->h_opts->sigma_pix_sq, nullptr);
@@ -1043,7 +1052,7 @@ ovb_status ovb_msckf_shard_compress(ovb_ctx *ctx, const ovb_frame *frame, const 
   launch_column_map(ctx, pk.n_feats, pk.bv);
   ctx->n_launch += 3; // cam poses, triangulate, column map (+ the per-feature kernel's own count)
   if (pk.m_total > 0)
-    launch_tsqr(ctx, ctx->d_Hs, pk.m_total, pk.n_all, pk.ldH, R_dev, pk.ldH);
+    compress_system(ctx, o2.compress, ctx->d_Hs, pk.m_total, pk.n_all, pk.ldH, R_dev, pk.ldH); // unused rows of the block read as zero
   else
     OVB_CUDA_CHECK(ctx, cudaMemsetAsync(R_dev, 0, sizeof(double) * (size_t)pk.n_all * pk.ldH, ctx->stream));
   cudaEventRecord(ctx->ev[4], ctx->stream);
@@ -1058,7 +1067,7 @@ ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_block
   const int N = ctx->N, n_all = ctx->last_n_all, ld = ctx->last_ldH, F = ctx->last_n_feats;
   const double *Rfinal = stacked_dev;
   if (n_blocks > 1) {
-    launch_tsqr(ctx, stacked_dev, n_blocks * n_all, n_all, ld, ctx->d_R, ld);
+    compress_system(ctx, ctx->h_opts->o.compress, stacked_dev, n_blocks * n_all, n_all, ld, ctx->d_R, ld);
     Rfinal = ctx->d_R;
   }
   ovb_launch(ctx, k_take_z, dim3((n_all + 127) / 128), dim3(128), (size_t)(0), Rfinal, ld, n_all, n_all, ctx->d_w);
@@ -1186,6 +1195,32 @@ ovb_status ovb_compress_gram(ovb_ctx *ctx, const double *H, int m, int n, const 
     return st;
   if (launch_compress_gram(ctx, ctx->d_Hs, m, n, ld, ctx->d_R, ld) < 0)
     return OVB_ERR_CUDA;
+  OVB_CUDA_CHECK(ctx, cudaGetLastError());
+  double *hs = ctx->h_stage;
+  OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(hs, ctx->d_R, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToHost, ctx->stream));
+  OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < n; j++)
+      R_out[(size_t)i * n + j] = hs[(size_t)i * ld + j];
+    z_out[i] = hs[(size_t)i * ld + n];
+  }
+  return OVB_OK;
+}
+
+ovb_status ovb_compress_cholqr2(ovb_ctx *ctx, const double *H, int m, int n, const double *res, double *R_out, double *z_out) {
+  if (!ctx || !H || !res || !R_out || !z_out || m < 1 || n < 1)
+    return OVB_ERR_ARG;
+  if (n > ctx->cfg.max_state)
+    return OVB_ERR_CAPACITY;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  int ld;
+  ovb_status st = stage_dense(ctx, H, m, n, res, nullptr, &ld);
+  if (st != OVB_OK)
+    return st;
+  if (launch_compress_cholqr2(ctx, ctx->d_Hs, m, n, ld, ctx->d_R, ld) < 0) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_compress_cholqr2: %d columns exceed what this path takes", n);
+    return OVB_ERR_CAPACITY;
+  }
   OVB_CUDA_CHECK(ctx, cudaGetLastError());
   double *hs = ctx->h_stage;
   OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(hs, ctx->d_R, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToHost, ctx->stream));

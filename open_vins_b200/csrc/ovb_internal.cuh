@@ -140,9 +140,10 @@ struct ovb_ctx {
   int max_rows;
   int sm_count;
   size_t info_bytes; // DevUpdateInfo rounded up: d_dx / h_dx start right behind d_info / h_info
-  int attr_done[4]; // per-context (= per-device) one-time cudaFuncSetAttribute flags: 0 tsqr, 1 feature, 2 ekf, 3 gram
+  int attr_done[8]; // per-context (= per-device) one-time cudaFuncSetAttribute flags: 0 tsqr, 1 feature, 2 ekf, 3 gram, 4 cholqr
   int tsqr_pdl;     // programmatic dependent launch between the TSQR level kernels (OVB_TSQR_PDL=0 disables: A/B timing only)
   int tsqr_cluster; // upper TSQR levels as one thread-block cluster (OVB_TSQR_CLUSTER=0 disables: A/B timing only)
+  int ekf_chol_dmma; // EKF Cholesky on the DMMA kernel of k_cholqr.cu (OVB_EKF_CHOL_DMMA=0 disables: A/B timing only)
   float stage_ms[6];
   // replay of the last update on device-resident inputs (bench: `value` leg; see ovb_msckf_replay)
   int replay_enabled, last_pk_valid;
@@ -179,6 +180,13 @@ void launch_tsqr(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, i
 // gather columns of Rin in the order info->col_canon (n_used of them) into Hs scratch and re-triangularise into Rout
 // [R | z] <- chol([H r]'[H r]) (k_gram.cu); returns the number of kernels launched or -1
 int launch_compress_gram(ovb_ctx *ctx, const double *A, int m, int n, int ldA, double *Rout, int ldR);
+// [R | z] <- shifted CholeskyQR2 of A (k_cholqr.cu; A is overwritten); returns kernels launched, or -1 when n+1 exceeds
+// what the single-CTA Cholesky takes (callers then use launch_tsqr)
+int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR);
+// EKF Cholesky on the DMMA kernel of k_cholqr.cu; false when r does not fit (caller uses k_ekf_chol)
+bool launch_chol_ekf_dmma(ovb_ctx *ctx, double *S, int ldS, int r, const double *res, double *w, double *invdiag, double **Lpk_out);
+// A <- A (L')^-1 for the rows of A [m x nt] with the packed factor of the DMMA Cholesky; false when it does not fit
+bool launch_trsm_rows(ovb_ctx *ctx, double *A, int ldA, int m, int nt, const double *Lpk);
 void launch_reorder_R(ovb_ctx *ctx, const double *Rin, int n_all, int ldRin, double *Rout, int ldRout);
 // EKF update from an upper-trapezoidal / dense H [r x n] with column->state map in d_info (device-side sizes)
 void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r_max, int n_max, bool sizes_from_info, double sigma2,
