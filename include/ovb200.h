@@ -317,7 +317,12 @@ ovb_status ovb_last_stage_ms(const ovb_ctx *ctx, float ms[6]);
  *                           buffer R_dev. Asynchronous on the context stream. Column order is canonical.
  *  ovb_msckf_shard_finish   stacked_dev = the n_blocks all-gathered blocks, stacked by rank (DEVICE pointer, overwritten):
  *                           compress the stack, EKFUpdate on this rank's P, return dx and the shard's per-feature results. */
-ovb_status ovb_set_stream(ovb_ctx *ctx, void *cuda_stream);
+ovb_status ovb_set_stream(ovb_ctx *ctx, void *cuda_stream); /* cuda_stream must be an explicit stream (not the default stream 0) */
+/* Contiguous feature ranges with (nearly) equal stacked-row counts: rank r works on features [bounds[r], bounds[r+1]). */
+ovb_status ovb_shard_partition(const int32_t *meas_off, int n_feats, int world, int32_t *bounds /* [world+1] */);
+/* ovb_msckf_shard_compress on features [f0, f1) of a full batch (no host-side copy of the subset by the caller). */
+ovb_status ovb_msckf_shard_compress_range(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, int f0, int f1,
+                                          const ovb_opts *opts, double *R_dev, int R_cap_doubles, int *n_cols, int *ld);
 ovb_status ovb_msckf_shard_compress(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, double *R_dev,
                                     int R_cap_doubles, int *n_cols, int *ld);
 ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_blocks, ovb_feat_out *out, double *dx, ovb_stats *stats);

@@ -269,6 +269,11 @@ struct StateHelper {
       if (cam.intrinsics_id > marg.first)
         cam.intrinsics_id -= marg.second;
     }
+    // every variable behind the removed block moves up (StateHelper.cpp:318-326): SLAM landmarks are appended at the end of
+    // the covariance by initialize(), i.e. always behind the oldest clone
+    for (auto &lm : state._features_SLAM)
+      if (lm.second->id > marg.first)
+        lm.second->id -= marg.second;
   }
 };
 

@@ -275,6 +275,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ovb_set_stream.argtypes = [vp, C.c_void_p]
     lib.ovb_msckf_shard_compress.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts), C.c_void_p,
                                              C.c_int, c_int_p, c_int_p]
+    lib.ovb_msckf_shard_compress_range.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.c_int, C.c_int, C.POINTER(ovb_opts),
+                                                   C.c_void_p, C.c_int, c_int_p, c_int_p]
+    lib.ovb_shard_partition.argtypes = [c_int_p, C.c_int, C.c_int, c_int_p]
     lib.ovb_msckf_shard_finish.argtypes = [vp, C.c_void_p, C.c_int, C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
     lib.ovb_set_replay.argtypes = [vp, C.c_int]
     lib.ovb_msckf_replay.argtypes = [vp, C.c_int, C.c_int, c_float_p, C.POINTER(C.c_float * 5)]
@@ -288,7 +291,7 @@ EXPORTED_SYMBOLS = [
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate", "ovb_cov_initialize",
     "ovb_msckf_update", "ovb_slam_update", "ovb_slam_anchor_change", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram", "ovb_compress_cholqr2",
     "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
-    "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_finish",
+    "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_compress_range", "ovb_shard_partition", "ovb_msckf_shard_finish",
 ]
 
 
@@ -310,6 +313,17 @@ def slam_anchor_change(frame: "FrameArrays", opts: ovb_opts, lm_off, value, valu
     no, nc = int(n_order[0]), int(n_cols[0])
     phisize = int(sz[no - 1])
     return nv, nvf, off[:no].copy(), sz[:no].copy(), Phi[:phisize * nc].reshape(phisize, nc).copy()
+
+
+def shard_partition(meas_off, world: int, lib=None):
+    """ovb_shard_partition: [(f0, f1)] * world, contiguous feature ranges balanced by stacked rows."""
+    lib = lib or load_library()
+    mo = np.ascontiguousarray(meas_off, dtype=np.int32)
+    bounds = np.zeros(world + 1, dtype=np.int32)
+    st = lib.ovb_shard_partition(_ptr(mo, c_int_p), len(mo) - 1, int(world), _ptr(bounds, c_int_p))
+    if st != OVB_OK:
+        raise OvbError(st, "ovb_shard_partition")
+    return [(int(bounds[i]), int(bounds[i + 1])) for i in range(world)]
 
 
 class OvbError(RuntimeError):
@@ -483,6 +497,13 @@ class Engine:
         self._check(self.lib.ovb_msckf_shard_compress(self.h, C.byref(fs), C.byref(bs), C.byref(opts), C.c_void_p(R_dev_ptr),
                                                       int(R_cap_doubles), _ptr(n, c_int_p), _ptr(ld, c_int_p)))
         return int(n[0]), int(ld[0])
+
+    def shard_compress_range(self, frame: FrameArrays, feats: FeatArrays, f0: int, f1: int, opts: ovb_opts, R_dev_ptr: int, R_cap_doubles: int):
+        n = C.c_int(0)
+        ld = C.c_int(0)
+        self._check(self.lib.ovb_msckf_shard_compress_range(self.h, C.byref(frame.struct()), C.byref(feats.struct()), int(f0), int(f1), C.byref(opts),
+                                                            C.c_void_p(R_dev_ptr), int(R_cap_doubles), C.byref(n), C.byref(ld)))
+        return n.value, ld.value
 
     def shard_finish(self, stacked_dev_ptr: int, n_blocks: int, n_feats: int):
         out = FeatOut(n_feats)

@@ -250,6 +250,8 @@ struct CqCholSmem {
   double Xp[2][CQ_MAXRB * 8 * CQ_XP];
   double invd[CQ_MAXRB * 8];
   double red[32];
+  double dummyT[64];        // target of the masked-out tile of a pair (operands zero: it stays zero)
+  double dummyX[2 * CQ_XP]; // zero operand rows for it
   int flag;
 };
 
@@ -385,11 +387,13 @@ struct CqTileOps {
   double2 c;
   double2 *cp;
 };
-__device__ __forceinline__ void cq_tile_load(CqTileOps &o, double *T, const double *Xp, int bi, int bj, int lane) {
+// valid == false: the pair's second slot is empty; it is pointed at a dummy tile with zero operands so that both DMMAs of
+// the pair execute unconditionally (a branch around mma.sync costs convergence code on every use)
+__device__ __forceinline__ void cq_tile_load(CqTileOps &o, CqCholSmem &sm, const double *Xp, int bi, int bj, int lane, bool valid) {
   const int g = lane >> 2, q = lane & 3;
-  const double *xa = Xp + (size_t)(8 * bi + g) * CQ_XP + q;
-  const double *xb = Xp + (size_t)(8 * bj + g) * CQ_XP + q;
-  o.cp = reinterpret_cast<double2 *>(T + (size_t)(tri(bi) + bj) * 64 + 2 * lane);
+  const double *xa = valid ? Xp + (size_t)(8 * bi + g) * CQ_XP + q : sm.dummyX + q;
+  const double *xb = valid ? Xp + (size_t)(8 * bj + g) * CQ_XP + q : sm.dummyX + q;
+  o.cp = reinterpret_cast<double2 *>((valid ? sm.T + (size_t)(tri(bi) + bj) * 64 : sm.dummyT) + 2 * lane);
   o.a0 = -xa[0];
   o.a1 = -xa[4];
   o.b0 = xb[0];
@@ -436,13 +440,10 @@ __device__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, bool strict, dou
       // block column k+1 (warp 0 takes the diagonal tile first), two tiles in flight
       for (int bi = k1 + widA; bi < NRB; bi += 2 * NA) {
         CqTileOps o0, o1;
-        cq_tile_load(o0, sm.T, Xk, bi, k1, lane);
-        const bool two = bi + NA < NRB;
-        if (two)
-          cq_tile_load(o1, sm.T, Xk, bi + NA, k1, lane);
+        cq_tile_load(o0, sm, Xk, bi, k1, lane, true);
+        cq_tile_load(o1, sm, Xk, bi + NA, k1, lane, bi + NA < NRB);
         cq_tile_mma_store(o0);
-        if (two)
-          cq_tile_mma_store(o1);
+        cq_tile_mma_store(o1);
       }
       CQ_PROBE_T(p1);
       bar_group(1, NA * 32);
@@ -479,15 +480,10 @@ __device__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, bool strict, dou
           r++;
         }
         CqTileOps o0, o1;
-        const bool v0 = bj0 < NB, v1 = two && bj1 < NB;
-        if (v0)
-          cq_tile_load(o0, sm.T, Xk, bi0, bj0, lane);
-        if (v1)
-          cq_tile_load(o1, sm.T, Xk, bi1, bj1, lane);
-        if (v0)
-          cq_tile_mma_store(o0);
-        if (v1)
-          cq_tile_mma_store(o1);
+        cq_tile_load(o0, sm, Xk, bi0, bj0, lane, bj0 < NB);
+        cq_tile_load(o1, sm, Xk, bi1, bj1, lane, two && bj1 < NB);
+        cq_tile_mma_store(o0);
+        cq_tile_mma_store(o1);
       }
       CQ_PROBE_T(p1);
     }
@@ -525,6 +521,10 @@ __device__ void cq_load_tiles(CqCholSmem &sm, const double *__restrict__ G, size
   cpa_commit();
   for (int e = tid; e < 2 * CQ_MAXRB * 8 * CQ_XP; e += CQ_CHOL_T)
     (&sm.Xp[0][0])[e] = 0.0;
+  if (tid < 64)
+    sm.dummyT[tid] = 0.0;
+  if (tid < 2 * CQ_XP)
+    sm.dummyX[tid] = 0.0;
   if (tid == 0)
     sm.flag = 0;
   cpa_wait<0>();
@@ -627,58 +627,56 @@ __global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_ekf(double *__restrict__ 
 //            which starts with the plain product  A[:, half 2] -= X[:, half 1] R[half 1, half 2].
 // L sits in shared memory in the Cholesky kernel's tile layout: tile (j, jb) read at g*8 + 4ks + q is exactly the
 // B-operand fragment of R[8jb.., 8j..] (conflict free).
-#define CQ_TRSM_NH 10 // column blocks per half
+#define CQ_TRSM_NH 10 // column blocks per half (at most)
 #define CQ_TRSM_SMEM (sizeof(double) * ((size_t)CQ_PK_DOUBLES + (size_t)(CQ_TRSM_T / 32) * CQ_TRSM_NH * 2 * 32))
+// All control flow around the DMMAs is compile-time (NH blocks, padded with zero tiles): a run-time bound inside the
+// unrolled loops makes the compiler guard every mma.sync / shfl.sync with convergence code and several code versions.
 template <int NH>
-__device__ __forceinline__ void cq_trsm_half(double (&acc)[NH][2], int b0, int nb, const double *Lt, const double *Ri, double *xs, int lane) {
+__device__ __forceinline__ void cq_trsm_half(double (&acc)[NH][2], int b0, const double *Lt, const double *Ri, double *xs, int lane) {
   const int g = lane >> 2, q = lane & 3;
 #pragma unroll
   for (int jb = 0; jb < NH; jb++) {
-    if (jb < nb) {
-      const int B = b0 + jb;
-      const double *Ld = Lt + (size_t)(tri(B) + B) * 64; // R[8B+t][8B+c] = Ld[c*8 + t], t <= c
-      const double *ri = Ri + B * 8;
-      double x[8];
+    const int B = b0 + jb;
+    const double *Ld = Lt + (size_t)(tri(B) + B) * 64; // R[8B+t][8B+c] = Ld[c*8 + t], t <= c
+    const double *ri = Ri + B * 8;
+    double x[8];
 #pragma unroll
-      for (int qq = 0; qq < 4; qq++) {
-        x[2 * qq] = __shfl_sync(0xffffffffu, acc[jb][0], (lane & ~3) | qq);
-        x[2 * qq + 1] = __shfl_sync(0xffffffffu, acc[jb][1], (lane & ~3) | qq);
-      }
+    for (int qq = 0; qq < 4; qq++) {
+      x[2 * qq] = __shfl_sync(0xffffffffu, acc[jb][0], (lane & ~3) | qq);
+      x[2 * qq + 1] = __shfl_sync(0xffffffffu, acc[jb][1], (lane & ~3) | qq);
+    }
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
-        x[c] *= ri[c];
+    for (int c = 0; c < 8; c++) {
+      x[c] *= ri[c];
 #pragma unroll
-        for (int c2 = c + 1; c2 < 8; c2++)
-          x[c2] -= x[c] * Ld[c2 * 8 + c];
-      }
-      acc[jb][0] = (q == 0) ? x[0] : (q == 1) ? x[2] : (q == 2) ? x[4] : x[6];
-      acc[jb][1] = (q == 0) ? x[1] : (q == 1) ? x[3] : (q == 2) ? x[5] : x[7];
-      // A-operand fragments of the two k-steps: element (row g, column 4ks + q), negated
-      const double af0 = -((q == 0) ? x[0] : (q == 1) ? x[1] : (q == 2) ? x[2] : x[3]);
-      const double af1 = -((q == 0) ? x[4] : (q == 1) ? x[5] : (q == 2) ? x[6] : x[7]);
-      if (xs != nullptr) {
-        xs[(2 * jb) * 32 + lane] = af0;
-        xs[(2 * jb + 1) * 32 + lane] = af1;
-      }
+      for (int c2 = c + 1; c2 < 8; c2++)
+        x[c2] -= x[c] * Ld[c2 * 8 + c];
+    }
+    acc[jb][0] = (q == 0) ? x[0] : (q == 1) ? x[2] : (q == 2) ? x[4] : x[6];
+    acc[jb][1] = (q == 0) ? x[1] : (q == 1) ? x[3] : (q == 2) ? x[5] : x[7];
+    // A-operand fragments of the two k-steps: element (row g, column 4ks + q), negated
+    const double af0 = -((q == 0) ? x[0] : (q == 1) ? x[1] : (q == 2) ? x[2] : x[3]);
+    const double af1 = -((q == 0) ? x[4] : (q == 1) ? x[5] : (q == 2) ? x[6] : x[7]);
+    if (xs != nullptr) {
+      xs[(2 * jb) * 32 + lane] = af0;
+      xs[(2 * jb + 1) * 32 + lane] = af1;
+    }
 #pragma unroll
-      for (int j = 0; j < NH; j++) {
-        if (j > jb && j < nb) {
-          const double *lf = Lt + (size_t)(tri(b0 + j) + B) * 64 + g * 8 + q;
-          dmma(acc[j][0], acc[j][1], af0, lf[0]);
-          dmma(acc[j][0], acc[j][1], af1, lf[4]);
-        }
-      }
+    for (int j = jb + 1; j < NH; j++) {
+      const double *lf = Lt + (size_t)(tri(b0 + j) + B) * 64 + g * 8 + q;
+      dmma(acc[j][0], acc[j][1], af0, lf[0]);
+      dmma(acc[j][0], acc[j][1], af1, lf[4]);
     }
   }
 }
 
 template <int NH>
-__device__ __forceinline__ void cq_trsm_load(double (&acc)[NH][2], const double *arow, bool row_ok, int b0, int nb, int nt, int q) {
+__device__ __forceinline__ void cq_trsm_load(double (&acc)[NH][2], const double *arow, bool row_ok, int b0, int nt, int q) {
 #pragma unroll
   for (int jb = 0; jb < NH; jb++) {
     const int col = 8 * (b0 + jb) + 2 * q;
     acc[jb][0] = acc[jb][1] = 0.0;
-    if (jb < nb && row_ok) {
+    if (row_ok) {
       if (col + 1 < nt) {
         const double2 v = *reinterpret_cast<const double2 *>(arow + col);
         acc[jb][0] = v.x;
@@ -690,69 +688,105 @@ __device__ __forceinline__ void cq_trsm_load(double (&acc)[NH][2], const double 
   }
 }
 template <int NH>
-__device__ __forceinline__ void cq_trsm_store(const double (&acc)[NH][2], double *arow, bool row_ok, int b0, int nb, int nt, int q) {
+__device__ __forceinline__ void cq_trsm_store(const double (&acc)[NH][2], double *arow, bool row_ok, int b0, int nt, int q) {
   if (!row_ok)
     return;
 #pragma unroll
   for (int jb = 0; jb < NH; jb++) {
     const int col = 8 * (b0 + jb) + 2 * q;
-    if (jb < nb) {
-      if (col + 1 < nt)
-        *reinterpret_cast<double2 *>(arow + col) = make_double2(acc[jb][0], acc[jb][1]);
-      else if (col < nt)
-        arow[col] = acc[jb][0];
-    }
+    if (col + 1 < nt)
+      *reinterpret_cast<double2 *>(arow + col) = make_double2(acc[jb][0], acc[jb][1]);
+    else if (col < nt)
+      arow[col] = acc[jb][0];
   }
 }
 
+// NH1 + NH2 >= ceil(nt / 8); NH2 == 0: single half
+template <int NH1, int NH2>
 __global__ void __launch_bounds__(CQ_TRSM_T) k_cq_trsm(double *__restrict__ A, int ldA, int m, int nt, const double *__restrict__ Lpk) {
   OVB_PDL_ENTER();
-  constexpr int NH = CQ_TRSM_NH;
   extern __shared__ __align__(16) double tsm[];
   double *Lt = tsm;
   double *Ri = tsm + CQ_PK_INV;
-  double *Xs = tsm + CQ_PK_DOUBLES; // per warp: first-half A-operand fragments [NH][2][32]
+  double *Xs = tsm + CQ_PK_DOUBLES; // per warp: first-half A-operand fragments [NH1][2][32]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
   const int NB = (nt + 7) >> 3;
-  const int nb1 = min(NB, NH), nb2 = NB - nb1;
+  constexpr int NBP = NH1 + NH2; // padded block count: tiles past NB are zero, their reciprocal pivots 1
   for (int e = 2 * tid; e < tri(NB) * 64; e += 2 * CQ_TRSM_T)
     cpa16(s_u32(Lt + e), Lpk + e, 16u);
   for (int e = 2 * tid; e < NB * 8; e += 2 * CQ_TRSM_T)
     cpa16(s_u32(Ri + e), Lpk + CQ_PK_INV + e, 16u);
   cpa_commit();
+  for (int e = tri(NB) * 64 + tid; e < tri(NBP) * 64; e += CQ_TRSM_T)
+    Lt[e] = 0.0;
+  for (int e = NB * 8 + tid; e < NBP * 8; e += CQ_TRSM_T)
+    Ri[e] = 1.0;
   cpa_wait<0>();
   __syncthreads();
-  double *xs = Xs + (size_t)wid * (NH * 2 * 32);
+  double *xs = Xs + (size_t)wid * (CQ_TRSM_NH * 2 * 32);
   const int ngroups = (m + 7) >> 3;
   for (int rg = blockIdx.x * (CQ_TRSM_T / 32) + wid; rg < ngroups; rg += gridDim.x * (CQ_TRSM_T / 32)) {
     const int row = 8 * rg + g;
     const bool row_ok = row < m;
     double *arow = A + (size_t)row * ldA;
-    double acc[NH][2];
-    cq_trsm_load<NH>(acc, arow, row_ok, 0, nb1, nt, q);
-    cq_trsm_half<NH>(acc, 0, nb1, Lt, Ri, nb2 > 0 ? xs : nullptr, lane);
-    cq_trsm_store<NH>(acc, arow, row_ok, 0, nb1, nt, q);
-    if (nb2 > 0) {
-      cq_trsm_load<NH>(acc, arow, row_ok, nb1, nb2, nt, q);
+#ifdef CQ_PROBE
+    long long t0 = clock64(), t1, t2, t3 = 0, t4 = 0;
+#endif
+    {
+      double acc[NH1][2];
+      cq_trsm_load<NH1>(acc, arow, row_ok, 0, nt, q);
+#ifdef CQ_PROBE
+      t1 = clock64();
+#endif
+      cq_trsm_half<NH1>(acc, 0, Lt, Ri, NH2 > 0 ? xs : nullptr, lane);
+#ifdef CQ_PROBE
+      t2 = clock64();
+#endif
+      cq_trsm_store<NH1>(acc, arow, row_ok, 0, nt, q);
+    }
+    if constexpr (NH2 > 0) {
+      double acc[NH2][2];
+      cq_trsm_load<NH2>(acc, arow, row_ok, NH1, nt, q);
       __syncwarp();
       // A[:, half 2] -= X[:, half 1] R[half 1, half 2]
 #pragma unroll 2
-      for (int jb = 0; jb < nb1; jb++) {
+      for (int jb = 0; jb < NH1; jb++) {
         const double af0 = xs[(2 * jb) * 32 + lane], af1 = xs[(2 * jb + 1) * 32 + lane];
 #pragma unroll
-        for (int j = 0; j < NH; j++) {
-          if (j < nb2) {
-            const double *lf = Lt + (size_t)(tri(nb1 + j) + jb) * 64 + g * 8 + q;
-            dmma(acc[j][0], acc[j][1], af0, lf[0]);
-            dmma(acc[j][0], acc[j][1], af1, lf[4]);
-          }
+        for (int j = 0; j < NH2; j++) {
+          const double *lf = Lt + (size_t)(tri(NH1 + j) + jb) * 64 + g * 8 + q;
+          dmma(acc[j][0], acc[j][1], af0, lf[0]);
+          dmma(acc[j][0], acc[j][1], af1, lf[4]);
         }
       }
-      cq_trsm_half<NH>(acc, nb1, nb2, Lt, Ri, nullptr, lane);
-      cq_trsm_store<NH>(acc, arow, row_ok, nb1, nb2, nt, q);
+#ifdef CQ_PROBE
+      t3 = clock64();
+#endif
+      cq_trsm_half<NH2>(acc, NH1, Lt, Ri, nullptr, lane);
+#ifdef CQ_PROBE
+      t4 = clock64();
+#endif
+      cq_trsm_store<NH2>(acc, arow, row_ok, NH1, nt, q);
       __syncwarp();
     }
+#ifdef CQ_PROBE
+    if (blockIdx.x == 0 && (tid == 0 || tid == 32 * 7) && rg < 40)
+      printf("trsm rg=%d tid=%d: load %lld half1 %lld gemm+load %lld half2 %lld total %lld\n", rg, tid, t1 - t0, t2 - t1, t3 - t2, t4 - t3, clock64() - t0);
+#endif
   }
+}
+
+static void cq_launch_trsm(ovb_ctx *ctx, int ctas, double *A, int ldA, int m, int nt, const double *Lpk) {
+  const int NB = (nt + 7) / 8;
+  const size_t smem = CQ_TRSM_SMEM;
+  if (NB <= 5)
+    ovb_launch(ctx, k_cq_trsm<5, 0>, dim3(ctas), dim3(CQ_TRSM_T), smem, A, ldA, m, nt, Lpk);
+  else if (NB <= 10)
+    ovb_launch(ctx, k_cq_trsm<10, 0>, dim3(ctas), dim3(CQ_TRSM_T), smem, A, ldA, m, nt, Lpk);
+  else if (NB <= 15)
+    ovb_launch(ctx, k_cq_trsm<10, 5>, dim3(ctas), dim3(CQ_TRSM_T), smem, A, ldA, m, nt, Lpk);
+  else
+    ovb_launch(ctx, k_cq_trsm<10, 10>, dim3(ctas), dim3(CQ_TRSM_T), smem, A, ldA, m, nt, Lpk);
 }
 
 // ------------------------------------------------------------------------------------------------------------ R = R2 R1
@@ -804,7 +838,10 @@ static bool cq_attrs(ovb_ctx *ctx) {
     cudaFuncSetAttribute(k_cq_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_cq_chol_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CqCholSmem));
     cudaFuncSetAttribute(k_cq_chol_ekf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CqCholSmem));
-    cudaFuncSetAttribute(k_cq_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CQ_TRSM_SMEM);
+    cudaFuncSetAttribute(k_cq_trsm<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CQ_TRSM_SMEM);
+    cudaFuncSetAttribute(k_cq_trsm<10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CQ_TRSM_SMEM);
+    cudaFuncSetAttribute(k_cq_trsm<10, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CQ_TRSM_SMEM);
+    cudaFuncSetAttribute(k_cq_trsm<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CQ_TRSM_SMEM);
     ctx->attr_done[4] = 1;
   }
   return true;
@@ -853,7 +890,7 @@ bool launch_trsm_rows(ovb_ctx *ctx, double *A, int ldA, int m, int nt, const dou
   int ctas = (ngroups + 3) / 4; // short matrices (the EKF's N rows): few row groups per CTA so that the groups spread over the SMs
   if (ctas > ctx->sm_count)
     ctas = ctx->sm_count;
-  ovb_launch(ctx, k_cq_trsm, dim3(ctas), dim3(CQ_TRSM_T), (size_t)CQ_TRSM_SMEM, A, ldA, m, nt, Lpk);
+  cq_launch_trsm(ctx, ctas, A, ldA, m, nt, Lpk);
   return true;
 }
 
@@ -888,7 +925,6 @@ int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, doub
   double *G = ctx->d_G, *L1 = G + (size_t)ldW * ldW, *L2 = L1 + (size_t)ldW * ldW;
   static_assert(CQ_PK_DOUBLES <= (CQ_MAXN + 8) * (CQ_MAXN + 8), "packed factor must fit its slot");
   const size_t gram_smem = sizeof(double) * 2 * CQ_KB * (size_t)(BW * 32 + 4);
-  const size_t trsm_smem = CQ_TRSM_SMEM;
   const int ngroups = (m + 7) / 8;
   int trsm_ctas = (ngroups + CQ_TRSM_T / 32 - 1) / (CQ_TRSM_T / 32);
   if (trsm_ctas > ctx->sm_count)
@@ -899,7 +935,7 @@ int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, doub
     ovb_launch(ctx, k_cq_chol_gram, dim3(1), dim3(CQ_CHOL_T), sizeof(CqCholSmem), (const double *)G, ldW, nt, pass == 0 ? 1e-11 : 1e-13,
                pass == 0 ? L1 : L2);
     if (pass == 0)
-      ovb_launch(ctx, k_cq_trsm, dim3(trsm_ctas), dim3(CQ_TRSM_T), trsm_smem, A, ldA, m, nt, (const double *)L1);
+      cq_launch_trsm(ctx, trsm_ctas, A, ldA, m, nt, (const double *)L1);
   }
   const int nT16 = (nt + 15) / 16;
   ovb_launch(ctx, k_cq_trmm, dim3(nT16, nT16), dim3(256), (size_t)0, (const double *)L2, (const double *)L1, nt, Rout, ldR);

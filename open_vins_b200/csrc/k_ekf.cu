@@ -499,10 +499,17 @@ __global__ void k_cov_init_augment(double *__restrict__ P, int ld, int N, int k,
   }
 }
 
-void launch_cov_init_augment(ovb_ctx *ctx, int k, int n, const double *Hx_dev, const double *Hinv_dev, double sigma2) {
+bool launch_cov_init_augment(ovb_ctx *ctx, int k, int n, const double *Hx_dev, const double *Hinv_dev, double sigma2) {
   const int N = ctx->N;
   size_t smem = sizeof(double) * ((size_t)N * k + (size_t)k * k);
+  if (smem > 200 * 1024)
+    return false; // N*k doubles must fit one CTA's shared memory (N <= ~8500 for a 3-wide landmark)
+  if (!ctx->attr_done[5]) {
+    cudaFuncSetAttribute(k_cov_init_augment, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    ctx->attr_done[5] = 1;
+  }
   k_cov_init_augment<<<1, 256, smem, ctx->stream>>>(ctx->P[ctx->cur], ctx->ldP, N, k, n, ctx->d_info, Hx_dev, Hinv_dev, sigma2);
+  return cudaGetLastError() == cudaSuccess;
 }
 
 // StateHelper::clone: append a copy of the `size`-wide variable at old_off (StateHelper.cpp:371-373)

@@ -479,23 +479,48 @@ static ovb_status pack_inputs(ovb_ctx *ctx, const ovb_frame *fr, const ovb_feat_
     else
       row += Mf >= 2 ? 2 * Mf - 3 : 0;
     d.key0 = (int)nkeys;
-    if (fb->cam_keys_off && fb->cam_keys) {
-      for (int k = fb->cam_keys_off[f]; k < fb->cam_keys_off[f + 1]; k++) {
-        if (fb->cam_keys[k] >= fr->n_cams)
-          return OVB_ERR_ARG;
-        hkeys[nkeys++] = fb->cam_keys[k];
+    // validate BEFORE anything is stored in the pinned blob: camera ids in range, at most one key per camera (the
+    // reference's feat->timestamps is a map keyed by camera id), room for the keys
+    for (int i = d.m0; i < d.m1; i++)
+      if (fb->cam[i] >= fr->n_cams || fb->clone[i] >= fr->n_clones) {
+        snprintf(ctx->err, sizeof(ctx->err), "feature %d: measurement %d refers to camera %d / clone %d outside the frame", f, i, (int)fb->cam[i],
+                 (int)fb->clone[i]);
+        return OVB_ERR_ARG;
       }
-    } else {
-      int last = -1;
-      for (int i = d.m0; i < d.m1; i++)
-        if ((int)fb->cam[i] != last) {
-          last = fb->cam[i];
-          hkeys[nkeys++] = (unsigned char)last;
+    if (o_keys + nkeys + (size_t)OVB_MAX_CAMS > ctx->blob_cap)
+      return OVB_ERR_CAPACITY;
+    {
+      unsigned seen = 0;
+      if (fb->cam_keys_off && fb->cam_keys) {
+        const int k0 = fb->cam_keys_off[f], k1 = fb->cam_keys_off[f + 1];
+        if (k0 < 0 || k1 < k0 || k1 - k0 > fr->n_cams) {
+          snprintf(ctx->err, sizeof(ctx->err), "feature %d: %d camera keys for %d cameras", f, k1 - k0, fr->n_cams);
+          return OVB_ERR_ARG;
         }
+        for (int k = k0; k < k1; k++) {
+          const unsigned c = fb->cam_keys[k];
+          if ((int)c >= fr->n_cams || (seen >> c) & 1u) {
+            snprintf(ctx->err, sizeof(ctx->err), "feature %d: camera key %u out of range or repeated", f, c);
+            return OVB_ERR_ARG;
+          }
+          seen |= 1u << c;
+          hkeys[nkeys++] = (unsigned char)c;
+        }
+      } else {
+        int last = -1;
+        for (int i = d.m0; i < d.m1; i++)
+          if ((int)fb->cam[i] != last) {
+            last = fb->cam[i];
+            if ((seen >> last) & 1u) { // measurements must be grouped by camera (include/ovb200.h, ovb_feat_batch)
+              snprintf(ctx->err, sizeof(ctx->err), "feature %d: measurements are not grouped by camera", f);
+              return OVB_ERR_ARG;
+            }
+            seen |= 1u << last;
+            hkeys[nkeys++] = (unsigned char)last;
+          }
+      }
     }
     d.key1 = (int)nkeys;
-    if (o_keys + nkeys + OVB_MAX_CAMS > ctx->blob_cap)
-      return OVB_ERR_CAPACITY;
     for (int i = d.m0; i < d.m1; i++)
       if (fb->cam[i] >= fr->n_cams || fb->clone[i] >= fr->n_clones)
         return OVB_ERR_ARG;
@@ -1014,15 +1039,69 @@ ovb_status ovb_last_stage_ms(const ovb_ctx *ctx, float ms[6]) {
 ovb_status ovb_set_stream(ovb_ctx *ctx, void *cuda_stream) {
   if (!ctx)
     return OVB_ERR_ARG;
+  if (!cuda_stream) {
+    // the legacy default stream (handle 0) has no ordering with the engine's non-blocking streams: adopting it would
+    // silently leave the engine on its own stream and race with the caller's collectives
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_set_stream: pass an explicit (non-default) CUDA stream handle");
+    return OVB_ERR_ARG;
+  }
   OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (cuda_stream) {
-    if (ctx->own_stream && ctx->stream)
-      cudaStreamDestroy(ctx->stream);
-    ctx->stream = (cudaStream_t)cuda_stream;
-    ctx->own_stream = 0;
-  }
+  if (ctx->own_stream && ctx->stream)
+    cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = 0;
   return OVB_OK;
+}
+
+// contiguous feature ranges with (nearly) equal stacked-row counts sum(max(2M-3, 0)); bounds[world + 1]
+ovb_status ovb_shard_partition(const int32_t *meas_off, int n_feats, int world, int32_t *bounds) {
+  if (!meas_off || !bounds || n_feats < 0 || world < 1)
+    return OVB_ERR_ARG;
+  long long total = 0;
+  for (int f = 0; f < n_feats; f++)
+    total += std::max(2 * (meas_off[f + 1] - meas_off[f]) - 3, 0);
+  bounds[0] = 0;
+  long long cum = 0;
+  int f = 0;
+  for (int r = 1; r < world; r++) {
+    const double target = (double)total * r / world;
+    while (f < n_feats && (double)cum < target) { // first f with cum(f) >= target
+      cum += std::max(2 * (meas_off[f + 1] - meas_off[f]) - 3, 0);
+      f++;
+    }
+    bounds[r] = f;
+  }
+  bounds[world] = n_feats;
+  return OVB_OK;
+}
+
+ovb_status ovb_msckf_shard_compress_range(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, int f0, int f1, const ovb_opts *opts,
+                                          double *R_dev, int R_cap_doubles, int *n_cols, int *ld) {
+  if (!ctx || !feats || f0 < 0 || f1 < f0 || f1 > feats->n_feats)
+    return OVB_ERR_ARG;
+  // shallow view of features [f0, f1): pointers advanced, offsets rebased
+  const int F = f1 - f0, m0 = feats->meas_off[f0], m1 = feats->meas_off[f1];
+  std::vector<int32_t> moff((size_t)F + 1), koff;
+  for (int f = 0; f <= F; f++)
+    moff[(size_t)f] = feats->meas_off[f0 + f] - m0;
+  ovb_feat_batch v = *feats;
+  v.n_feats = F;
+  v.n_meas = m1 - m0;
+  v.meas_off = moff.data();
+  v.cam = feats->cam + m0;
+  v.clone = feats->clone + m0;
+  v.uv = feats->uv + 2 * (size_t)m0;
+  v.uvn = feats->uvn + 2 * (size_t)m0;
+  if (feats->cam_keys_off && feats->cam_keys) {
+    const int k0 = feats->cam_keys_off[f0];
+    koff.resize((size_t)F + 1);
+    for (int f = 0; f <= F; f++)
+      koff[(size_t)f] = feats->cam_keys_off[f0 + f] - k0;
+    v.cam_keys_off = koff.data();
+    v.cam_keys = feats->cam_keys + k0;
+  }
+  return ovb_msckf_shard_compress(ctx, frame, &v, opts, R_dev, R_cap_doubles, n_cols, ld); // pack_inputs copies: the view may die here
 }
 
 ovb_status ovb_msckf_shard_compress(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, double *R_dev,
@@ -1037,6 +1116,7 @@ ovb_status ovb_msckf_shard_compress(ovb_ctx *ctx, const ovb_frame *frame, const 
   ovb_status st = pack_inputs(ctx, frame, feats, &o2, nullptr, &pk);
   if (st != OVB_OK)
     return st;
+  cudaEventRecord(ctx->ev[1], ctx->stream); // inputs resident from here on
   *n_cols = pk.n_all;
   *ld = pk.ldH;
   if ((size_t)pk.n_all * pk.ldH > (size_t)R_cap_doubles)
@@ -1087,6 +1167,7 @@ ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_block
   cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[0], ctx->ev[6]);
   cudaEventElapsedTime(&ctx->stage_ms[3], ctx->ev[0], ctx->ev[4]);
   cudaEventElapsedTime(&ctx->stage_ms[4], ctx->ev[4], ctx->ev[5]);
+  cudaEventElapsedTime(&ctx->stage_ms[0], ctx->ev[1], ctx->ev[5]); // inputs resident -> EKF update done (collective included)
   const DevUpdateInfo *inf = ctx->h_info;
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -1460,8 +1541,12 @@ ovb_status ovb_cov_initialize(ovb_ctx *ctx, const int *off, const int *sz, int n
     for (int i = 0; i < k * k; i++)
       stage[(size_t)k * n + i] = Inv[i];
     OVB_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_Y, stage.data(), sizeof(double) * stage.size(), cudaMemcpyHostToDevice, ctx->stream));
-    launch_cov_init_augment(ctx, k, n, ctx->d_Y, ctx->d_Y + (size_t)k * n, sigma2);
+    const bool launched = launch_cov_init_augment(ctx, k, n, ctx->d_Y, ctx->d_Y + (size_t)k * n, sigma2);
     OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // `stage` is pageable host memory owned by this scope
+    if (!launched) { // nothing was written: N and the covariance are unchanged
+      snprintf(ctx->err, sizeof(ctx->err), "ovb_cov_initialize: covariance augmentation kernel could not be launched (N=%d, k=%d)", N, k);
+      return OVB_ERR_CAPACITY;
+    }
   }
   ctx->N = N + k;
   for (int q = 0; q < k; q++) {

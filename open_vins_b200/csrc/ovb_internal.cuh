@@ -191,7 +191,8 @@ void launch_reorder_R(ovb_ctx *ctx, const double *Rin, int n_all, int ldRin, dou
 // EKF update from an upper-trapezoidal / dense H [r x n] with column->state map in d_info (device-side sizes)
 void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r_max, int n_max, bool sizes_from_info, double sigma2,
                        const double *Rdiag_dev);
-void launch_cov_init_augment(ovb_ctx *ctx, int k, int n, const double *Hx_dev, const double *Hinv_dev, double sigma2);
+// false: the launch was refused (shared-memory footprint) or failed; the caller must not grow N
+bool launch_cov_init_augment(ovb_ctx *ctx, int k, int n, const double *Hx_dev, const double *Hinv_dev, double sigma2);
 void launch_cov_clone(ovb_ctx *ctx, int old_off, int size, const double *dnc_dt_dev, int dt_off);
 void launch_cov_marginalize(ovb_ctx *ctx, int off, int size);
 void launch_cov_propagate(ovb_ctx *ctx, int new_off, int p, int q, const int *old_idx_dev, const double *Phi_dev, const double *Q_dev);

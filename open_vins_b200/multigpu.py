@@ -5,19 +5,33 @@ independent per feature, so features are partitioned across ranks (balanced by s
 compressed blocks [R_g | z_g] (n x (n+1) doubles each) with ONE all-gather per update; every rank then compresses the
 G stacked triangles and applies the identical EKF update to its replica of P. No other collective is on the data path.
 
+Small updates are NOT sharded: one config-2 update (400 features) is ~0.6 ms of latency-bound kernels, and splitting it
+only adds an all-gather and a second compression. Below REPLICATE_BELOW_ROWS stacked rows every rank simply runs the
+whole update on its replica (deterministic kernels keep the replicas bitwise equal; no collective at all).
+
 The compute backend is abstract so the plumbing can be exercised on CPU (gloo) in tests; the product backend is
 `EngineBackend` (the CUDA engine through the C ABI).
 """
 from __future__ import annotations
 
+import contextlib
 import json
 import time
 
 import numpy as np
 
+REPLICATE_BELOW_ROWS = 60_000  # ~1000 features of the rpng_sim stereo track-length mix
+
+
+def stacked_rows(meas_off) -> int:
+    meas_off = np.asarray(meas_off, dtype=np.int64)
+    M = meas_off[1:] - meas_off[:-1]
+    return int(np.maximum(2 * M - 3, 0).sum())
+
 
 def partition_features(meas_off, world: int):
-    """Contiguous feature ranges with (nearly) equal stacked-row counts sum(max(2M-3,0)). Returns [(f0, f1)] * world."""
+    """Contiguous feature ranges with (nearly) equal stacked-row counts sum(max(2M-3,0)). Returns [(f0, f1)] * world.
+    numpy twin of ovb_shard_partition (csrc/ovb_api.cu), used by the CPU test backend."""
     meas_off = np.asarray(meas_off, dtype=np.int64)
     M = meas_off[1:] - meas_off[:-1]
     rows = np.maximum(2 * M - 3, 0)
@@ -35,7 +49,9 @@ def partition_features(meas_off, world: int):
 
 
 class EngineBackend:
-    """CUDA engine + torch device tensors for the exchanged blocks."""
+    """CUDA engine + torch device tensors for the exchanged blocks. Engine kernels and the NCCL all-gather are issued on
+    ONE dedicated, explicit CUDA stream (never the legacy default stream: the engine's own streams are non-blocking and
+    have no implicit ordering with it), so shard_compress -> all_gather -> finish is ordered without host syncs."""
 
     def __init__(self, engine, device):
         import torch
@@ -44,16 +60,26 @@ class EngineBackend:
         self.device = device
         self.R_local = None
         self.R_all = None
-        eng_stream = torch.cuda.current_stream(device).cuda_stream
-        self.eng.set_stream(eng_stream)  # kernels and NCCL calls are ordered on one stream: no host sync in between
+        self.stream = torch.cuda.Stream(device)
+        self.eng.set_stream(self.stream.cuda_stream)
 
-    def shard_compress(self, frame, feats, opts, world):
+    def stream_ctx(self):
+        return self.torch.cuda.stream(self.stream)
+
+    def partition(self, meas_off, world):
+        from . import capi
+        return capi.shard_partition(meas_off, world)
+
+    def full_update(self, frame, feats, opts):
+        return self.eng.msckf_update(frame, feats, opts)
+
+    def shard_compress(self, frame, feats, f0, f1, opts, world):
         torch = self.torch
         cap = 512 * 520
         if self.R_local is None:
             self.R_local = torch.empty(cap, dtype=torch.float64, device=self.device)
             self.R_all = torch.empty(cap * world, dtype=torch.float64, device=self.device)
-        n, ld = self.eng.shard_compress(frame, feats, opts, self.R_local.data_ptr(), cap)
+        n, ld = self.eng.shard_compress_range(frame, feats, f0, f1, opts, self.R_local.data_ptr(), cap)
         self.n, self.ld = n, ld
         return self.R_local[: n * ld]
 
@@ -64,80 +90,63 @@ class EngineBackend:
         return self.eng.shard_finish(stacked.data_ptr(), world, n_feats)
 
 
-def sharded_update(backend, dist, frame, feats, opts, rank: int, world: int):
-    """One MSCKF update with features sharded over `world` ranks. Returns (status, out_shard, dx, stats, (f0, f1))."""
-    parts = partition_features(feats.meas_off, world)
-    f0, f1 = parts[rank]
-    shard = feats.subset(np.arange(f0, f1))
-    block = backend.shard_compress(frame, shard, opts, world)
-    if world > 1:
+def sharded_update(backend, dist, frame, feats, opts, rank: int, world: int, replicate_below_rows: int = REPLICATE_BELOW_ROWS):
+    """One MSCKF update on `world` ranks. Returns (status, out, dx, stats, (f0, f1)); (f0, f1) is the feature range whose
+    per-feature results `out` holds (the whole batch when the update was replicated)."""
+    F = len(feats.meas_off) - 1
+    if world == 1 or stacked_rows(feats.meas_off) < replicate_below_rows:
+        st, out, dx, stats = backend.full_update(frame, feats, opts)
+        return st, out, dx, stats, (0, F)
+    f0, f1 = backend.partition(feats.meas_off, world)[rank]
+    with getattr(backend, "stream_ctx", contextlib.nullcontext)():
+        block = backend.shard_compress(frame, feats, f0, f1, opts, world)
         stacked = backend.gather_target(world)
         dist.all_gather_into_tensor(stacked, block)
-    else:
-        stacked = block
-    st, out, dx, stats = backend.finish(stacked, world, shard.n_feats)
+        st, out, dx, stats = backend.finish(stacked, world, f1 - f0)
     return st, out, dx, stats, (f0, f1)
 
 
-def bench_sharded(args, rank, local_rank, world, case, opts, workload_name, ClockSampler, peaks, emit=None):
-    """bench.py's N>1 leg: the config-2 update with its 400 features sharded over N GPUs (strong scaling)."""
-    import torch
-    import torch.distributed as dist
-    from . import capi
+def _relerr(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
-    dev = torch.device("cuda", local_rank)
-    cap = max(1024, case.feats.n_feats)
-    eng = capi.Engine(max_state=256, max_feats=cap, max_meas=cap * 48, device=local_rank)
-    backend = EngineBackend(eng, dev)
-    K, W = args.steps, args.warmup
-    F = case.feats.n_feats
-    sampler = ClockSampler(local_rank)
+
+def time_sharded(eng, backend, dist, torch, case, opts, rank, world, K, W, threshold):
+    """K timed sharded updates of `case` (after W warm-ups). Device time per step = CUDA events on the shared stream from
+    'inputs resident' to 'EKF update done' (all-gather inside), host time = wall clock around the three calls.
+    Returns dict(t_dev, t_host, used, sharded_vs_single) with times as max over ranks."""
+    dev = backend.device
+    # correctness first (untimed): the sharded result equals the single-GPU result of the same engine on the same inputs
+    eng.cov_set(case.P)
+    st1, out1, dx1, _ = eng.msckf_update(case.frame, case.feats, opts)
+    P1 = eng.cov_get()
+    eng.cov_set(case.P)
+    st, out, dx, stats, (f0, f1) = sharded_update(backend, dist, case.frame, case.feats, opts, rank, world, threshold)
+    torch.cuda.synchronize()
+    P2 = eng.cov_get()
+    err = max(_relerr(P2, P1), _relerr(dx, dx1))
+    same_gate = bool(np.array_equal(out.status, out1.status[f0:f1]))
     for _ in range(W):
         eng.cov_set(case.P)
-        sharded_update(backend, dist, case.frame, case.feats, opts, rank, world)
+        sharded_update(backend, dist, case.frame, case.feats, opts, rank, world, threshold)
     torch.cuda.synchronize()
     dist.barrier()
-    if rank == 0:
-        sampler.start()
-    t_host = 0.0
-    t_dev = 0.0
+    t_host = t_dev = 0.0
     used = 0
     for _ in range(K):
         eng.cov_set(case.P)
         torch.cuda.synchronize()
         dist.barrier()
         t = time.perf_counter()
-        st, out, dx, stats, _ = sharded_update(backend, dist, case.frame, case.feats, opts, rank, world)
+        st, out, dx, stats, _ = sharded_update(backend, dist, case.frame, case.feats, opts, rank, world, threshold)
         t_host += time.perf_counter() - t
-        t_dev += eng.last_stage_ms()[5] * 1e-3  # CUDA events: first shard kernel .. results on the host
+        t_dev += eng.last_stage_ms()[0] * 1e-3
         used = stats.n_feats_used
-    clocks = sampler.stop() if rank == 0 else None
-    tt = torch.tensor([t_host, t_dev], dtype=torch.float64, device=dev)
+    tt = torch.tensor([t_host, t_dev, err], dtype=torch.float64, device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    used_t = torch.tensor([used], dtype=torch.int64, device=dev)
+    used_t = torch.tensor([used, int(same_gate)], dtype=torch.int64, device=dev)
     dist.all_reduce(used_t, op=dist.ReduceOp.SUM)
-    # replicas must agree bit for bit
     Pchk = torch.from_numpy(eng.cov_get()).to(dev)
     Pmax = Pchk.clone()
     dist.all_reduce(Pmax, op=dist.ReduceOp.MAX)
-    same = bool(torch.equal(Pchk, Pmax))
-    cnt = eng.last_counters()
-    if rank == 0:
-        t_host, t_dev = float(tt[0]), float(tt[1])
-        line = {
-            "metric": "msckf_updates_per_sec", "value": K / t_dev, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "feats_per_sec": F * K / t_dev,
-            "config": {"workload": workload_name, "features_in": F, "features_used": int(used_t[0]), "sharding": f"features over {world} ranks, "
-                       "one all-gather of the compressed (R,z) block per update, EKF update replicated", "l2": "inputs re-uploaded every step",
-                       "replicas_bitwise_equal": same},
-            "e2e": {"value": K / t_host, "unit": "updates/s", "ms_per_step": 1e3 * t_host / K, "h2d_bytes_per_step": cnt["h2d_bytes"],
-                    "d2h_bytes_per_step": cnt["d2h_bytes"], "timing": "host clock around shard_compress + all_gather + finish, max over ranks"},
-            "gpu_launches": cnt["launches"] * K, "gpu_launches_per_step": cnt["launches"],
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": None, "peak": peaks()[0], "unit": "GB/s", "frac": None, "traffic": None,
-                         "note": "see the N=1 line: the per-rank kernels are the same; at N>1 the step is latency-bound (NCCL + second-level QR)"},
-        }
-        (emit or (lambda l: print(json.dumps(l), flush=True)))(line)
-    eng.close()
-    dist.destroy_process_group()
+    return {"t_host": float(tt[0]), "t_dev": float(tt[1]), "sharded_vs_single_relerr": float(tt[2]), "features_used": int(used_t[0]),
+            "gate_decisions_equal_on_all_ranks": int(used_t[1]) == world, "replicas_bitwise_equal": bool(torch.equal(Pchk, Pmax))}

@@ -24,9 +24,11 @@ def test_partition_is_contiguous_and_balanced():
         rows = np.maximum(2 * M - 3, 0)
         loads = [rows[a:b].sum() for a, b in parts]
         assert max(loads) - min(loads) <= 2 * rows.max() + 1
+        assert capi.shard_partition(off, world) == parts  # the C implementation (ovb_shard_partition) agrees with the numpy twin
     # degenerate: fewer features than ranks
     parts = multigpu.partition_features([0, 5, 9], 4)
     assert parts[0][0] == 0 and parts[-1][1] == 2 and all(a <= b for a, b in parts)
+    assert capi.shard_partition([0, 5, 9], 4) == parts
 
 
 class OracleBackend:
@@ -35,7 +37,11 @@ class OracleBackend:
     def __init__(self, oracle, P, layout):
         self.o, self.P, self.layout = oracle, np.array(P), layout
 
-    def shard_compress(self, frame, feats, opts, world):
+    def partition(self, meas_off, world):
+        return capi.shard_partition(meas_off, world)  # the C partition (host code of libovb200.so)
+
+    def shard_compress(self, frame, feats, f0, f1, opts, world):
+        feats = feats.subset(np.arange(f0, f1))
         cols = []
         for off, sz in sorted([(o, 6) for o in self.layout.clone_off] + [(o, 6) for o in self.layout.cam_ext_off if o >= 0] +
                               [(o, 8) for o in self.layout.cam_intr_off if o >= 0]):
@@ -73,7 +79,7 @@ def _worker(rank, world, port, q):
     case = sim.make_update_case(n_feats=40, n_clones=8, n_cams=2, seed=5, calib_ext=True, calib_intr=True)
     opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, col_order=capi.COLS_CANONICAL)
     be = OracleBackend(ovo_py, case.P, case.layout)
-    st, out, dx, _, (f0, f1) = multigpu.sharded_update(be, dist, case.frame, case.feats, opts, rank, world)
+    st, out, dx, _, (f0, f1) = multigpu.sharded_update(be, dist, case.frame, case.feats, opts, rank, world, replicate_below_rows=0)
     q.put((rank, st, dx, be.P_new, out.status.copy(), f0, f1))
     dist.barrier()
     dist.destroy_process_group()

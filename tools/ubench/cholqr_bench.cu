@@ -115,7 +115,7 @@ int main() {
   const size_t trsm_smem = CQ_TRSM_SMEM;
   CK(cudaFuncSetAttribute(k_cq_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(k_cq_chol_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CqCholSmem)));
-  CK(cudaFuncSetAttribute(k_cq_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CQ_TRSM_SMEM));
+  CK(cudaFuncSetAttribute(k_cq_trsm<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CQ_TRSM_SMEM));
   cudaEvent_t e[8];
   for (auto &x : e) cudaEventCreate(&x);
   for (int rep = 0; rep < 4; rep++) {
@@ -128,14 +128,18 @@ int main() {
     cudaEventRecord(e[2]);
     k_cq_chol_gram<<<1, CQ_CHOL_T, sizeof(CqCholSmem)>>>(G, ldW, nt, 1e-11, Rpk);
     cudaEventRecord(e[3]);
-    k_cq_trsm<<<sms, CQ_TRSM_T, trsm_smem>>>(A, ld, m, nt, Rpk);
+    k_cq_trsm<10, 10><<<sms, CQ_TRSM_T, trsm_smem>>>(A, ld, m, nt, Rpk);
     cudaEventRecord(e[4]);
     k_cq_trmm<<<dim3((nt + 15) / 16, (nt + 15) / 16), 256>>>(Rpk, Rpk, nt, Rout, ld);
     cudaEventRecord(e[5]);
+    k_cq_trsm<10, 10><<<7, CQ_TRSM_T, trsm_smem>>>(A, ld, 194, nt, Rpk);
+    cudaEventRecord(e[6]);
+    k_cq_trsm<10, 10><<<1, CQ_TRSM_T, trsm_smem>>>(A, ld, 8, nt, Rpk);
+    cudaEventRecord(e[7]);
     CK(cudaDeviceSynchronize());
-    float t[5];
-    for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], e[i], e[i + 1]);
-    printf("rep %d: gram %.1f us  reduce %.1f us  chol %.1f us  trsm %.1f us  trmm %.1f us\n", rep, 1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3], 1e3 * t[4]);
+    float t[7];
+    for (int i = 0; i < 7; i++) cudaEventElapsedTime(&t[i], e[i], e[i + 1]);
+    printf("rep %d: gram %.1f us  reduce %.1f us  chol %.1f us  trsm %.1f us  trmm %.1f us  trsm(194 rows) %.1f us  trsm(8 rows) %.1f us\n", rep, 1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3], 1e3 * t[4], 1e3 * t[5], 1e3 * t[6]);
   }
   return 0;
 }
