@@ -887,7 +887,9 @@ bool launch_trsm_rows(ovb_ctx *ctx, double *A, int ldA, int m, int nt, const dou
     return false;
   cq_attrs(ctx);
   const int ngroups = (m + 7) / 8;
-  int ctas = (ngroups + 3) / 4; // short matrices (the EKF's N rows): few row groups per CTA so that the groups spread over the SMs
+  // short matrices (the EKF's N rows): one row group per CTA while the SMs last — a row group alone on its SM runs its
+  // 20-block substitution chain ~3x faster than four groups sharing the SM's FP64 pipe (tools/ubench/cholqr_bench.cu)
+  int ctas = ngroups;
   if (ctas > ctx->sm_count)
     ctas = ctx->sm_count;
   cq_launch_trsm(ctx, ctas, A, ldA, m, nt, Lpk);
