@@ -72,6 +72,29 @@ def build_host_test(force: bool = False) -> str:
     return exe
 
 
+def build_sim_tools(force: bool = False, with_oracle: bool = True):
+    """rpng_sim runners (tools/run_simulation.cpp over include/ovb200_vio.hpp): the product executable
+    open_vins_b200/ovb_run_simulation (CUDA engine) and, as test infrastructure, tests/cpp/run_simulation_oracle (the CPU
+    oracle behind the same host code). Returns (engine_exe, oracle_exe or None)."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tools", "run_simulation.cpp")
+    inc = os.path.join(root, "include")
+    hdrs = [os.path.join(inc, h) for h in ("ovb200.h", "ovb200_host.hpp", "ovb200_math.hpp", "ovb200_sim.hpp", "ovb200_vio.hpp")]
+    cxx = os.environ.get("CXX", "g++")
+    exe = os.path.join(HERE, "ovb_run_simulation")
+    if force or _stale(exe, [src, OUT] + hdrs):
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-DOVB_SIM_ENGINE", "-I", inc, src, "-L", HERE, "-lovb200", "-Wl,-rpath,$ORIGIN", "-o", exe])
+    oexe = None
+    if with_oracle:
+        odir = os.path.join(root, "oracle")
+        osrc = os.path.join(root, "tests", "cpp", "oracle_backend.hpp")
+        oexe = os.path.join(root, "tests", "cpp", "run_simulation_oracle")
+        if force or _stale(oexe, [src, osrc, OUT, os.path.join(odir, "libovoracle.so")] + hdrs):
+            subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-DOVB_SIM_ORACLE", "-I", os.path.join(root, "tests", "cpp"), "-I", inc, src, "-L", HERE,
+                                   "-lovb200", "-L", odir, "-lovoracle", "-Wl,-rpath,$ORIGIN/../../open_vins_b200", "-Wl,-rpath,$ORIGIN/../../oracle", "-o", oexe])
+    return exe, oexe
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)

@@ -1,0 +1,134 @@
+// sim_probe.cpp — test helper: prints values of the host-side simulator / propagator functions for tests/test_sim_cpu.py.
+//   sim_probe undistort u v            -> xn yn            (cam0 of rpng_sim)
+//   sim_probe distort xn yn            -> u v
+//   sim_probe spline TRAJ t            -> R(9) p(3) w(3) v(3) alpha(3) a(3) start_time
+//   sim_probe propfd METHOD            -> max |F_analytic - F_numeric| over the 15+24 state, and |F| for scale
+#include "../../include/ovb200_vio.hpp"
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+using namespace ovb200;
+
+// error state of b relative to a (JPL left error for quaternions: q_b = dq(dtheta) ⊗ q_a), additive elsewhere
+static Vec3 qerr(const Vec4 &qb, const Vec4 &qa) {
+  const Vec4 ainv{-qa[0], -qa[1], -qa[2], qa[3]};
+  const Vec4 d = quat_multiply(qb, ainv);
+  return {2 * d[0], 2 * d[1], 2 * d[2]};
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2)
+    return 2;
+  const std::string cmd = argv[1];
+  SimParams sp;
+  rpng_sim_cameras(2, sp);
+  if (cmd == "undistort" && argc >= 4) {
+    float x, y;
+    sp.camera_intrinsics[0].undistort_f((float)std::atof(argv[2]), (float)std::atof(argv[3]), x, y);
+    std::printf("%.9g %.9g\n", x, y);
+    return 0;
+  }
+  if (cmd == "distort" && argc >= 4) {
+    float u, v;
+    sp.camera_intrinsics[0].distort_f((float)std::atof(argv[2]), (float)std::atof(argv[3]), u, v);
+    std::printf("%.9g %.9g\n", u, v);
+    return 0;
+  }
+  if (cmd == "spline" && argc >= 4) {
+    const std::string traj = argv[2];
+    auto data = traj.substr(traj.size() - 4) == ".bin" ? load_trajectory_bin(traj) : load_simulated_trajectory(traj);
+    BsplineSE3 s;
+    s.feed_trajectory(data);
+    for (int i = 3; i < argc; i++) {
+      Mat3 R;
+      Vec3 p, w, v, al, a;
+      const double t = s.get_start_time() + std::atof(argv[i]);
+      const bool ok = s.get_acceleration(t, R, p, w, v, al, a);
+      std::printf("%d", (int)ok);
+      for (double x : R) std::printf(" %.17g", x);
+      for (const Vec3 *q : {&p, &w, &v, &al, &a})
+        for (double x : *q) std::printf(" %.17g", x);
+      std::printf(" %.17g\n", s.get_start_time());
+    }
+    return 0;
+  }
+  if (cmd == "propfd" && argc >= 3) {
+    const std::string m = argv[2];
+    VioOptions vo;
+    vo.do_fej = false; // numeric Jacobian around the current estimate
+    vo.integration_method = m == "discrete" ? INTEGRATION_DISCRETE : (m == "analytical" ? INTEGRATION_ANALYTICAL : INTEGRATION_RK4);
+    struct NullCov : CovBackend {
+      int dim() override { return 0; }
+      void set(const std::vector<double> &, int) override {}
+      std::vector<double> get() override { return {}; }
+      std::vector<double> get_marginal(const std::vector<int> &, const std::vector<int> &) override { return {}; }
+      void clone(int, int, const double *, int) override {}
+      void marginalize(int, int) override {}
+      void propagate(int, int, const std::vector<int> &, const std::vector<int> &, const std::vector<double> &, const std::vector<double> &) override {}
+      int msckf_update(const ovb_frame *, const ovb_feat_batch *, const ovb_opts *, ovb_feat_out *, double *, ovb_stats *) override { return 0; }
+    };
+    VioManager sys(vo, sp, std::make_shared<NullCov>());
+    VioState s0 = sys.state;
+    s0.q = s0.q_fej = quatnorm({0.1, -0.2, 0.3, 0.9});
+    s0.p = s0.p_fej = {1, 2, 3};
+    s0.v = s0.v_fej = {0.5, -0.3, 0.2};
+    s0.bg = {0.01, -0.02, 0.005};
+    s0.ba = {0.05, 0.02, -0.03};
+    const double dwv[6] = {1.01, 0.002, -0.003, 0.99, 0.004, 1.02}, dav[6] = {0.98, -0.001, 0.002, 1.01, 0.003, 0.99};
+    const double tgv[9] = {1e-3, -2e-3, 5e-4, 3e-4, 1e-3, -1e-3, 2e-4, -4e-4, 6e-4};
+    std::copy(dwv, dwv + 6, s0.dw);
+    std::copy(dav, dav + 6, s0.da);
+    std::copy(tgv, tgv + 9, s0.tg);
+    s0.q_GYROtoIMU = quatnorm({0.01, -0.02, 0.015, 1.0});
+    ImuData d0, d1;
+    d0.timestamp = 0, d1.timestamp = 0.0025;
+    d0.wm = {0.3, -0.2, 0.5}, d1.wm = {0.31, -0.19, 0.52};
+    d0.am = {0.5, 9.6, 1.0}, d1.am = {0.55, 9.62, 0.98};
+    Propagator prop(9.81);
+    const int n = 39;
+    std::vector<double> F, Qd;
+    VioState nominal = s0;
+    prop.predict_and_compute(nominal, d0, d1, F, Qd);
+    double maxdiff = 0, maxF = 0;
+    const double eps = 1e-6;
+    for (int j = 0; j < n; j++) {
+      VioState sp2 = s0;
+      auto rot = [&](Vec4 &q) { q = quat_multiply(quatnorm({0.5 * eps * (j % 3 == 0), 0.5 * eps * (j % 3 == 1), 0.5 * eps * (j % 3 == 2), 1.0}), q); };
+      if (j < 3) rot(sp2.q);
+      else if (j < 6) sp2.p[(size_t)(j - 3)] += eps;
+      else if (j < 9) sp2.v[(size_t)(j - 6)] += eps;
+      else if (j < 12) sp2.bg[(size_t)(j - 9)] += eps;
+      else if (j < 15) sp2.ba[(size_t)(j - 12)] += eps;
+      else if (j < 21) sp2.dw[j - 15] += eps;
+      else if (j < 27) sp2.da[j - 21] += eps;
+      else if (j < 36) sp2.tg[j - 27] += eps;
+      else rot(sp2.q_GYROtoIMU);
+      sp2.q_fej = sp2.q, sp2.p_fej = sp2.p, sp2.v_fej = sp2.v;
+      std::vector<double> F2, Q2;
+      prop.predict_and_compute(sp2, d0, d1, F2, Q2);
+      double col[15];
+      const Vec3 dth = qerr(sp2.q, nominal.q);
+      for (int k = 0; k < 3; k++) {
+        col[k] = dth[(size_t)k] / eps;
+        col[3 + k] = (sp2.p[(size_t)k] - nominal.p[(size_t)k]) / eps;
+        col[6 + k] = (sp2.v[(size_t)k] - nominal.v[(size_t)k]) / eps;
+        col[9 + k] = (sp2.bg[(size_t)k] - nominal.bg[(size_t)k]) / eps;
+        col[12 + k] = (sp2.ba[(size_t)k] - nominal.ba[(size_t)k]) / eps;
+      }
+      for (int i = 0; i < 15; i++) {
+        maxdiff = std::max(maxdiff, std::abs(col[i] - F[(size_t)i * n + j]));
+        maxF = std::max(maxF, std::abs(F[(size_t)i * n + j]));
+      }
+    }
+    double asym = 0, mind = 1e300;
+    for (int i = 0; i < n; i++) {
+      for (int j = 0; j < n; j++)
+        asym = std::max(asym, std::abs(Qd[(size_t)i * n + j] - Qd[(size_t)j * n + i]));
+      if (i < 15)
+        mind = std::min(mind, Qd[(size_t)i * n + i]);
+    }
+    std::printf("%.6g %.6g %.6g %.6g\n", maxdiff, maxF, asym, mind);
+    return 0;
+  }
+  return 2;
+}

@@ -1,0 +1,100 @@
+"""CPU tests of the host-side rpng_sim pipeline (include/ovb200_sim.hpp, ovb200_vio.hpp): simulator, B-spline, Propagator,
+runner + ATE, with the CPU oracle as the update backend (tests/cpp/run_simulation_oracle).
+Reference: ov_msckf/src/sim/Simulator.cpp, ov_core/src/sim/BsplineSE3.cpp, ov_msckf/src/state/Propagator.cpp,
+ov_msckf/src/test_sim_repeat.cpp:134-160 (determinism), ov_eval/src/calc/ResultTrajectory.cpp:82-109 (ATE)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from open_vins_b200 import build as b
+from open_vins_b200 import simrun
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TRAJ = simrun.TRAJ_FIXTURE
+
+
+@pytest.fixture(scope="module")
+def exes(oracle):
+    eng, orc = b.build_sim_tools()
+    probe = os.path.join(ROOT, "tests", "cpp", "sim_probe")
+    src = os.path.join(ROOT, "tests", "cpp", "sim_probe.cpp")
+    if not os.path.exists(probe) or os.path.getmtime(probe) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(ROOT, "include", "ovb200_vio.hpp"))):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), src, "-L", os.path.join(ROOT, "open_vins_b200"),
+                               "-lovb200", "-Wl,-rpath,$ORIGIN/../../open_vins_b200", "-o", probe])
+    return {"engine": eng, "oracle": orc, "probe": probe}
+
+
+def _probe(exes, *args):
+    out = subprocess.run([exes["probe"]] + [str(a) for a in args], check=True, capture_output=True, text=True).stdout
+    return [np.array([float(x) for x in line.split()]) for line in out.strip().splitlines()]
+
+
+def test_undistort_matches_opencv(exes):
+    """CamRadtan::undistort_f = cv::undistortPoints (cam/CamRadtan.h:95-114): the restated 5-step fixed-point iteration
+    against the OpenCV of this image, bit for bit in float32, over the image."""
+    cv2 = pytest.importorskip("cv2")
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1.0]])
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05])
+    rng = np.random.default_rng(0)
+    for u, v in np.column_stack([rng.uniform(0, 752, 40), rng.uniform(0, 480, 40)]).astype(np.float32):
+        ref = cv2.undistortPoints(np.array([[[u, v]]], dtype=np.float32), K, D).ravel()
+        got = _probe(exes, "undistort", repr(float(u)), repr(float(v)))[0].astype(np.float32)
+        assert np.array_equal(got, ref.astype(np.float32)), (u, v, got, ref)
+        # distort(undistort(uv)) returns to the pixel within the 5-iteration accuracy
+        back = _probe(exes, "distort", repr(float(got[0])), repr(float(got[1])))[0]
+        assert np.abs(back - [u, v]).max() < 0.5  # 5 iterations leave a fraction of a pixel in the image corners (OpenCV behaves the same)
+
+
+def test_bspline_derivatives(exes):
+    """BsplineSE3::get_velocity / get_acceleration (sim/BsplineSE3.cpp:122-233) against central differences of get_pose."""
+    h = 2.0**-10  # exactly representable next to timestamps of ~1.5e9 s (ulp 2.4e-7)
+    ts = [5.015625, 12.265625, 40.015625]  # off the spline knots (multiples of 0.05 s), exact on the 2^-22 s grid
+    for t in ts:
+        lo, mid, hi = _probe(exes, "spline", TRAJ, t - h, t, t + h)
+        assert lo[0] == mid[0] == hi[0] == 1
+        p = lambda r: r[10:13]
+        v, a = mid[16:19], mid[22:25]
+        assert np.allclose((p(hi) - p(lo)) / (2 * h), v, atol=1e-4)
+        assert np.allclose((p(hi) - 2 * p(mid) + p(lo)) / h**2, a, atol=1e-4)
+        R = lambda r: r[1:10].reshape(3, 3)  # R_GtoI
+        W = R(mid) @ ((R(hi).T - R(lo).T) / (2 * h))  # R_ItoG' d/dt R_ItoG = skew(w_IinI)
+        w = np.array([W[2, 1], W[0, 2], W[1, 0]])
+        assert np.allclose(w, mid[13:16], atol=2e-4)
+
+
+@pytest.mark.parametrize("method", ["discrete", "rk4", "analytical"])
+def test_propagator_F_matches_finite_differences(exes, method):
+    """compute_F_and_G_analytic / _discrete (state/Propagator.cpp:683-950) incl. the 24 IMU-intrinsic columns: the
+    state-transition matrix equals the numerical Jacobian of the mean propagation (predict_mean_*, :482-681)."""
+    maxdiff, maxF, asym, mind = _probe(exes, "propfd", method)[0]
+    assert maxF == pytest.approx(1.0)
+    assert maxdiff < 2e-6  # O(dt^2) consistency between the mean integrator and the linearisation, dt = 2.5 ms
+    assert asym == 0.0 and mind > 0
+
+
+def test_simulation_is_repeatable_and_consistent(exes, tmp_path):
+    """ov_msckf/src/test_sim_repeat.cpp: two runs from the same seeds are bit-identical; the filter stays consistent
+    (position ATE of the 200-frame mono run well below 0.2 m, the initial 1-sigma being 5 cm)."""
+    e1, e2 = str(tmp_path / "a.txt"), str(tmp_path / "b.txt")
+    kw = dict(exe=exes["oracle"], traj=TRAJ, cams=1, clones=11, msckf=50, pts=200, frames=200)
+    r1 = simrun.run(est=e1, timing=str(tmp_path / "t.csv"), **kw)
+    r2 = simrun.run(est=e2, **kw)
+    assert open(e1).read() == open(e2).read()
+    assert r1["frames"] == 200 and r1["state_dim"] == 15 + 24 + 1 + 14 + 6 * 11
+    t, p, q, pg, qg = simrun.load_estimate(e1)
+    assert simrun.ate_rmse(p, pg) == pytest.approx(r1["ate_pos_m"], rel=1e-9)
+    assert r1["ate_pos_m"] < 0.2 and r1["ate_ori_deg"] < 1.0
+    # chi² gate at the 95 % quantile: about 5 % of the features that reach it are rejected
+    h = r1["status_hist"]
+    assert 0.01 < h[8] / (h[0] + h[8]) < 0.12
+    # timing file in the reference's CSV layout (core/VioManager.cpp:117-121)
+    rows = open(tmp_path / "t.csv").read().strip().splitlines()
+    assert rows[0].startswith("# timestamp (sec),tracking,propagation,msckf update") and len(rows) == 201
+    assert len(rows[1].split(",")) == 6
+
+
+def test_stereo_calib_off_runs(exes):
+    r = simrun.run(exe=exes["oracle"], traj=TRAJ, cams=2, clones=8, msckf=20, pts=100, frames=60, calib=0)
+    assert r["state_dim"] == 15 + 6 * 8 and r["ate_pos_m"] < 0.2
