@@ -335,6 +335,11 @@ ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_block
 /* out[0] kernels launched by the last update pipeline, out[1] of which TSQR level kernels,
  * out[2]/out[3] bytes copied host->device / device->host by the last ovb_msckf_update. */
 ovb_status ovb_last_counters(const ovb_ctx *ctx, int64_t out[4]);
+/* Per-kernel timing (measurement support): ovb_set_profile(ctx,1) brackets every kernel of the update pipeline that is
+ * launched on the context stream with CUDA events (programmatic dependent launch is off meanwhile); ovb_profile_read
+ * returns the kernels of the last update in launch order: NUL-separated mangled names and durations in microseconds. */
+ovb_status ovb_set_profile(ovb_ctx *ctx, int enabled);
+ovb_status ovb_profile_read(ovb_ctx *ctx, char *names, int name_cap, float *us, int cap, int *n);
 ovb_status ovb_set_replay(ovb_ctx *ctx, int enabled);
 ovb_status ovb_msckf_replay(ovb_ctx *ctx, int steps, int flush_l2, float *ms_per_step, float stage_ms_sum[5]);
 

@@ -72,10 +72,9 @@ def build_host_test(force: bool = False) -> str:
     return exe
 
 
-def build_sim_tools(force: bool = False, with_oracle: bool = True):
-    """rpng_sim runners (tools/run_simulation.cpp over include/ovb200_vio.hpp): the product executable
-    open_vins_b200/ovb_run_simulation (CUDA engine) and, as test infrastructure, tests/cpp/run_simulation_oracle (the CPU
-    oracle behind the same host code). Returns (engine_exe, oracle_exe or None)."""
+def build_sim_tools(force: bool = False) -> str:
+    """rpng_sim runner (tools/run_simulation.cpp over include/ovb200_vio.hpp) with the CUDA engine as backend:
+    open_vins_b200/ovb_run_simulation. (The checker twin with the CPU backend is built by the test infrastructure.)"""
     root = os.path.dirname(HERE)
     src = os.path.join(root, "tools", "run_simulation.cpp")
     inc = os.path.join(root, "include")
@@ -84,15 +83,7 @@ def build_sim_tools(force: bool = False, with_oracle: bool = True):
     exe = os.path.join(HERE, "ovb_run_simulation")
     if force or _stale(exe, [src, OUT] + hdrs):
         subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-DOVB_SIM_ENGINE", "-I", inc, src, "-L", HERE, "-lovb200", "-Wl,-rpath,$ORIGIN", "-o", exe])
-    oexe = None
-    if with_oracle:
-        odir = os.path.join(root, "oracle")
-        osrc = os.path.join(root, "tests", "cpp", "oracle_backend.hpp")
-        oexe = os.path.join(root, "tests", "cpp", "run_simulation_oracle")
-        if force or _stale(oexe, [src, osrc, OUT, os.path.join(odir, "libovoracle.so")] + hdrs):
-            subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-DOVB_SIM_ORACLE", "-I", os.path.join(root, "tests", "cpp"), "-I", inc, src, "-L", HERE,
-                                   "-lovb200", "-L", odir, "-lovoracle", "-Wl,-rpath,$ORIGIN/../../open_vins_b200", "-Wl,-rpath,$ORIGIN/../../oracle", "-o", oexe])
-    return exe, oexe
+    return exe
 
 
 if __name__ == "__main__":

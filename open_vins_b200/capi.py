@@ -279,6 +279,8 @@ def load_library(path: str | None = None) -> C.CDLL:
                                                    C.c_void_p, C.c_int, c_int_p, c_int_p]
     lib.ovb_shard_partition.argtypes = [c_int_p, C.c_int, C.c_int, c_int_p]
     lib.ovb_msckf_shard_finish.argtypes = [vp, C.c_void_p, C.c_int, C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
+    lib.ovb_set_profile.argtypes = [vp, C.c_int]
+    lib.ovb_profile_read.argtypes = [vp, C.c_char_p, C.c_int, c_float_p, C.c_int, c_int_p]
     lib.ovb_set_replay.argtypes = [vp, C.c_int]
     lib.ovb_msckf_replay.argtypes = [vp, C.c_int, C.c_int, c_float_p, C.POINTER(C.c_float * 5)]
     if path is None:
@@ -290,7 +292,7 @@ EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate", "ovb_cov_initialize",
     "ovb_msckf_update", "ovb_slam_update", "ovb_slam_anchor_change", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram", "ovb_compress_cholqr2",
-    "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters",
+    "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters", "ovb_set_profile", "ovb_profile_read",
     "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_compress_range", "ovb_shard_partition", "ovb_msckf_shard_finish",
 ]
 
@@ -519,6 +521,18 @@ class Engine:
         a = (C.c_int64 * 4)()
         self._check(self.lib.ovb_last_counters(self.h, C.byref(a)))
         return dict(launches=int(a[0]), tsqr_level_launches=int(a[1]), h2d_bytes=int(a[2]), d2h_bytes=int(a[3]))
+
+    def set_profile(self, enabled=True):
+        self._check(self.lib.ovb_set_profile(self.h, int(bool(enabled))))
+
+    def profile_read(self):
+        """[(kernel name, microseconds)] of the last update, in launch order (main-stream kernels)."""
+        buf = C.create_string_buffer(16384)
+        us = np.zeros(96, dtype=np.float32)
+        n = np.zeros(1, dtype=np.int32)
+        self._check(self.lib.ovb_profile_read(self.h, buf, len(buf), _ptr(us, c_float_p), 96, _ptr(n, c_int_p)))
+        names = buf.raw.split(b"\0")[: int(n[0])]
+        return [(nm.decode(), float(us[i])) for i, nm in enumerate(names)]
 
     def set_replay(self, enabled=True):
         self._check(self.lib.ovb_set_replay(self.h, int(enabled)))

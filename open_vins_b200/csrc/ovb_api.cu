@@ -174,6 +174,10 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
 }
 
 void ovb_destroy(ovb_ctx *ctx) {
+  if (ctx)
+    for (int i = 0; i < 2 * 96; i++)
+      if (ctx->prof_ev[i])
+        cudaEventDestroy(ctx->prof_ev[i]);
   if (!ctx)
     return;
   cudaSetDevice(ctx->device);
@@ -752,6 +756,7 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
   const int N = ctx->N;
   ctx->n_launch = 0;
   ctx->n_launch_tsqr_level = 0;
+  ctx->prof_n = 0;
   if (!slam) {
     launch_cam_poses(ctx);
     launch_triangulate(ctx, F, bv);
@@ -802,6 +807,48 @@ static int enqueue_update(ovb_ctx *ctx, int F, BlobView bv, int ldH, int max_M, 
   if (ev)
     cudaEventRecord(ev[5], ctx->stream);
   return r;
+}
+
+// Per-kernel timing of the update pipeline (bench.py's roofline block): while on, every kernel launched through
+// ovb_launch on the context stream is bracketed by CUDA events and programmatic dependent launch is disabled, so each
+// duration is that kernel alone, in stream order, with whatever the previous kernels left in L2.
+ovb_status ovb_set_profile(ovb_ctx *ctx, int enabled) {
+  if (!ctx)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (enabled && ctx->prof_ev[0] == nullptr)
+    for (int i = 0; i < 2 * 96; i++)
+      OVB_CUDA_CHECK(ctx, cudaEventCreate(&ctx->prof_ev[i]));
+  ctx->prof_on = enabled ? 1 : 0;
+  ctx->prof_n = 0;
+  return OVB_OK;
+}
+
+// kernels of the LAST update call, in launch order: names (NUL-separated, truncated to name_cap bytes in total) and their
+// durations in microseconds. *n = number of entries (<= cap). Call after the update returned (the stream is idle).
+ovb_status ovb_profile_read(ovb_ctx *ctx, char *names, int name_cap, float *us, int cap, int *n) {
+  if (!ctx || !names || !us || !n || name_cap < 1)
+    return OVB_ERR_ARG;
+  OVB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  int w = 0, k = 0;
+  for (; k < ctx->prof_n && k < cap; k++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->prof_ev[2 * k], ctx->prof_ev[2 * k + 1]) != cudaSuccess)
+      cudaGetLastError();
+    us[k] = 1e3f * ms;
+    const char *nm = nullptr;
+    if (cudaFuncGetName(&nm, ctx->prof_fn[k]) != cudaSuccess || !nm) {
+      cudaGetLastError();
+      nm = "?";
+    }
+    for (const char *c = nm; *c && w < name_cap - 2; c++)
+      names[w++] = *c;
+    names[w++] = 0;
+  }
+  if (w < name_cap)
+    names[w] = 0;
+  *n = k;
+  return OVB_OK;
 }
 
 ovb_status ovb_last_counters(const ovb_ctx *ctx, int64_t out[4]) {

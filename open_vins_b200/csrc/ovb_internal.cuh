@@ -157,6 +157,10 @@ struct ovb_ctx {
   double *d_Gpart, *d_G;
   size_t Gpart_cap, G_cap;
   size_t last_h2d_bytes, last_d2h_bytes;
+  // per-kernel profile (ovb_set_profile): CUDA events around every ovb_launch of the main stream; PDL is off while it is on
+  int prof_on, prof_n;
+  cudaEvent_t prof_ev[2 * 96];
+  const void *prof_fn[96];
 };
 
 #define OVB_CUDA_CHECK(ctx, call)                                                                                     \
@@ -221,7 +225,14 @@ static inline void ovb_launch(ovb_ctx *ctx, void (*kern)(KArgs...), dim3 grid, d
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = ctx->tsqr_pdl ? 1 : 0;
+  cfg.numAttrs = (ctx->tsqr_pdl && !ctx->prof_on) ? 1 : 0;
+  const bool prof = ctx->prof_on && ctx->prof_n < 96 && ctx->prof_ev[0] != nullptr;
+  if (prof)
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (prof) {
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], ctx->stream);
+    ctx->prof_fn[ctx->prof_n++] = (const void *)kern;
+  }
 }
 #endif

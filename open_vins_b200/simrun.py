@@ -16,6 +16,9 @@ from . import capi
 HERE = os.path.dirname(os.path.abspath(__file__))
 ENGINE_EXE = os.path.join(HERE, "ovb_run_simulation")
 TRAJ_FIXTURE = os.path.join(os.path.dirname(HERE), "tests", "golden", "traj_tum_corridor1_head.bin")
+# update cases captured from rpng_sim runs (tests/golden/make_rpng_sim_cases.py): BASELINE.json configs 1 and 2
+CASE_CONFIG1 = os.path.join(os.path.dirname(HERE), "tests", "golden", "rpng_sim_mono11_f50.case.gz")
+CASE_CONFIG2 = os.path.join(os.path.dirname(HERE), "tests", "golden", "rpng_sim_stereo20_f400.case.gz")
 
 
 def run(exe=None, traj=None, cams=2, clones=11, msckf=10, pts=250, frames=0, calib=1, est=None, timing=None, capture=None, integration="rk4",
@@ -46,7 +49,8 @@ def ate_rmse(p_est, p_gt):
 
 def load_case(path):
     """One captured MSCKF update (written by the runner's --capture): returns (FrameArrays, FeatArrays, ovb_opts, P)."""
-    with open(path, "rb") as f:
+    import gzip
+    with (gzip.open(path, "rb") if str(path).endswith(".gz") else open(path, "rb")) as f:
         hdr = f.readline().decode()
         assert hdr.startswith("OVBCASE1"), hdr
         kv = {k: int(v) for k, v in re.findall(r"(\w+)=(\d+)", hdr)}

@@ -20,7 +20,7 @@ CONFIGS = [
 
 @pytest.mark.parametrize("cfg", CONFIGS)
 def test_ate_engine_vs_oracle(oracle, tmp_path, cfg):
-    eng, orc = b.build_sim_tools()
+    eng, orc = b.build_sim_tools(), oracle.build_sim_runner()
     eg, eo = str(tmp_path / "g.txt"), str(tmp_path / "o.txt")
     rg = simrun.run(exe=eng, est=eg, **cfg)
     ro = simrun.run(exe=orc, est=eo, **cfg)

@@ -17,7 +17,7 @@ TRAJ = simrun.TRAJ_FIXTURE
 
 @pytest.fixture(scope="module")
 def exes(oracle):
-    eng, orc = b.build_sim_tools()
+    eng, orc = b.build_sim_tools(), oracle.build_sim_runner()
     probe = os.path.join(ROOT, "tests", "cpp", "sim_probe")
     src = os.path.join(ROOT, "tests", "cpp", "sim_probe.cpp")
     if not os.path.exists(probe) or os.path.getmtime(probe) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(ROOT, "include", "ovb200_vio.hpp"))):
