@@ -336,7 +336,7 @@ def bench_update(args, w: Workload, local_rank=0, dist=None, rank=0, world=1):
     import torch
     from open_vins_b200 import capi
     F = w.n_feats
-    eng = capi.Engine(max_state=w.max_state, max_feats=max(1024, F), max_meas=max(1024, F) * 64, device=local_rank)
+    eng = capi.Engine(max_state=w.max_state, max_feats=max(1024, F), max_meas=max(65536, int(w.feats.n_meas) + 1024), device=local_rank)
     eng.set_replay(True)
     K, W = args.steps, args.warmup
 

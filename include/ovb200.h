@@ -89,8 +89,8 @@ typedef enum {
                                         ~1e-6 relative, so it misses the 1e-9 parity bar there (tests/test_gpu_gram.py) */
   OVB_COMPRESS_CHOLQR2 = 2           /* shifted CholeskyQR2 on the FP64 tensor-core path (csrc/k_cholqr.cu): two Gram +
                                         Cholesky passes with a row-wise triangular solve in between. No condition-number
-                                        loss in R'R / R'z; systems wider than 159 columns fall back to the
-                                        Householder TSQR */
+                                        loss in R'R / R'z; systems wider than 159 columns use the blocked
+                                        variant (up to 512 columns), beyond that the Householder TSQR */
 } ovb_compress_mode;
 
 /* ---- context ---- */
@@ -299,7 +299,7 @@ ovb_status ovb_compress(ovb_ctx *ctx, const double *H, int m, int n, const doubl
  * rows whose pivot is at round-off level are zero. */
 ovb_status ovb_compress_gram(ovb_ctx *ctx, const double *H, int m, int n, const double *res, double *R_out, double *z_out);
 
-/* Same contract through the shifted CholeskyQR2 (OVB_COMPRESS_CHOLQR2); n <= 159, else OVB_ERR_CAPACITY. */
+/* Same contract through the shifted CholeskyQR2 (OVB_COMPRESS_CHOLQR2); n <= 512, else OVB_ERR_CAPACITY. */
 ovb_status ovb_compress_cholqr2(ovb_ctx *ctx, const double *H, int m, int n, const double *res, double *R_out, double *z_out);
 
 /* chi² 0.95 quantile table used by the gate (boost::math::quantile in the reference, UpdaterMSCKF.cpp:52-55). */

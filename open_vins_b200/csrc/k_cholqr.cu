@@ -584,25 +584,34 @@ __global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_gram(const double *__rest
 #endif
 }
 
-// EKF mode (StateHelper::EKFUpdate's LLT, state/StateHelper.cpp:160-161): S (r x r, lower triangle in global memory) with
-// the residual as right-hand-side row -> L written back over the lower triangle of S, w = L^-1 res, 1/diag(L); a
-// non-positive pivot raises info->not_spd. ldS even.
+// Block mode — EKF (StateHelper::EKFUpdate's LLT, state/StateHelper.cpp:160-161) and the diagonal blocks of the blocked
+// factorisation of wide systems: S (r x r, lower triangle in global memory), optionally with the residual as one right-hand-
+// side row (res != nullptr) -> L written back over the lower triangle of S, w = L^-1 res, 1/diag(L), the packed factor for
+// k_cq_trsm. floor_dev == nullptr: strict, a non-positive pivot raises info->not_spd; else pivots are floored at *floor_dev
+// (shifted Gram matrices). ldS even.
 __global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_ekf(double *__restrict__ S, int ldS, int r, const double *__restrict__ res, double *__restrict__ w,
-                                                          double *__restrict__ invdiag, DevUpdateInfo *__restrict__ info, double *__restrict__ Lpk) {
+                                                          double *__restrict__ invdiag, DevUpdateInfo *__restrict__ info, double *__restrict__ Lpk,
+                                                          const double *__restrict__ floor_dev) {
   OVB_PDL_ENTER();
   extern __shared__ __align__(16) unsigned char cq_raw[];
   CqCholSmem &sm = *reinterpret_cast<CqCholSmem *>(cq_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  cq_load_tiles(sm, S, (size_t)ldS, r, r + 1, res, 0);
+  const int nrows = r + (res != nullptr ? 1 : 0);
+  cq_load_tiles(sm, S, (size_t)ldS, r, nrows, res, 0);
   __syncthreads();
-  cq_chol_tiles(sm, r, r + 1, true, 0.0);
+  if (floor_dev != nullptr)
+    cq_chol_tiles(sm, r, nrows, false, *floor_dev);
+  else
+    cq_chol_tiles(sm, r, nrows, true, 0.0);
   for (int i = wid; i < r; i += CQ_CHOL_T / 32)
     for (int j = lane; j <= i; j += 32)
       S[(size_t)i * ldS + j] = cq_el(sm.T, i, j);
-  for (int j = tid; j < r; j += CQ_CHOL_T) {
-    w[j] = cq_el(sm.T, r, j);
-    invdiag[j] = sm.invd[j];
-  }
+  if (res != nullptr)
+    for (int j = tid; j < r; j += CQ_CHOL_T)
+      w[j] = cq_el(sm.T, r, j);
+  if (invdiag != nullptr)
+    for (int j = tid; j < r; j += CQ_CHOL_T)
+      invdiag[j] = sm.invd[j];
   if (Lpk != nullptr) { // the factor as k_cq_trsm consumes it (Y = M L^-T)
     const int NB = (r + 7) >> 3;
     for (int e = 2 * tid; e < tri(NB) * 64; e += 2 * CQ_CHOL_T)
@@ -610,7 +619,7 @@ __global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_ekf(double *__restrict__ 
     for (int e = tid; e < CQ_MAXB * 8; e += CQ_CHOL_T)
       Lpk[CQ_PK_INV + e] = (e < r) ? sm.invd[e] : 1.0;
   }
-  if (tid == 0 && sm.flag)
+  if (tid == 0 && sm.flag && info != nullptr)
     info->not_spd = 1;
 }
 
@@ -832,6 +841,142 @@ __global__ void __launch_bounds__(256) k_cq_trmm(const double *__restrict__ L2, 
     Rout[(size_t)i * ldR + j] = (j >= i) ? acc : 0.0;
 }
 
+// ------------------------------------------------------------------------------------------------------------ wide systems
+// C[M x N] -= A[M x K] B[N x K]'   (all row-major; DMMA). The trailing update of the blocked Cholesky (A = B = the solved
+// panel, lower_only) and the panel update of the blocked triangular solve (A = solved columns, B = rows of L).
+// CTA tile 64 x 64, 8 warps as 2 x 4 (warp tile 32 x 16), K in chunks of 32 through shared memory (cp.async, zero fill).
+#define CQ_GN_T 256
+__global__ void __launch_bounds__(CQ_GN_T) k_cq_gemm_nt(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda, const double *__restrict__ B,
+                                                       int ldb, int M, int N, int K, int lower_only) {
+  OVB_PDL_ENTER();
+  __shared__ __align__(16) double As[64][36];
+  __shared__ __align__(16) double Bs[64][36];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (lower_only && n0 > m0 + 63)
+    return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int wm = (wid >> 2) * 32, wn = (wid & 3) * 16;
+  double acc[4][2][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+      acc[a][b][0] = acc[a][b][1] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int e = tid; e < 64 * 16; e += CQ_GN_T) {
+      const int r = e >> 4, u = e & 15, k = k0 + 2 * u;
+      unsigned ba = 0, bb = 0;
+      if (m0 + r < M)
+        ba = (k + 1 < K) ? 16u : (k < K ? 8u : 0u);
+      if (n0 + r < N)
+        bb = (k + 1 < K) ? 16u : (k < K ? 8u : 0u);
+      cpa16(s_u32(&As[r][2 * u]), ba ? (const void *)(A + (size_t)(m0 + r) * lda + k) : (const void *)A, ba);
+      cpa16(s_u32(&Bs[r][2 * u]), bb ? (const void *)(B + (size_t)(n0 + r) * ldb + k) : (const void *)B, bb);
+    }
+    cpa_commit();
+    cpa_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+      double fa[4], fb[2];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+        fa[a] = As[wm + 8 * a + g][4 * ks + q];
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+        fb[b] = Bs[wn + 8 * b + g][4 * ks + q];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+          dmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int i = m0 + wm + 8 * a + g, j = n0 + wn + 8 * b + 2 * q;
+      if (i < M) {
+        double *c = C + (size_t)i * ldc + j;
+        if (j + 1 < N) {
+          double2 v = *reinterpret_cast<double2 *>(c);
+          v.x -= acc[a][b][0];
+          v.y -= acc[a][b][1];
+          *reinterpret_cast<double2 *>(c) = v;
+        } else if (j < N) {
+          c[0] -= acc[a][b][0];
+        }
+      }
+    }
+}
+
+// max diagonal of G -> G += shift_rel * max * I; *floor_out = shift / 4 (the pivot floor of the block factorisations)
+__global__ void __launch_bounds__(256) k_cq_shift(double *__restrict__ G, int ldG, int n, double shift_rel, double *__restrict__ floor_out) {
+  OVB_PDL_ENTER();
+  __shared__ double red[8];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const double d = G[(size_t)i * ldG + i];
+    mx = (d > mx) ? d : mx;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double y = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = (y > mx) ? y : mx;
+  }
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.0;
+  for (int w = 0; w < 8; w++)
+    mx = (red[w] > mx) ? red[w] : mx;
+  const double shift = shift_rel * mx;
+  for (int i = threadIdx.x; i < n; i += 256)
+    G[(size_t)i * ldG + i] += shift;
+  if (threadIdx.x == 0)
+    *floor_out = 0.25 * shift;
+}
+
+// R = R2 R1 with R1 = L1', R2 = L2' (plain row-major lower factors): Rout[i][j] = sum_{k=i..j} L2[k][i] L1[j][k], rows i < nt-1
+__global__ void __launch_bounds__(256) k_cq_trmm_wide(const double *__restrict__ L2, const double *__restrict__ L1, int ldL, int nt, double *__restrict__ Rout,
+                                                     int ldR) {
+  OVB_PDL_ENTER();
+  __shared__ double As[32][33]; // L2[k][i]
+  __shared__ double Bs[32][33]; // L1[j][k]
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int n = nt - 1;
+  double acc[4] = {0, 0, 0, 0};
+  if (tj >= ti) {
+    for (int tk = ti; tk <= tj; tk++) {
+      for (int e = tid; e < 1024; e += 256) {
+        const int a = e >> 5, b = e & 31;
+        const int k = tk * 32 + a, i = ti * 32 + b;
+        As[a][b] = (k < nt && i < nt && k >= i) ? L2[(size_t)k * ldL + i] : 0.0;
+        const int j = tj * 32 + a, k2 = tk * 32 + b;
+        Bs[a][b] = (j < nt && k2 < nt && j >= k2) ? L1[(size_t)j * ldL + k2] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < 32; kk++) {
+        const double b = Bs[tx][kk];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          acc[u] += As[kk][ty + 8 * u] * b;
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const int i = ti * 32 + ty + 8 * u, j = tj * 32 + tx;
+    if (i < n && j < nt)
+      Rout[(size_t)i * ldR + j] = (j >= i) ? acc[u] : 0.0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------ launchers
 static bool cq_attrs(ovb_ctx *ctx) {
   if (!ctx->attr_done[4]) {
@@ -876,7 +1021,7 @@ bool launch_chol_ekf_dmma(ovb_ctx *ctx, double *S, int ldS, int r, const double 
     const int ldW = CQ_MAXN + 8;
     Lpk = ctx->d_G + (size_t)3 * ldW * ldW;
   }
-  ovb_launch(ctx, k_cq_chol_ekf, dim3(1), dim3(CQ_CHOL_T), sizeof(CqCholSmem), S, ldS, r, res, w, invdiag, ctx->d_info, Lpk);
+  ovb_launch(ctx, k_cq_chol_ekf, dim3(1), dim3(CQ_CHOL_T), sizeof(CqCholSmem), S, ldS, r, res, w, invdiag, ctx->d_info, Lpk, (const double *)nullptr);
   if (Lpk_out)
     *Lpk_out = Lpk;
   return true;
@@ -896,13 +1041,147 @@ bool launch_trsm_rows(ovb_ctx *ctx, double *A, int ldA, int m, int nt, const dou
   return true;
 }
 
+// ---- wide systems (more columns than one CTA's Cholesky takes): blocked right-looking factorisation in global memory
+#define CQ_WB 128                 // diagonal block of the blocked Cholesky / column panel of the blocked solve
+#define CQ_WMAX 520               // leading dimension of the wide Gram buffers (nt <= 513)
+#define CQ_WBLOCKS ((CQ_WMAX + CQ_WB - 1) / CQ_WB)
+static bool cq_ensure_wide(ovb_ctx *ctx) {
+  const size_t need = (size_t)2 * CQ_WMAX * CQ_WMAX + (size_t)2 * CQ_WBLOCKS * CQ_PK_DOUBLES + 64;
+  if (need > ctx->cqw_cap) {
+    if (ctx->d_cqw)
+      cudaFree(ctx->d_cqw);
+    ctx->d_cqw = nullptr;
+    if (cudaMalloc(&ctx->d_cqw, sizeof(double) * need) != cudaSuccess)
+      return false;
+    ctx->cqw_cap = need;
+  }
+  return true;
+}
+static void cq_gemm_nt(ovb_ctx *ctx, double *C, int ldc, const double *A, int lda, const double *B, int ldb, int M, int N, int K, int lower_only) {
+  if (M <= 0 || N <= 0 || K <= 0)
+    return;
+  ovb_launch(ctx, k_cq_gemm_nt, dim3((N + 63) / 64, (M + 63) / 64), dim3(CQ_GN_T), (size_t)0, C, ldc, A, lda, B, ldb, M, N, K, lower_only);
+}
+static void cq_trsm_any(ovb_ctx *ctx, double *A, int ldA, int m, int nt, const double *Lpk) {
+  const int ngroups = (m + 7) / 8;
+  int ctas = (ngroups + CQ_TRSM_T / 32 - 1) / (CQ_TRSM_T / 32);
+  if (ngroups <= ctx->sm_count)
+    ctas = ngroups; // short panels: one row group per CTA (see launch_trsm_rows)
+  if (ctas > ctx->sm_count)
+    ctas = ctx->sm_count;
+  cq_launch_trsm(ctx, ctas, A, ldA, m, nt, Lpk);
+}
+// L L' = S for the leading n x n block of the (n + extra) x n lower matrix at S (extra right-hand-side rows below it are
+// solved along: they end as rhs L^-T). Lpk: CQ_WBLOCKS packed diagonal-block factors. floor_dev: see k_cq_chol_ekf.
+static void cq_chol_blocked(ovb_ctx *ctx, double *S, int ld, int n, int extra, double *Lpk, const double *floor_dev, DevUpdateInfo *info) {
+  for (int J = 0, b = 0; J < n; J += CQ_WB, b++) {
+    const int nb = (n - J < CQ_WB) ? n - J : CQ_WB;
+    double *Lb = Lpk + (size_t)b * CQ_PK_DOUBLES;
+    ovb_launch(ctx, k_cq_chol_ekf, dim3(1), dim3(CQ_CHOL_T), sizeof(CqCholSmem), S + (size_t)J * ld + J, ld, nb, (const double *)nullptr, (double *)nullptr,
+               (double *)nullptr, info, Lb, floor_dev);
+    const int mrem = n + extra - (J + nb);
+    if (mrem > 0) {
+      double *panel = S + (size_t)(J + nb) * ld + J;
+      cq_trsm_any(ctx, panel, ld, mrem, nb, Lb);
+      const int ncols = n - (J + nb);
+      cq_gemm_nt(ctx, S + (size_t)(J + nb) * ld + (J + nb), ld, panel, ld, panel, ld, mrem, ncols, nb, 1);
+    }
+  }
+}
+// X <- X (L')^-1 for the rows of X [m x n] with the blocked factor (plain L in S, packed diagonal blocks in Lpk)
+static void cq_trsm_blocked(ovb_ctx *ctx, double *X, int ldx, int m, int n, const double *S, int ld, const double *Lpk) {
+  for (int J = 0, b = 0; J < n; J += CQ_WB, b++) {
+    const int nb = (n - J < CQ_WB) ? n - J : CQ_WB;
+    if (J > 0) // X[:, J..] -= X[:, 0..J) L[J.., 0..J)'
+      cq_gemm_nt(ctx, X + J, ldx, X, ldx, S + (size_t)J * ld, ld, m, nb, J, 0);
+    cq_trsm_any(ctx, X + J, ldx, m, nb, Lpk + (size_t)b * CQ_PK_DOUBLES);
+  }
+}
+
+__global__ void k_cq_copy_row(const double *__restrict__ src, double *__restrict__ dst, int n) {
+  OVB_PDL_ENTER();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    dst[i] = src[i];
+}
+__global__ void k_cq_inv_diag(const double *__restrict__ S, int ld, int n, double *__restrict__ inv) {
+  OVB_PDL_ENTER();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double d = S[(size_t)i * ld + i];
+    inv[i] = d != 0.0 ? 1.0 / d : 0.0;
+  }
+}
+
+bool launch_chol_solve_wide(ovb_ctx *ctx, double *S, int ldS, int r, double *w, double *invdiag, double *M, int ldM, int N, bool gate_only) {
+  if (r > CQ_WMAX - 8 || (ldS & 1) || (ldM & 1) || r + 1 > ctx->cfg.max_state + 1)
+    return false;
+  cq_attrs(ctx);
+  if (!cq_ensure_wide(ctx))
+    return false;
+  double *Lpk = ctx->d_cqw + (size_t)2 * CQ_WMAX * CQ_WMAX;
+  // the residual rides as row r of S (solved along with the panels): w = L^-1 res
+  ovb_launch(ctx, k_cq_copy_row, dim3((r + 127) / 128), dim3(128), (size_t)0, (const double *)w, S + (size_t)r * ldS, r);
+  cq_chol_blocked(ctx, S, ldS, r, 1, Lpk, nullptr, ctx->d_info);
+  ovb_launch(ctx, k_cq_copy_row, dim3((r + 127) / 128), dim3(128), (size_t)0, (const double *)(S + (size_t)r * ldS), w, r);
+  ovb_launch(ctx, k_cq_inv_diag, dim3((r + 127) / 128), dim3(128), (size_t)0, (const double *)S, ldS, r, invdiag);
+  if (!gate_only)
+    cq_trsm_blocked(ctx, M, ldM, N, r, S, ldS, Lpk);
+  return true;
+}
+
+// wide CholeskyQR2: same scheme as below with the blocked factorisation / solve
+static int cq_compress_wide(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR) {
+  const int nt = n + 1;
+  if (nt > CQ_WMAX - 7 || !cq_ensure_wide(ctx))
+    return -1;
+  const int nT = (nt + 31) / 32, BW = 4, nblk_side = (nT + BW - 1) / BW, nblk = nblk_side * (nblk_side + 1) / 2;
+  int nslab = ctx->sm_count / nblk;
+  if (nslab < 1)
+    nslab = 1;
+  const int max_slabs = (m + CQ_KB - 1) / CQ_KB;
+  if (nslab > max_slabs)
+    nslab = max_slabs;
+  int slab_rows = (((m + nslab - 1) / nslab) + 3) & ~3;
+  nslab = (m + slab_rows - 1) / slab_rows;
+  const size_t need_part = (size_t)nslab * nblk * 16 * 1024;
+  if (need_part > ctx->Gpart_cap) {
+    if (ctx->d_Gpart)
+      cudaFree(ctx->d_Gpart);
+    ctx->d_Gpart = nullptr;
+    if (cudaMalloc(&ctx->d_Gpart, sizeof(double) * need_part) != cudaSuccess)
+      return -1;
+    ctx->Gpart_cap = need_part;
+  }
+  double *G1 = ctx->d_cqw, *G2 = G1 + (size_t)CQ_WMAX * CQ_WMAX, *Lpk1 = G2 + (size_t)CQ_WMAX * CQ_WMAX, *Lpk2 = Lpk1 + (size_t)CQ_WBLOCKS * CQ_PK_DOUBLES;
+  double *floor_dev = Lpk2 + (size_t)CQ_WBLOCKS * CQ_PK_DOUBLES;
+  const size_t gram_smem = sizeof(double) * 2 * CQ_KB * (size_t)(2 * BW * 32 + 4);
+  int launches = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    double *G = pass == 0 ? G1 : G2;
+    ovb_launch(ctx, k_cq_gram, dim3(nblk, nslab), dim3(CQ_GRAM_T), gram_smem, (const double *)A, ldA, m, nt, slab_rows, BW, nblk_side, ctx->d_Gpart);
+    ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, nslab, nblk, BW, nblk_side, nt, G, (int)CQ_WMAX);
+    ovb_launch(ctx, k_cq_shift, dim3(1), dim3(256), (size_t)0, G, (int)CQ_WMAX, nt, pass == 0 ? 1e-11 : 1e-13, floor_dev + pass);
+    cq_chol_blocked(ctx, G, CQ_WMAX, nt, 0, pass == 0 ? Lpk1 : Lpk2, floor_dev + pass, (DevUpdateInfo *)nullptr);
+    if (pass == 0)
+      cq_trsm_blocked(ctx, A, ldA, m, nt, G1, CQ_WMAX, Lpk1);
+    launches += 3 + 3 * ((nt + CQ_WB - 1) / CQ_WB);
+  }
+  const int nT32 = (nt + 31) / 32;
+  ovb_launch(ctx, k_cq_trmm_wide, dim3(nT32, nT32), dim3(256), (size_t)0, (const double *)G2, (const double *)G1, (int)CQ_WMAX, nt, Rout, ldR);
+  ctx->n_launch += launches + 1;
+  return launches + 1;
+}
+
 // [R | z] <- shifted CholeskyQR2 of A [m x (n+1)] (A is overwritten by Q1). Returns the number of kernels launched, or -1
 // when the system is too wide for this path (the caller falls back to the Householder TSQR).
 int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, double *Rout, int ldR) {
   const int nt = n + 1;
-  if (nt > CQ_MAXN || (ldA & 1) || m < 1)
+  if ((ldA & 1) || m < 1)
     return -1;
   cq_attrs(ctx);
+  if (nt > CQ_MAXN)
+    return cq_compress_wide(ctx, A, m, n, ldA, Rout, ldR);
   const int nT = (nt + 31) / 32; // warp tiles per side (<= 5)
   const int BW = nT, nblk_side = 1, nblk = 1;
   int nslab = ctx->sm_count;

@@ -416,6 +416,15 @@ void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r, int n, bo
   double *invdiag = ctx->d_w + ctx->cfg.max_state; // d_w holds 4 x max_state doubles: [w | 1/diag(L) | ...]
   double *Lpk = nullptr; // packed factor for the register solve (only written by the DMMA Cholesky)
   const bool dmma_chol = ctx->ekf_chol_dmma && launch_chol_ekf_dmma(ctx, ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, &Lpk);
+  // wider than one CTA's Cholesky: blocked DMMA factorisation + blocked solve (Y = M L^-T in place over M)
+  const bool wide = !dmma_chol && ctx->ekf_chol_dmma && r < ld && launch_chol_solve_wide(ctx, ctx->d_S, ld, r, ctx->d_w, invdiag, ctx->d_M, ld, N, gate_only);
+  if (wide) {
+    if (gate_only)
+      return;
+    dim3 g2w((N + EK_T - 1) / EK_T, (N + EK_T - 1) / EK_T);
+    ovb_launch(ctx, k_ekf_downdate, dim3(g2w), dim3(256), (size_t)(0), P, ld, (const double *)ctx->d_M, ld, N, r, ctx->d_w, ctx->d_dx, ctx->d_info);
+    return;
+  }
   if (!dmma_chol)
     ovb_launch(ctx, k_ekf_chol, dim3(1), dim3(EKC_THREADS), (size_t)(use_smem ? chol_bytes : 0), ctx->d_S, ld, r, ctx->d_w, ctx->d_w, invdiag, ctx->d_info, use_smem);
   if (gate_only)

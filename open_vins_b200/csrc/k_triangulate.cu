@@ -33,6 +33,20 @@ void launch_cam_poses(ovb_ctx *ctx) {
   k_cam_poses<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_frame, ctx->d_cc);
 }
 
+// Sum of one contribution per measurement IN MEASUREMENT ORDER — the order of the reference's loops over
+// feat->timestamps (feat/FeatureInitializer.cpp:58-85, :238-283, :391-419) — so that every accumulated double is the
+// reference's bit for bit: c[] holds this lane's contribution for measurement base + lane of the current 32-wide chunk,
+// `count` (warp uniform) of them are real. A butterfly sum would differ in the last bits, and the LM loop's float32 casts
+// turn such a difference into 1e-8-level jumps of p_FinG now and then (hard part 8). All lanes end
+// with the same sums.
+template <int NV> __device__ __forceinline__ void seq_add(double (&s)[NV], const double (&c)[NV], int count) {
+  for (int l = 0; l < count; l++) {
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+      s[k] += __shfl_sync(0xffffffffu, c[k], l);
+  }
+}
+
 struct Rel {
   dm3 R;  // R_AtoCi
   dv3 t;  // p_CiinA
@@ -52,18 +66,23 @@ __device__ __forceinline__ Rel rel_pose(const DevCamPoses *fr, int cam, int cl, 
 // feat/FeatureInitializer.cpp:377-423 — returns the cost, identical in all lanes
 __device__ __forceinline__ double lm_cost(const DevCamPoses *fr, const BlobView &bv, int m0, int m1, int lane, const dm3 &R_GtoA, dv3 p_AinG,
                                           double alpha, double beta, double rho) {
-  double err = 0.0;
-  for (int i = m0 + lane; i < m1; i += 32) {
-    Rel r = rel_pose(fr, bv.cam[i], bv.clone[i], R_GtoA, p_AinG);
-    double hi1 = r.R.m[0] * alpha + r.R.m[1] * beta + r.R.m[2] + rho * r.q.x;
-    double hi2 = r.R.m[3] * alpha + r.R.m[4] * beta + r.R.m[5] + rho * r.q.y;
-    double hi3 = r.R.m[6] * alpha + r.R.m[7] * beta + r.R.m[8] + rho * r.q.z;
-    float z0 = (float)(hi1 / hi3), z1 = (float)(hi2 / hi3);
-    float r0 = __fsub_rn(bv.uvn[2 * i], z0), r1 = __fsub_rn(bv.uvn[2 * i + 1], z1);
-    float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)));
-    err += (double)nrm * (double)nrm; // exact: product of two promoted floats
+  double err[1] = {0.0};
+  for (int base = m0; base < m1; base += 32) {
+    const int i = base + lane;
+    double c[1] = {0.0};
+    if (i < m1) {
+      Rel r = rel_pose(fr, bv.cam[i], bv.clone[i], R_GtoA, p_AinG);
+      double hi1 = r.R.m[0] * alpha + r.R.m[1] * beta + r.R.m[2] + rho * r.q.x;
+      double hi2 = r.R.m[3] * alpha + r.R.m[4] * beta + r.R.m[5] + rho * r.q.y;
+      double hi3 = r.R.m[6] * alpha + r.R.m[7] * beta + r.R.m[8] + rho * r.q.z;
+      float z0 = (float)(hi1 / hi3), z1 = (float)(hi2 / hi3);
+      float r0 = __fsub_rn(bv.uvn[2 * i], z0), r1 = __fsub_rn(bv.uvn[2 * i + 1], z1);
+      float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)));
+      c[0] = (double)nrm * (double)nrm; // exact: product of two promoted floats
+    }
+    seq_add<1>(err, c, min(32, m1 - base));
   }
-  return warp_sum(err);
+  return err[0];
 }
 
 __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restrict__ fr, const DevOpts *__restrict__ dop,
@@ -112,36 +131,26 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
     dv3 p_f;
     if (!op.triangulate_1d) {
       // ---- A = sum Bperp'Bperp, b = sum Ai p_CiinA (:58-85)
-      double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      double b[3] = {0, 0, 0};
-      for (int i = m0 + lane; i < m1; i += 32) {
-        Rel r = rel_pose(fr, bv.cam[i], bv.clone[i], R_GtoA, p_AinG);
-        dv3 bi = mTv3(r.R, mk3((double)bv.uvn[2 * i], (double)bv.uvn[2 * i + 1], 1.0));
-        double nb = norm3(bi);
-        bi = mk3(bi.x / nb, bi.y / nb, bi.z / nb);
-        dm3 Bp = skew3(bi);
-        dm3 Ai = mulT33(Bp, Bp);
-#pragma unroll
-        for (int k = 0; k < 9; k++)
-          A[k] += Ai.m[k];
-        dv3 Aip = mv3(Ai, r.t);
-        b[0] += Aip.x;
-        b[1] += Aip.y;
-        b[2] += Aip.z;
+      double Ab[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // A00 A01 A02 A11 A12 A22 | b0 b1 b2
+      for (int base = m0; base < m1; base += 32) {
+        const int i = base + lane;
+        double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (i < m1) {
+          Rel r = rel_pose(fr, bv.cam[i], bv.clone[i], R_GtoA, p_AinG);
+          dv3 bi = mTv3(r.R, mk3((double)bv.uvn[2 * i], (double)bv.uvn[2 * i + 1], 1.0));
+          double nb = norm3(bi);
+          bi = mk3(bi.x / nb, bi.y / nb, bi.z / nb);
+          dm3 Bp = skew3(bi);
+          dm3 Ai = mulT33(Bp, Bp);
+          dv3 Aip = mv3(Ai, r.t);
+          c[0] = Ai.m[0], c[1] = Ai.m[1], c[2] = Ai.m[2], c[3] = Ai.m[4], c[4] = Ai.m[5], c[5] = Ai.m[8];
+          c[6] = Aip.x, c[7] = Aip.y, c[8] = Aip.z;
+        }
+        seq_add<9>(Ab, c, min(32, m1 - base));
       }
-      // 6 unique entries reduced; the mirrored ones follow the same operation sequence
-      A[0] = warp_sum(A[0]);
-      A[1] = warp_sum(A[1]);
-      A[2] = warp_sum(A[2]);
-      A[4] = warp_sum(A[4]);
-      A[5] = warp_sum(A[5]);
-      A[8] = warp_sum(A[8]);
-      A[3] = A[1];
-      A[6] = A[2];
-      A[7] = A[5];
-      b[0] = warp_sum(b[0]);
-      b[1] = warp_sum(b[1]);
-      b[2] = warp_sum(b[2]);
+      // the mirrored entries of A follow the same operation sequence as their twins
+      double A[9] = {Ab[0], Ab[1], Ab[2], Ab[1], Ab[3], Ab[4], Ab[2], Ab[4], Ab[5]};
+      double b[3] = {Ab[6], Ab[7], Ab[8]};
       p_f = colpiv_solve3(A, mk3(b[0], b[1], b[2]));
       double condA = cond_sym3(A);
       if (fabs(condA) > op.max_cond_number)
@@ -155,21 +164,23 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
       dv3 ba = mk3((double)bv.uvn[2 * ameas], (double)bv.uvn[2 * ameas + 1], 1.0);
       double nba = norm3(ba);
       ba = mk3(ba.x / nba, ba.y / nba, ba.z / nba);
-      double A1 = 0.0, b1 = 0.0;
-      for (int i = m0 + lane; i < m1; i += 32) {
-        if (i == ameas)
-          continue;
-        Rel r = rel_pose(fr, bv.cam[i], bv.clone[i], R_GtoA, p_AinG);
-        dv3 bi = mTv3(r.R, mk3((double)bv.uvn[2 * i], (double)bv.uvn[2 * i + 1], 1.0));
-        double nb = norm3(bi);
-        bi = mk3(bi.x / nb, bi.y / nb, bi.z / nb);
-        dm3 Bp = skew3(bi);
-        dv3 Bb = mv3(Bp, ba);
-        A1 += dot3(Bb, Bb);
-        b1 += dot3(Bb, mv3(Bp, r.t));
+      double Ab1[2] = {0.0, 0.0};
+      for (int base = m0; base < m1; base += 32) {
+        const int i = base + lane;
+        double c[2] = {0.0, 0.0};
+        if (i < m1 && i != ameas) { // the anchor observation is skipped (:150-151): adding 0.0 leaves the sums unchanged
+          Rel r = rel_pose(fr, bv.cam[i], bv.clone[i], R_GtoA, p_AinG);
+          dv3 bi = mTv3(r.R, mk3((double)bv.uvn[2 * i], (double)bv.uvn[2 * i + 1], 1.0));
+          double nb = norm3(bi);
+          bi = mk3(bi.x / nb, bi.y / nb, bi.z / nb);
+          dm3 Bp = skew3(bi);
+          dv3 Bb = mv3(Bp, ba);
+          c[0] = dot3(Bb, Bb);
+          c[1] = dot3(Bb, mv3(Bp, r.t));
+        }
+        seq_add<2>(Ab1, c, min(32, m1 - base));
       }
-      A1 = warp_sum(A1);
-      b1 = warp_sum(b1);
+      const double A1 = Ab1[0], b1 = Ab1[1];
       double depth = b1 / A1;
       p_f = mk3(depth * ba.x, depth * ba.y, depth * ba.z);
       if (p_f.z < op.min_dist || p_f.z > op.max_dist)
@@ -199,37 +210,43 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
           for (int k = 0; k < 6; k++)
             Hs[k] = 0.0;
           g[0] = g[1] = g[2] = 0.0;
-          for (int i = m0 + lane; i < m1; i += 32) {
-            Rel r = rel_pose(fr, bv.cam[i], bv.clone[i], R_GtoA, p_AinG);
-            double hi1 = r.R.m[0] * alpha + r.R.m[1] * beta + r.R.m[2] + rho * r.q.x;
-            double hi2 = r.R.m[3] * alpha + r.R.m[4] * beta + r.R.m[5] + rho * r.q.y;
-            double hi3 = r.R.m[6] * alpha + r.R.m[7] * beta + r.R.m[8] + rho * r.q.z;
-            double h3sq = hi3 * hi3;
-            double H0[3], H1[3];
-            H0[0] = (r.R.m[0] * hi3 - hi1 * r.R.m[6]) / h3sq;
-            H0[1] = (r.R.m[1] * hi3 - hi1 * r.R.m[7]) / h3sq;
-            H0[2] = (r.q.x * hi3 - hi1 * r.q.z) / h3sq;
-            H1[0] = (r.R.m[3] * hi3 - hi2 * r.R.m[6]) / h3sq;
-            H1[1] = (r.R.m[4] * hi3 - hi2 * r.R.m[7]) / h3sq;
-            H1[2] = (r.q.y * hi3 - hi2 * r.q.z) / h3sq;
-            float z0 = (float)(hi1 / hi3), z1 = (float)(hi2 / hi3);
-            double rd0 = (double)__fsub_rn(bv.uvn[2 * i], z0), rd1 = (double)__fsub_rn(bv.uvn[2 * i + 1], z1);
+          double Hg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // Hess 00 01 02 11 12 22 | grad 0 1 2
+          for (int base = m0; base < m1; base += 32) {
+            const int i = base + lane;
+            double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (i < m1) {
+              Rel r = rel_pose(fr, bv.cam[i], bv.clone[i], R_GtoA, p_AinG);
+              double hi1 = r.R.m[0] * alpha + r.R.m[1] * beta + r.R.m[2] + rho * r.q.x;
+              double hi2 = r.R.m[3] * alpha + r.R.m[4] * beta + r.R.m[5] + rho * r.q.y;
+              double hi3 = r.R.m[6] * alpha + r.R.m[7] * beta + r.R.m[8] + rho * r.q.z;
+              double h3sq = hi3 * hi3;
+              double H0[3], H1[3];
+              H0[0] = (r.R.m[0] * hi3 - hi1 * r.R.m[6]) / h3sq;
+              H0[1] = (r.R.m[1] * hi3 - hi1 * r.R.m[7]) / h3sq;
+              H0[2] = (r.q.x * hi3 - hi1 * r.q.z) / h3sq;
+              H1[0] = (r.R.m[3] * hi3 - hi2 * r.R.m[6]) / h3sq;
+              H1[1] = (r.R.m[4] * hi3 - hi2 * r.R.m[7]) / h3sq;
+              H1[2] = (r.q.y * hi3 - hi2 * r.q.z) / h3sq;
+              float z0 = (float)(hi1 / hi3), z1 = (float)(hi2 / hi3);
+              double rd0 = (double)__fsub_rn(bv.uvn[2 * i], z0), rd1 = (double)__fsub_rn(bv.uvn[2 * i + 1], z1);
+              c[0] = H0[0] * H0[0] + H1[0] * H1[0];
+              c[1] = H0[0] * H0[1] + H1[0] * H1[1];
+              c[2] = H0[0] * H0[2] + H1[0] * H1[2];
+              c[3] = H0[1] * H0[1] + H1[1] * H1[1];
+              c[4] = H0[1] * H0[2] + H1[1] * H1[2];
+              c[5] = H0[2] * H0[2] + H1[2] * H1[2];
 #pragma unroll
-            for (int a = 0; a < 3; a++)
-              g[a] += H0[a] * rd0 + H1[a] * rd1;
-            Hs[0] += H0[0] * H0[0] + H1[0] * H1[0];
-            Hs[1] += H0[0] * H0[1] + H1[0] * H1[1];
-            Hs[2] += H0[0] * H0[2] + H1[0] * H1[2];
-            Hs[3] += H0[1] * H0[1] + H1[1] * H1[1];
-            Hs[4] += H0[1] * H0[2] + H1[1] * H1[2];
-            Hs[5] += H0[2] * H0[2] + H1[2] * H1[2];
+              for (int a = 0; a < 3; a++)
+                c[6 + a] = H0[a] * rd0 + H1[a] * rd1;
+            }
+            seq_add<9>(Hg, c, min(32, m1 - base));
           }
 #pragma unroll
           for (int k = 0; k < 6; k++)
-            Hs[k] = warp_sum(Hs[k]);
+            Hs[k] = Hg[k];
 #pragma unroll
           for (int k = 0; k < 3; k++)
-            g[k] = warp_sum(g[k]);
+            g[k] = Hg[6 + k];
         }
         double Hl[9] = {Hs[0] * (1.0 + lam), Hs[1], Hs[2], Hs[1], Hs[3] * (1.0 + lam), Hs[4], Hs[2], Hs[4], Hs[5] * (1.0 + lam)};
         dv3 dx = colpiv_solve3(Hl, mk3(g[0], g[1], g[2]));

@@ -185,7 +185,7 @@ void ovb_destroy(ovb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
   void *dev[] = {ctx->P[0],   ctx->P[1], ctx->d_arena, ctx->d_cc, ctx->d_feat_order, ctx->d_info, ctx->d_chi2_table, ctx->d_Hs, ctx->d_W[0],
                  ctx->d_W[1], ctx->d_R,  ctx->d_R2,    ctx->d_M,  ctx->d_S,          ctx->d_Y,    ctx->d_w,          ctx->d_scratch,
-                 ctx->d_dump, ctx->P_snap, ctx->d_flush, ctx->d_Gpart, ctx->d_G};
+                 ctx->d_dump, ctx->P_snap, ctx->d_flush, ctx->d_Gpart, ctx->d_G, ctx->d_cqw};
   for (void *p : dev)
     if (p)
       cudaFree(p);
@@ -1402,9 +1402,8 @@ ovb_status ovb_ekf_update(ovb_ctx *ctx, const int *off, const int *sz, int nvar,
   }
   if (r > n) {
     // more rows than columns: compress first (identical update, UpdaterMSCKF.cpp:275 does the same before EKFUpdate)
-    launch_tsqr(ctx, ctx->d_Hs, r, n, ld, ctx->d_R, ld);
+    rr = compress_system(ctx, OVB_COMPRESS_CHOLQR2, ctx->d_Hs, r, n, ld, ctx->d_R, ld);
     Hdev = ctx->d_R;
-    rr = n;
   }
   ovb_launch(ctx, k_take_z, dim3((rr + 127) / 128), dim3(128), (size_t)(0), Hdev, ld, rr, n, ctx->d_w);
   // k_take_z reads column n: for the uncompressed case that is the staged residual column

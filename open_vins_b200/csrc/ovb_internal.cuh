@@ -156,6 +156,8 @@ struct ovb_ctx {
   // normal-equations compression (k_gram.cu)
   double *d_Gpart, *d_G;
   size_t Gpart_cap, G_cap;
+  double *d_cqw; // wide systems (k_cholqr.cu): [G1 | G2 | packed diagonal-block factors | scalars]
+  size_t cqw_cap;
   size_t last_h2d_bytes, last_d2h_bytes;
   // per-kernel profile (ovb_set_profile): CUDA events around every ovb_launch of the main stream; PDL is off while it is on
   int prof_on, prof_n;
@@ -191,6 +193,9 @@ int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, doub
 bool launch_chol_ekf_dmma(ovb_ctx *ctx, double *S, int ldS, int r, const double *res, double *w, double *invdiag, double **Lpk_out);
 // A <- A (L')^-1 for the rows of A [m x nt] with the packed factor of the DMMA Cholesky; false when it does not fit
 bool launch_trsm_rows(ovb_ctx *ctx, double *A, int ldA, int m, int nt, const double *Lpk);
+// wide EKF (r > 160): blocked DMMA Cholesky of S (r x r lower, residual staged in w) and Y = M L^-T in place; false when r
+// exceeds OVB_MAX_COLS or the leading dimensions are odd
+bool launch_chol_solve_wide(ovb_ctx *ctx, double *S, int ldS, int r, double *w, double *invdiag, double *M, int ldM, int N, bool gate_only);
 void launch_reorder_R(ovb_ctx *ctx, const double *Rin, int n_all, int ldRin, double *Rout, int ldRout);
 // EKF update from an upper-trapezoidal / dense H [r x n] with column->state map in d_info (device-side sizes)
 void launch_ekf_update(ovb_ctx *ctx, const double *H, int ldHm, int r_max, int n_max, bool sizes_from_info, double sigma2,

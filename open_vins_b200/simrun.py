@@ -22,10 +22,10 @@ CASE_CONFIG2 = os.path.join(os.path.dirname(HERE), "tests", "golden", "rpng_sim_
 
 
 def run(exe=None, traj=None, cams=2, clones=11, msckf=10, pts=250, frames=0, calib=1, est=None, timing=None, capture=None, integration="rk4",
-        timeout=1800):
+        compress="cholqr2", timeout=1800):
     """Runs the simulation; returns the parsed JSON summary. capture = (frame_index, path_prefix) dumps that update's inputs."""
     cmd = [exe or ENGINE_EXE, "--traj", traj or TRAJ_FIXTURE, "--cams", str(cams), "--clones", str(clones), "--msckf", str(msckf), "--pts", str(pts),
-           "--frames", str(frames), "--calib", str(int(calib)), "--integration", integration]
+           "--frames", str(frames), "--calib", str(int(calib)), "--integration", integration, "--compress", compress]
     if est:
         cmd += ["--est", est]
     if timing:

@@ -89,8 +89,8 @@ def test_compress_cholqr2_zero_and_capacity(eng):
     H = np.zeros((50, 12))
     R, z = eng.compress(H, np.zeros(50), mode=capi.COMPRESS_CHOLQR2)
     assert not R.any() and not z.any()
-    with pytest.raises(capi.OvbError):
-        eng.compress(np.ones((400, 160)), np.ones(400), mode=capi.COMPRESS_CHOLQR2)
+    with pytest.raises(capi.OvbError):  # wider than the wide path as well (n + 1 > 513)
+        eng.compress(np.ones((600, 520)), np.ones(600), mode=capi.COMPRESS_CHOLQR2)
 
 
 CASES = [
@@ -156,3 +156,80 @@ def test_ekf_not_spd_leaves_P(eng):
     assert st == capi.OVB_ERR_NOT_SPD
     assert np.array_equal(eng.cov_get(), P)
     assert not dx.any()
+
+
+# ---------------------------------------------------------------------------------------------------------------- wide systems
+@pytest.fixture(scope="module")
+def eng_wide():
+    e = capi.Engine(max_state=640, max_feats=256, max_meas=8192, max_rows=16384)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("shape", [(700, 160), (3000, 200), (8000, 243), (6000, 317), (8000, 500), (1200, 511), (300, 400)])
+def test_compress_cholqr2_wide(eng_wide, shape):
+    """More columns than one CTA's Cholesky takes (configs 4 and 5): blocked DMMA factorisation / solve. Same invariants."""
+    m, n = shape
+    rng = np.random.default_rng(m + 3 * n)
+    H = rng.standard_normal((m, n))
+    res = rng.standard_normal(m)
+    R, z = eng_wide.compress(H, res, mode=capi.COMPRESS_CHOLQR2)
+    assert np.array_equal(np.tril(R, -1), np.zeros_like(R)) and (np.diag(R) >= 0).all() and np.isfinite(R).all() and np.isfinite(z).all()
+    G = H.T @ H
+    assert np.linalg.norm(R.T @ R - G) <= 1e-12 * np.linalg.norm(G)
+    assert np.linalg.norm(R.T @ z - H.T @ res) <= 1e-12 * np.linalg.norm(H) * np.linalg.norm(res)
+    if m > 2 * n:
+        Rq = np.linalg.qr(np.column_stack([H, res]), mode="r")
+        sgn = np.sign(np.diag(Rq)[:n])
+        assert np.abs(R - sgn[:, None] * Rq[:n, :n]).max() <= 1e-10 * np.abs(Rq).max()
+        assert np.abs(z - sgn * Rq[:n, n]).max() <= 1e-10 * np.abs(Rq).max()
+
+
+def test_compress_cholqr2_wide_ill_conditioned(eng_wide):
+    m, n, kappa = 5000, 300, 1e6
+    rng = np.random.default_rng(11)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    H = (U * np.logspace(0, -np.log10(kappa), n)) @ V.T
+    H *= np.logspace(0, -3, n)[rng.permutation(n)] * 300.0
+    res = rng.standard_normal(m)
+    R, z = eng_wide.compress(H, res, mode=capi.COMPRESS_CHOLQR2)
+    Rq = np.linalg.qr(np.column_stack([H, res]), mode="r")
+    A = rng.standard_normal((n, n))
+    P = A @ A.T / n + 1e-2 * np.eye(n)
+    Pp, dx = _posterior(R, z, P)
+    Ph, dxh = _posterior(Rq[:n, :n], Rq[:n, n], P)
+    assert np.linalg.norm(Pp - Ph) <= 1e-9 * np.linalg.norm(Ph)
+    assert np.linalg.norm(dx - dxh) <= 1e-9 * np.linalg.norm(dxh)
+
+
+@pytest.mark.parametrize("r", [161, 200, 256, 257, 384, 500])
+def test_ekf_wide_sizes(eng_wide, oracle, r):
+    """EKFUpdate with an innovation covariance wider than 160: blocked Cholesky + blocked gain solve."""
+    N = 520
+    rng = np.random.default_rng(r)
+    A = rng.standard_normal((N, N))
+    P = A @ A.T / N + 1e-3 * np.eye(N)
+    off, sz, n = [4], [r + 3], r + 3
+    H = rng.standard_normal((r, n))
+    res = rng.standard_normal(r)
+    st_r, P_r, dx_r = oracle.ekf_update(P, off, sz, H, res, sigma2=0.5)
+    eng_wide.cov_set(P)
+    st_g, dx_g = eng_wide.ekf_update(off, sz, H, res, sigma2=0.5)
+    P_g = eng_wide.cov_get()
+    assert st_g == st_r == capi.OVB_OK
+    assert np.linalg.norm(P_g - P_r) <= 1e-10 * np.linalg.norm(P_r)
+    assert np.linalg.norm(dx_g - dx_r) <= 1e-9 * np.linalg.norm(dx_r)
+    assert np.array_equal(P_g, P_g.T)
+
+
+def test_config4_msckf_cholqr2(eng_wide, oracle):
+    """Config-4 window (4 cameras, 31 clone poses, full calibration: 242 stacked columns) through the wide CholeskyQR2."""
+    ms = sim.make_update_case(n_feats=60, n_clones=31, n_cams=4, seed=4, calib_ext=True, calib_intr=True)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1, col_order=capi.COLS_CANONICAL, compress=capi.COMPRESS_CHOLQR2)
+    eng_wide.cov_set(ms.P)
+    st, out, dx, stats = eng_wide.msckf_update(ms.frame, ms.feats, opts)
+    ref = oracle.msckf_update(ms.frame, ms.feats, opts, ms.P, dumps=False)
+    assert st == ref["status"] == 0 and np.array_equal(out.status, ref["out"].status) and stats.cols_stacked == 242
+    assert np.linalg.norm(eng_wide.cov_get() - ref["P"]) <= 1e-9 * np.linalg.norm(ref["P"])
+    assert np.linalg.norm(dx - ref["dx"]) <= 1e-9 * np.linalg.norm(ref["dx"])

@@ -44,11 +44,12 @@ def test_triangulation_parity(eng, oracle, cfg, tri1d):
     assert ok.sum() >= 0.5 * len(ok)
     rel = np.linalg.norm(got.p_FinG[ok] - ref.p_FinG[ok], axis=1) / np.linalg.norm(ref.p_FinG[ok], axis=1)
     relA = np.linalg.norm(got.p_FinA[ok] - ref.p_FinA[ok], axis=1) / np.linalg.norm(ref.p_FinA[ok], axis=1)
-    # 1e-12 bar; a float32 rounding flip inside the LM loop (SURVEY.md hard part 8) may move a feature by ~1e-8:
-    # tolerate at most 1% of features above the bar and none above 1e-6
-    bad = (rel > 1e-12) | (relA > 1e-12)
-    assert bad.mean() <= 0.01, f"{bad.sum()} of {ok.sum()} features above 1e-12 (max {rel.max():.3e})"
-    assert rel.max() < 1e-6 and relA.max() < 1e-6
+    # BASELINE.json: triangulated points within 1e-12 rel, for EVERY feature. The kernel accumulates in the reference's
+    # measurement order (seq_add, csrc/k_triangulate.cu), so the float32 casts inside the LM loop see the same doubles as the
+    # oracle and no rounding flip can separate the two (round 1 tolerated 1 % outliers up to 1e-6 from butterfly sums)
+    assert rel.max() <= 1e-12 and relA.max() <= 1e-12, f"max rel {rel.max():.3e} / {relA.max():.3e}"
+    exact = np.all(got.p_FinG[ok] == ref.p_FinG[ok], axis=1).mean()
+    assert exact >= 0.99, f"only {exact:.3f} of the features bit-identical" 
 
 
 @pytest.mark.parametrize("cfg", CASES[:4])
@@ -209,7 +210,7 @@ def test_full_update_parity(eng, oracle, cfg, order):
     assert np.array_equal(out.status, ref["out"].status)
     ok = ref["out"].status == 0
     rel = np.linalg.norm(out.p_FinG[ok] - ref["out"].p_FinG[ok], axis=1) / np.linalg.norm(ref["out"].p_FinG[ok], axis=1)
-    assert (rel > 1e-12).mean() <= 0.01 and rel.max() < 1e-6
+    assert rel.max() <= 1e-12
     seen = np.isfinite(ref["out"].chi2)
     assert np.allclose(out.chi2[seen], ref["out"].chi2[seen], rtol=1e-8)
     assert stats.n_feats_used == ref["stats"].n_feats_used and stats.rows_stacked == ref["stats"].rows_stacked

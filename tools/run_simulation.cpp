@@ -18,7 +18,7 @@ using namespace ovb200;
 static void write_blob(FILE *f, const void *p, size_t bytes) { std::fwrite(p, 1, bytes, f); }
 
 int main(int argc, char **argv) {
-  std::string traj, est_path, timing_path, capture_prefix, integration = "rk4";
+  std::string traj, est_path, timing_path, capture_prefix, integration = "rk4", compress = "cholqr2";
   int cams = 2, clones = 11, msckf = 10, pts = 250, frames = 0, calib = 1, capture_frame = -1;
   for (int i = 1; i < argc; i++) {
     auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : ""); };
@@ -33,6 +33,7 @@ int main(int argc, char **argv) {
     else if (a == "--est") est_path = next();
     else if (a == "--timing") timing_path = next();
     else if (a == "--integration") integration = next();
+    else if (a == "--compress") compress = next();
     else if (a == "--capture") { capture_frame = std::stoi(next()); capture_prefix = next(); }
   }
   std::vector<std::array<double, 8>> traj_data =
@@ -50,6 +51,7 @@ int main(int argc, char **argv) {
   vo.max_clone_size = clones;
   vo.max_msckf_in_update = msckf;
   vo.do_calib_camera_pose = vo.do_calib_camera_intrinsics = vo.do_calib_camera_timeoffset = vo.do_calib_imu_intrinsics = vo.do_calib_imu_g_sensitivity = calib != 0;
+  vo.compress = compress == "tsqr" ? OVB_COMPRESS_HOUSEHOLDER_TSQR : (compress == "gram" ? OVB_COMPRESS_NORMAL_EQUATIONS : OVB_COMPRESS_CHOLQR2);
   vo.integration_method = integration == "discrete" ? INTEGRATION_DISCRETE : (integration == "analytical" ? INTEGRATION_ANALYTICAL : INTEGRATION_RK4);
   try {
     Simulator sim(sp, traj_data);
