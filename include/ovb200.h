@@ -259,6 +259,21 @@ typedef struct {
 ovb_status ovb_slam_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_landmarks *landmarks,
                            const ovb_opts *opts, ovb_feat_out *out, double *dx, ovb_stats *stats);
 
+/* UpdaterSLAM::delayed_init (update/UpdaterSLAM.cpp:61-251) in ONE call: triangulate + Gauss-Newton every new track (:118-142),
+ * then, one feature after the other like the reference (each StateHelper::initialize mutates the covariance AND the state
+ * mean that the next feature's Jacobians are evaluated at): full Jacobians (:197-219) -> StateHelper::initialize (Givens
+ * split, Mahalanobis gate, covariance augmentation, EKF update; state/StateHelper.cpp:393-577). After every accepted
+ * feature `on_init` is called: the host applies Type::update(dx) to its State (dx has the NEW covariance size, the landmark's
+ * block at lm_off included), sets the new Landmark to its triangulated value (+) dx_new, and REFRESHES the arrays `frame`
+ * points to (clone poses, calibration) — the engine re-reads them for the next feature. Landmark representations:
+ * ovb_opts.feat_rep = GLOBAL_3D .. ANCHORED_MSCKF_INVERSE_DEPTH (the 1-wide ANCHORED_INVERSE_DEPTH_SINGLE keeps the staged
+ * route of INTEGRATION.md §3b). sigma_pix / chi2_multipler: per-feature class values (aruco vs slam options, :225-228) or NULL
+ * for ovb_opts'. out->status: OVB_FEAT_OK = initialised, a triangulation status, or OVB_FEAT_CHI2 (gate); lm_off_out[f] = the
+ * new landmark's covariance id or -1. */
+typedef void (*ovb_init_callback)(void *user, int feat_index, int lm_off, int lm_size, const double *dx_new, const double *dx, int n_dx);
+ovb_status ovb_slam_delayed_init(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, const double *sigma_pix,
+                                 const double *chi2_multipler, ovb_init_callback on_init, void *user, ovb_feat_out *out, int32_t *lm_off_out);
+
 /* UpdaterSLAM::perform_anchor_change (update/UpdaterSLAM.cpp:506-647), host math only (no context, no GPU work): re-express an
  * anchored landmark (ovb_opts.feat_rep = one of the ANCHORED_* representations) in a new anchor camera/clone and return
  *   new_value / new_value_fej [3]  the landmark's xyz in the new anchor frame (Landmark::set_from_xyz),

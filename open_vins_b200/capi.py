@@ -98,6 +98,9 @@ class ovb_stats(C.Structure):
                 ("ms_total", C.c_float)]
 
 
+INIT_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
+
+
 def _ptr(a: np.ndarray | None, typ):
     if a is None:
         return C.cast(None, typ)
@@ -260,6 +263,8 @@ def load_library(path: str | None = None) -> C.CDLL:
                                            C.c_int, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p, c_int_p]
     lib.ovb_slam_update.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_landmarks), C.POINTER(ovb_opts),
                                     C.POINTER(ovb_feat_out), c_double_p, C.POINTER(ovb_stats)]
+    lib.ovb_slam_delayed_init.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts), c_double_p, c_double_p, INIT_CALLBACK,
+                                          C.c_void_p, C.POINTER(ovb_feat_out), c_int_p]
     lib.ovb_triangulate.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts),
                                     C.POINTER(ovb_feat_out)]
     lib.ovb_feature_jacobians.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts),
@@ -291,7 +296,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate", "ovb_cov_initialize",
-    "ovb_msckf_update", "ovb_slam_update", "ovb_slam_anchor_change", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram", "ovb_compress_cholqr2",
+    "ovb_msckf_update", "ovb_slam_update", "ovb_slam_delayed_init", "ovb_slam_anchor_change", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram", "ovb_compress_cholqr2",
     "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters", "ovb_set_profile", "ovb_profile_read",
     "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_compress_range", "ovb_shard_partition", "ovb_msckf_shard_finish",
 ]
@@ -438,6 +443,22 @@ class Engine:
                                       _ptr(dx, c_double_p), C.byref(stats))
         self._check(st, allow=(OVB_ERR_NEG_DIAG,))
         return st, out, dx, stats
+
+    def slam_delayed_init(self, frame: FrameArrays, feats: FeatArrays, opts: ovb_opts, on_init=None, sigma_pix=None, chi2_multipler=None):
+        """UpdaterSLAM::delayed_init in one call. on_init(feat_index, lm_off, dx_new, dx) must apply dx to the caller's state and
+        refresh the arrays of `frame` IN PLACE. Returns (FeatOut, lm_off array)."""
+        out = FeatOut(feats.n_feats)
+        lm_off = np.full(feats.n_feats, -1, dtype=np.int32)
+
+        def _cb(user, f, off, size, dxn, dx, n):
+            if on_init is not None:
+                on_init(int(f), int(off), np.ctypeslib.as_array(dxn, shape=(size,)).copy(), np.ctypeslib.as_array(dx, shape=(n,)).copy())
+        cb = INIT_CALLBACK(_cb)
+        sp = None if sigma_pix is None else np.ascontiguousarray(sigma_pix, dtype=np.float64)
+        cm = None if chi2_multipler is None else np.ascontiguousarray(chi2_multipler, dtype=np.float64)
+        self._check(self.lib.ovb_slam_delayed_init(self.h, C.byref(frame.struct()), C.byref(feats.struct()), C.byref(opts), _ptr(sp, c_double_p),
+                                                   _ptr(cm, c_double_p), cb, None, C.byref(out.struct()), _ptr(lm_off, c_int_p)))
+        return out, lm_off
 
     def triangulate(self, frame: FrameArrays, feats: FeatArrays, opts: ovb_opts):
         out = FeatOut(feats.n_feats)

@@ -31,7 +31,7 @@
 #define CQ_GRAM_T 512    // threads of k_cq_gram (16 warps, one 32x32 output tile each)
 #define CQ_KB 32         // rows per staged chunk in k_cq_gram
 #define CQ_CHOL_T 384
-#define CQ_CHOL_NA 4     // look-ahead warps of the Cholesky
+#define CQ_CHOL_NA 5     // look-ahead warps of the Cholesky
 #define CQ_XP 12         // pitch of the panel buffer (conflict-free 8x4 fragments)
 #define CQ_TRSM_T 640
 
@@ -95,7 +95,7 @@ __device__ __forceinline__ bool cq_tile_origin(int blk, int w, int BW, int nblk_
 // both DMMA operands are the SAME fragment pattern X[k0 + (lane&3)][c0 + (lane>>2)] of the staged rows, so one staged
 // chunk feeds the row- and the column-side of every tile. grid = (upper blocks, slabs).
 __global__ void __launch_bounds__(CQ_GRAM_T) k_cq_gram(const double *__restrict__ A, int ldA, int m, int nt, int slab_rows, int BW, int nblk_side,
-                                                      double *__restrict__ Gpart) {
+                                                      double *__restrict__ Gpart, int cs) {
   OVB_PDL_ENTER();
   extern __shared__ __align__(16) double gsm[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -182,14 +182,52 @@ __global__ void __launch_bounds__(CQ_GRAM_T) k_cq_gram(const double *__restrict_
     }
     __syncthreads();
   }
+  if (cs <= 1) {
+    if (active) {
+      double *dst = Gpart + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + wid) * 1024;
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          *reinterpret_cast<double2 *>(dst + (8 * a + g) * 32 + 8 * b + 2 * q) = make_double2(acc[a][b][0], acc[a][b][1]);
+    }
+    return;
+  }
+  // ---- cluster of `cs` slabs (cluster dims (1, cs, 1)): the partial tiles meet in distributed shared memory, each CTA sums
+  // 1/cs of every tile in rank order (fixed order: bitwise reproducible) and only the cluster's sum goes to global memory —
+  // cs times less partial traffic for the reduction kernel to read back
+  double *stage = gsm; // the pipeline buffers are free now (the loop ended with a barrier): [16 warps][1024]
   if (active) {
-    double *dst = Gpart + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + wid) * 1024;
+    double *dst = stage + (size_t)wid * 1024;
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
       for (int b = 0; b < 4; b++)
         *reinterpret_cast<double2 *>(dst + (8 * a + g) * 32 + 8 * b + 2 * q) = make_double2(acc[a][b][0], acc[a][b][1]);
   }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (active) {
+    const int per = 1024 / cs; // elements of each tile this CTA sums
+    double *dst = Gpart + ((((size_t)blockIdx.y / cs) * gridDim.x + blockIdx.x) * 16 + wid) * 1024 + (size_t)rank * per;
+    const unsigned base = s_u32(stage + (size_t)wid * 1024 + (size_t)rank * per);
+    for (int e = lane; e < per; e += 32) {
+      double sum = 0.0;
+      for (int r = 0; r < cs; r++) {
+        unsigned ra;
+        double v;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(base + 8u * (unsigned)e), "r"((unsigned)r));
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+        sum += v;
+      }
+      dst[e] = sum;
+    }
+  }
+  // nobody leaves while a peer may still read its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // G[i][j] = sum over slabs in a FIXED order (bitwise reproducible), for i <= j, mirrored. grid = (16 warp tiles x 8 chunks
@@ -415,12 +453,13 @@ __device__ __forceinline__ void cq_tile_mma_store(CqTileOps &o) {
 // The factorisation proper, on a tile-packed lower triangle already in shared memory. n columns, nrows = n + extra rows.
 __device__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, bool strict, double floor_d) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // look-ahead group = the warps of sub-partition 0 (wid % 4 == 0): the pivot chain then never queues behind the other
-  // warps' DMMAs in the FP64 pipe of its sub-partition
-  constexpr int NW = CQ_CHOL_T / 32, NA = NW / 4, NBW = NW - NA;
-  const bool inA = (wid & 3) == 0;
-  const int widA = wid >> 2, tidA = widA * 32 + lane;  // rank inside the look-ahead group
-  const int widB = wid - (wid >> 2) - 1;               // rank among the other warps
+  // look-ahead group = warps 0..NA-1 (NA * 32 >= 152 rows: one panel row per thread at the widest step). The FP64/DMMA pipe
+  // is ONE unit shared by the four sub-partitions of an SM (tools/ubench/cholqr_bench.cu: a lone warp's DMMA chain slows
+  // down 3x as soon as other sub-partitions issue FP64 work), so no warp placement isolates the pivot chain.
+  constexpr int NW = CQ_CHOL_T / 32, NA = CQ_CHOL_NA, NBW = NW - NA;
+  const bool inA = wid < NA;
+  const int widA = wid, tidA = tid; // rank inside the look-ahead group
+  const int widB = wid - NA;        // rank among the other warps
 #ifdef CQ_PROBE
   long long p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0;
 #endif
@@ -490,7 +529,7 @@ __device__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, bool strict, dou
     __syncthreads();
     CQ_PROBE_T(p6);
 #ifdef CQ_PROBE
-    if ((k == 0 || k == 8 || k == 16) && (tid == 0 || tid == 32 || tid == 128 || tid == CQ_CHOL_T - 32)) {
+    if ((k == 0 || k == 8 || k == 16) && (tid == 0 || tid == 32 || tid == NA * 32 || tid == CQ_CHOL_T - 32)) {
       if (inA)
         printf("chol k=%d tid=%d A: tiles %lld bar %lld diag %lld bar %lld panel %lld wait %lld | step %lld\n", k, tid, p1 - p0, p2 - p1, p3 - p2, p4 - p3,
                p5 - p4, p6 - p5, p6 - p0);
@@ -734,7 +773,9 @@ __global__ void __launch_bounds__(CQ_TRSM_T) k_cq_trsm(double *__restrict__ A, i
   __syncthreads();
   double *xs = Xs + (size_t)wid * (CQ_TRSM_NH * 2 * 32);
   const int ngroups = (m + 7) >> 3;
-  for (int rg = blockIdx.x * (CQ_TRSM_T / 32) + wid; rg < ngroups; rg += gridDim.x * (CQ_TRSM_T / 32)) {
+  // row groups are dealt round-robin over the CTAs first (warp w of CTA b takes group b + w * gridDim.x): a short matrix puts
+  // one group on each SM instead of twenty on the first
+  for (int rg = blockIdx.x + gridDim.x * wid; rg < ngroups; rg += gridDim.x * (CQ_TRSM_T / 32)) {
     const int row = 8 * rg + g;
     const bool row_ok = row < m;
     double *arow = A + (size_t)row * ldA;
@@ -978,6 +1019,41 @@ __global__ void __launch_bounds__(256) k_cq_trmm_wide(const double *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------ launchers
+#define CQ_GRAM_CS 4 // slabs per cluster in k_cq_gram
+// launch k_cq_gram over nslab_padded slabs (a multiple of CQ_GRAM_CS) as clusters of CQ_GRAM_CS along y
+static void cq_launch_gram(ovb_ctx *ctx, int nblk, int nslab_padded, size_t smem, const double *A, int ldA, int m, int nt, int slab_rows, int BW, int nblk_side,
+                           double *Gpart, int cs) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nblk, nslab_padded);
+  cfg.blockDim = dim3(CQ_GRAM_T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (ctx->tsqr_pdl && !ctx->prof_on) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  if (cs > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 1;
+    at[na].val.clusterDim.y = cs;
+    at[na].val.clusterDim.z = 1;
+    na++;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  const bool prof = ctx->prof_on && ctx->prof_n < 96 && ctx->prof_ev[0] != nullptr;
+  if (prof)
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
+  cudaLaunchKernelEx(&cfg, k_cq_gram, A, ldA, m, nt, slab_rows, BW, nblk_side, Gpart, cs);
+  if (prof) {
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], ctx->stream);
+    ctx->prof_fn[ctx->prof_n++] = (const void *)k_cq_gram;
+  }
+}
+
 static bool cq_attrs(ovb_ctx *ctx) {
   if (!ctx->attr_done[4]) {
     cudaFuncSetAttribute(k_cq_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -1159,7 +1235,7 @@ static int cq_compress_wide(ovb_ctx *ctx, double *A, int m, int n, int ldA, doub
   int launches = 0;
   for (int pass = 0; pass < 2; pass++) {
     double *G = pass == 0 ? G1 : G2;
-    ovb_launch(ctx, k_cq_gram, dim3(nblk, nslab), dim3(CQ_GRAM_T), gram_smem, (const double *)A, ldA, m, nt, slab_rows, BW, nblk_side, ctx->d_Gpart);
+    cq_launch_gram(ctx, nblk, nslab, gram_smem, (const double *)A, ldA, m, nt, slab_rows, BW, nblk_side, ctx->d_Gpart, 1);
     ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, nslab, nblk, BW, nblk_side, nt, G, (int)CQ_WMAX);
     ovb_launch(ctx, k_cq_shift, dim3(1), dim3(256), (size_t)0, G, (int)CQ_WMAX, nt, pass == 0 ? 1e-11 : 1e-13, floor_dev + pass);
     cq_chol_blocked(ctx, G, CQ_WMAX, nt, 0, pass == 0 ? Lpk1 : Lpk2, floor_dev + pass, (DevUpdateInfo *)nullptr);
@@ -1191,7 +1267,10 @@ int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, doub
   int slab_rows = (m + nslab - 1) / nslab;
   slab_rows = (slab_rows + 3) & ~3;
   nslab = (m + slab_rows - 1) / slab_rows;
-  const size_t need_part = (size_t)nslab * nblk * 16 * 1024;
+  // clusters of CQ_GRAM_CS slabs pre-reduce their partial tiles in distributed shared memory (empty slabs pad the grid)
+  const int cs = (ctx->gram_cluster && nslab >= 2 * CQ_GRAM_CS) ? CQ_GRAM_CS : 1;
+  const int nslab_pad = (nslab + cs - 1) / cs * cs, npart = nslab_pad / cs;
+  const size_t need_part = (size_t)nslab_pad * nblk * 16 * 1024;
   const int ldW = CQ_MAXN + 8;
   if (!cq_ensure_G(ctx))
     return -1;
@@ -1205,14 +1284,16 @@ int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, doub
   }
   double *G = ctx->d_G, *L1 = G + (size_t)ldW * ldW, *L2 = L1 + (size_t)ldW * ldW;
   static_assert(CQ_PK_DOUBLES <= (CQ_MAXN + 8) * (CQ_MAXN + 8), "packed factor must fit its slot");
-  const size_t gram_smem = sizeof(double) * 2 * CQ_KB * (size_t)(BW * 32 + 4);
+  size_t gram_smem = sizeof(double) * 2 * CQ_KB * (size_t)(BW * 32 + 4);
+  if (cs > 1 && gram_smem < sizeof(double) * 16 * 1024)
+    gram_smem = sizeof(double) * 16 * 1024; // staging of the 16 warp tiles for the cluster reduction
   const int ngroups = (m + 7) / 8;
   int trsm_ctas = (ngroups + CQ_TRSM_T / 32 - 1) / (CQ_TRSM_T / 32);
   if (trsm_ctas > ctx->sm_count)
     trsm_ctas = ctx->sm_count;
   for (int pass = 0; pass < 2; pass++) {
-    ovb_launch(ctx, k_cq_gram, dim3(nblk, nslab), dim3(CQ_GRAM_T), gram_smem, (const double *)A, ldA, m, nt, slab_rows, BW, nblk_side, ctx->d_Gpart);
-    ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, nslab, nblk, BW, nblk_side, nt, G, ldW);
+    cq_launch_gram(ctx, nblk, nslab_pad, gram_smem, (const double *)A, ldA, m, nt, slab_rows, BW, nblk_side, ctx->d_Gpart, cs);
+    ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, npart, nblk, BW, nblk_side, nt, G, ldW);
     ovb_launch(ctx, k_cq_chol_gram, dim3(1), dim3(CQ_CHOL_T), sizeof(CqCholSmem), (const double *)G, ldW, nt, pass == 0 ? 1e-11 : 1e-13,
                pass == 0 ? L1 : L2);
     if (pass == 0)

@@ -100,6 +100,8 @@ ovb_status ovb_create(const ovb_config *cfg, ovb_ctx **out) {
     ctx->feat_classes = e3 ? atoi(e3) : 1;
     const char *e4 = getenv("OVB_EKF_CHOL_DMMA");
     ctx->ekf_chol_dmma = e4 ? atoi(e4) : 1;
+    const char *e5 = getenv("OVB_GRAM_CLUSTER");
+    ctx->gram_cluster = e5 ? atoi(e5) : 0; // measured slower on B200 (37 clusters of 4 do not co-schedule on 148 SMs: second wave), profiles/README.md
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = 1;
@@ -718,6 +720,100 @@ ovb_status ovb_feature_jacobians(ovb_ctx *ctx, const ovb_frame *frame, const ovb
     if (Hx_out)
       for (int j = 0; j < n_all; j++)
         Hx_out[(size_t)i * ld_out + j] = host[(size_t)i * pk.ldH + j];
+  }
+  return OVB_OK;
+}
+
+// UpdaterSLAM::delayed_init in one call (see include/ovb200.h). Composition of the staged entry points with the state mean
+// moved by the caller's callback between the features, exactly the reference's sequential structure.
+ovb_status ovb_slam_delayed_init(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_batch *feats, const ovb_opts *opts, const double *sigma_pix,
+                                 const double *chi2_multipler, ovb_init_callback on_init, void *user, ovb_feat_out *out, int32_t *lm_off_out) {
+  if (!ctx || !frame || !feats || !opts || !out || !out->status || !out->p_FinA || !out->p_FinG || !out->anchor_cam || !out->anchor_clone || !lm_off_out)
+    return OVB_ERR_ARG;
+  if (opts->feat_rep == OVB_REP_ANCHORED_INVERSE_DEPTH_SINGLE) {
+    snprintf(ctx->err, sizeof(ctx->err), "ovb_slam_delayed_init: the 1-wide SINGLE representation uses the staged route (INTEGRATION.md)");
+    return OVB_ERR_ARG;
+  }
+  const int F = feats->n_feats;
+  for (int f = 0; f < F; f++)
+    lm_off_out[f] = -1;
+  if (F <= 0)
+    return OVB_OK;
+  // 1. triangulate + GN all tracks at the current state (UpdaterSLAM.cpp:118-142)
+  ovb_status st = ovb_triangulate(ctx, frame, feats, opts, out);
+  if (st != OVB_OK)
+    return st;
+  // 2. one feature after the other
+  std::vector<double> Hf, Hx, res, HR, dx;
+  std::vector<int32_t> colidx(OVB_MAX_COLS);
+  for (int f = 0; f < F; f++) {
+    if (out->status[f] != OVB_FEAT_OK)
+      continue;
+    const int m0 = feats->meas_off[f], m1 = feats->meas_off[f + 1], rows = 2 * (m1 - m0);
+    // shallow one-feature view of the batch
+    int32_t moff[2] = {0, m1 - m0}, koff[2] = {0, 0};
+    ovb_feat_batch v = *feats;
+    v.n_feats = 1;
+    v.n_meas = m1 - m0;
+    v.meas_off = moff;
+    v.cam = feats->cam + m0;
+    v.clone = feats->clone + m0;
+    v.uv = feats->uv + 2 * (size_t)m0;
+    v.uvn = feats->uvn + 2 * (size_t)m0;
+    if (feats->cam_keys_off && feats->cam_keys) {
+      koff[1] = feats->cam_keys_off[f + 1] - feats->cam_keys_off[f];
+      v.cam_keys_off = koff;
+      v.cam_keys = feats->cam_keys + feats->cam_keys_off[f];
+    }
+    int32_t st1 = OVB_FEAT_OK, ac = out->anchor_cam[f], acl = out->anchor_clone[f];
+    double pA[3] = {out->p_FinA[3 * f], out->p_FinA[3 * f + 1], out->p_FinA[3 * f + 2]};
+    double pG[3] = {out->p_FinG[3 * f], out->p_FinG[3 * f + 1], out->p_FinG[3 * f + 2]}, c2 = 0;
+    ovb_feat_out o1{&st1, pA, pG, &ac, &acl, &c2};
+    Hf.assign((size_t)rows * 3, 0.0);
+    Hx.assign((size_t)rows * OVB_MAX_COLS, 0.0);
+    res.assign((size_t)rows, 0.0);
+    int32_t row_off[2], ncols = 0;
+    st = ovb_feature_jacobians(ctx, frame, &v, opts, &o1, 0, Hf.data(), Hx.data(), res.data(), row_off, &ncols, colidx.data(), OVB_MAX_COLS);
+    if (st != OVB_OK)
+      return st;
+    // Hx_order: the variables this feature touches = runs of consecutive covariance columns with a non-zero entry
+    std::vector<int> used;
+    for (int j = 0; j < ncols; j++) {
+      bool nz = false;
+      for (int i = 0; i < rows && !nz; i++)
+        nz = Hx[(size_t)i * OVB_MAX_COLS + j] != 0.0;
+      if (nz)
+        used.push_back(j);
+    }
+    std::vector<int> off, sz;
+    for (size_t a = 0; a < used.size();) {
+      size_t b = a + 1;
+      while (b < used.size() && colidx[(size_t)used[b]] == colidx[(size_t)used[b - 1]] + 1)
+        b++;
+      off.push_back(colidx[(size_t)used[a]]);
+      sz.push_back((int)(b - a));
+      a = b;
+    }
+    const int n = (int)used.size();
+    HR.assign((size_t)rows * n, 0.0);
+    for (int i = 0; i < rows; i++)
+      for (int j = 0; j < n; j++)
+        HR[(size_t)i * n + j] = Hx[(size_t)i * OVB_MAX_COLS + used[(size_t)j]];
+    const double sp = sigma_pix ? sigma_pix[f] : opts->sigma_pix, cm = chi2_multipler ? chi2_multipler[f] : opts->chi2_multipler;
+    const int N0 = ctx->N;
+    int accepted = 0;
+    double dx_new[3] = {0, 0, 0};
+    dx.assign((size_t)N0 + 3, 0.0);
+    st = ovb_cov_initialize(ctx, off.data(), sz.data(), (int)off.size(), HR.data(), Hf.data(), res.data(), rows, 3, sp * sp, cm, &accepted, dx_new, dx.data());
+    if (st != OVB_OK)
+      return st;
+    if (!accepted) {
+      out->status[f] = OVB_FEAT_CHI2;
+      continue;
+    }
+    lm_off_out[f] = N0;
+    if (on_init)
+      on_init(user, f, N0, 3, dx_new, dx.data(), N0 + 3); // the host moves its mean and refreshes the frame arrays
   }
   return OVB_OK;
 }

@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -146,6 +147,42 @@ int main(int argc, char **argv) {
     wr(out, updater.uv);
     wr(out, updater.uvn);
     wr(out, updater.keys);
+    // ---- StateHelper::initialize -> marginalize_old_clone: every variable behind the removed clone moves up, the SLAM
+    // landmarks at the end of the covariance included (state/StateHelper.cpp:318-326)
+    {
+      const int N0 = state.max_covariance_size();
+      auto lm = std::make_shared<Landmark>();
+      lm->_featid = 777;
+      Var newvar(-1, 3);
+      const Var oldest(state._clones_IMU.begin()->second->id, 6), newest(state._clones_IMU.rbegin()->second->id, 6);
+      std::vector<Var> H_order = {oldest, newest};
+      const int r = 6;
+      std::vector<double> H_R((size_t)r * 12), H_L((size_t)r * 3), res(r);
+      for (int i = 0; i < r; i++) {
+        for (int j = 0; j < 12; j++)
+          H_R[(size_t)i * 12 + j] = 0.3 * std::sin(1.0 + 0.7 * i + 1.3 * j);
+        for (int j = 0; j < 3; j++)
+          H_L[(size_t)i * 3 + j] = (i % 3 == j ? 2.0 : 0.0) + 0.2 * std::cos(0.5 * i + j);
+        res[i] = 0.01 * (i - 2);
+      }
+      std::vector<double> dx_new, dx2;
+      if (!StateHelper::initialize(state, newvar, H_order, H_R, H_L, res, 1.0, 1e6, dx_new, dx2))
+        throw std::runtime_error("initialize rejected the synthetic landmark");
+      lm->id = newvar.first;
+      state._features_SLAM[lm->_featid] = lm;
+      if (lm->id != N0 || state.max_covariance_size() != N0 + 3)
+        throw std::runtime_error("initialize: landmark not appended at the end of the covariance");
+      const std::vector<double> blk_before = StateHelper::get_marginal_covariance(state, {Var(lm->id, 3)});
+      state._options.max_clone_size = (int)state._clones_IMU.size() - 1;
+      StateHelper::marginalize_old_clone(state);
+      if (lm->id != N0 - 6 || state.max_covariance_size() != N0 - 3)
+        throw std::runtime_error("marginalize_old_clone: landmark id not shifted");
+      const std::vector<double> blk_after = StateHelper::get_marginal_covariance(state, {Var(lm->id, 3)});
+      for (size_t i = 0; i < 9; i++)
+        if (blk_before[i] != blk_after[i])
+          throw std::runtime_error("marginalize_old_clone: landmark block moved to the wrong place");
+      std::printf("host_shim_test: marginalize bookkeeping ok (landmark id %d -> %d)\n", N0, lm->id);
+    }
     std::printf("host_shim_test: %d features in, %d used, dx norm2 %.6e\n", F, (int)feature_vec.size(), [&] {
       double s = 0;
       for (double v : dx)

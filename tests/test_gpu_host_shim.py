@@ -68,6 +68,8 @@ def test_cpp_host_mirror_runs_the_update(oracle, name, tmp_path):
     case_path, out_path = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
     _write_case(case_path, d, frame, feats, opts)
     res = subprocess.run([exe, case_path, out_path], capture_output=True, text=True, timeout=300)
+    # initialize -> marginalize_old_clone must shift the SLAM landmark ids too (checked inside the driver)
+    assert "marginalize bookkeeping ok" in res.stdout, res.stdout + res.stderr
     assert res.returncode == 0, res.stderr
     r = _read_out(out_path)
     # every feature that entered is flagged for deletion, the two malformed extras included (UpdaterMSCKF.cpp:90-94, :276-279)

@@ -188,3 +188,75 @@ def test_anchor_change_propagation_shape(oracle):
     Pt = J @ P @ J.T
     assert np.linalg.norm(Pg - Pt) <= 1e-12 * np.linalg.norm(Pt)
     eng.close()
+
+
+def _apply_dx_to_frame(fr, dx):
+    """Host side of StateHelper::EKFUpdate's mean update (state/StateHelper.cpp:185-188) for the variables the frame carries:
+    JPL left error on rotations (R <- exp(-dtheta) R), additive elsewhere; FEJ values stay. In place (the engine re-reads)."""
+    for c, o in enumerate(fr.clone_off):
+        fr.clone_R[c] = (sim.exp_so3(-dx[o:o + 3]) @ fr.clone_R[c].reshape(3, 3)).reshape(-1)
+        fr.clone_p[c] += dx[o + 3:o + 6]
+    for k in range(fr.n_cams):
+        o = fr.cam_ext_off[k]
+        if o >= 0:
+            fr.cam_R[k] = (sim.exp_so3(-dx[o:o + 3]) @ fr.cam_R[k].reshape(3, 3)).reshape(-1)
+            fr.cam_p[k] += dx[o + 3:o + 6]
+        o = fr.cam_intr_off[k]
+        if o >= 0:
+            fr.cam_intr[k] += dx[o:o + 8]
+
+
+def test_delayed_init_one_call(oracle):
+    """ovb_slam_delayed_init = UpdaterSLAM::delayed_init (update/UpdaterSLAM.cpp:61-251) as ONE ABI call, the state mean moved
+    by the caller's callback between the features. Checked against the same sequence composed from the oracle's
+    triangulation / Jacobians / StateHelper::initialize with the identical mean update."""
+    import copy
+    kw = dict(n_feats=10, n_clones=8, n_cams=2, seed=23, calib_ext=True, calib_intr=True, outlier_frac=0.0, degenerate_frac=0.0)
+    case_g, case_o = sim.make_update_case(**kw), sim.make_update_case(**kw)
+    opts = capi.default_opts(do_calib_camera_pose=1, do_calib_camera_intrinsics=1)
+    eng = capi.Engine(max_state=256, max_feats=64, max_meas=2048)
+    eng.cov_set(case_g.P)
+    log_g = []
+
+    def on_init(f, lm_off, dx_new, dx):
+        log_g.append((f, lm_off, dx_new, dx))
+        _apply_dx_to_frame(case_g.frame, dx)
+    out_g, lm_off = eng.slam_delayed_init(case_g.frame, case_g.feats, opts, on_init)
+    # ---- oracle composition
+    fr = case_o.frame
+    tri, _ = oracle.triangulate(fr, case_o.feats, opts)
+    P = case_o.P.copy()
+    log_o, status_o = [], tri.status.copy()
+    for f in np.flatnonzero(tri.status == 0):
+        one = case_o.feats.subset([f])
+        o = capi.FeatOut(1)
+        o.status[:] = 0
+        o.p_FinA[0], o.p_FinG[0] = tri.p_FinA[f], tri.p_FinG[f]
+        o.anchor_cam[0], o.anchor_clone[0] = tri.anchor_cam[f], tri.anchor_clone[f]
+        # canonical column list = what the engine reports; build it from the layout
+        cols = []
+        for off, sz in sorted([(int(x), 6) for x in fr.clone_off] + [(int(x), 6) for x in fr.cam_ext_off if x >= 0] + [(int(x), 8) for x in fr.cam_intr_off if x >= 0]):
+            cols += list(range(off, off + sz))
+        cols = np.array(cols)
+        Hf, Hx, res, _ = oracle.feature_jacobians(fr, one, opts, o, 0, cols)
+        used = np.flatnonzero(np.abs(Hx).sum(axis=0) > 0)
+        cc = cols[used]
+        starts = [0] + [i for i in range(1, len(cc)) if cc[i] != cc[i - 1] + 1] + [len(cc)]
+        off = [int(cc[a]) for a in starts[:-1]]
+        sz = [int(b - a) for a, b in zip(starts[:-1], starts[1:])]
+        st, acc, P, dxn, dx = oracle.cov_initialize(P, off, sz, Hx[:, used], Hf, res, sigma2=1.0, chi2_mult=float(opts.chi2_multipler))
+        assert st == 0
+        if acc:
+            log_o.append((int(f), P.shape[0] - 3, dxn, dx))
+            _apply_dx_to_frame(fr, dx)
+        else:
+            status_o[f] = capi.FEAT_CHI2
+    assert np.array_equal(out_g.status, status_o)
+    assert len(log_g) == len(log_o) >= 4
+    for (fg, og, dng, dg), (fo, oo, dno, do) in zip(log_g, log_o):
+        assert fg == fo and og == oo == lm_off[fg]
+        assert np.linalg.norm(dng - dno) <= 1e-8 * max(np.linalg.norm(dno), 1e-12)
+        assert np.linalg.norm(dg - do) <= 1e-8 * max(np.linalg.norm(do), 1e-300)
+    Pg = eng.cov_get()
+    assert Pg.shape == P.shape and np.linalg.norm(Pg - P) <= 1e-9 * np.linalg.norm(P)
+    eng.close()

@@ -122,7 +122,7 @@ int main() {
     CK(cudaMemcpy(A, A0, sizeof(double) * hA.size(), cudaMemcpyDeviceToDevice));
     cudaDeviceSynchronize();
     cudaEventRecord(e[0]);
-    k_cq_gram<<<dim3(1, nslab), CQ_GRAM_T, gram_smem>>>(A, ld, m, nt, slab_rows, BW, 1, Gpart);
+    k_cq_gram<<<dim3(1, nslab), CQ_GRAM_T, gram_smem>>>(A, ld, m, nt, slab_rows, BW, 1, Gpart, 1);
     cudaEventRecord(e[1]);
     k_cq_reduce<<<dim3(CQ_RED_GX, 1), CQ_RED_T>>>(Gpart, nslab, 1, BW, 1, nt, G, ldW);
     cudaEventRecord(e[2]);
