@@ -194,12 +194,12 @@ def _apply_dx_to_frame(fr, dx):
     """Host side of StateHelper::EKFUpdate's mean update (state/StateHelper.cpp:185-188) for the variables the frame carries:
     JPL left error on rotations (R <- exp(-dtheta) R), additive elsewhere; FEJ values stay. In place (the engine re-reads)."""
     for c, o in enumerate(fr.clone_off):
-        fr.clone_R[c] = (sim.exp_so3(-dx[o:o + 3]) @ fr.clone_R[c].reshape(3, 3)).reshape(-1)
+        fr.clone_R[c] = (sim.exp_so3(-dx[o:o + 3]) @ fr.clone_R[c].reshape(3, 3)).reshape(fr.clone_R[c].shape)
         fr.clone_p[c] += dx[o + 3:o + 6]
     for k in range(fr.n_cams):
         o = fr.cam_ext_off[k]
         if o >= 0:
-            fr.cam_R[k] = (sim.exp_so3(-dx[o:o + 3]) @ fr.cam_R[k].reshape(3, 3)).reshape(-1)
+            fr.cam_R[k] = (sim.exp_so3(-dx[o:o + 3]) @ fr.cam_R[k].reshape(3, 3)).reshape(fr.cam_R[k].shape)
             fr.cam_p[k] += dx[o + 3:o + 6]
         o = fr.cam_intr_off[k]
         if o >= 0:
