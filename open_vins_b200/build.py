@@ -28,7 +28,7 @@ UNITS = [
     ("ovb_api.cu", []),
     ("anchor_change.cu", []),  # host-only math (UpdaterSLAM::perform_anchor_change)
 ]
-HEADERS = ["ovb_internal.cuh", "geom.cuh", "chol.cuh", "chi2_table.inc", os.path.join("..", "..", "include", "ovb200.h")]
+HEADERS = ["ovb_internal.cuh", "geom.cuh", "chol.cuh", "chol_tiles.cuh", "chi2_table.inc", os.path.join("..", "..", "include", "ovb200.h")]
 
 
 def _stale(target: str, deps: list[str]) -> bool:

@@ -21,6 +21,7 @@
 //
 // Everything is deterministic (no atomics, fixed reduction order): replicas on different GPUs stay bitwise equal.
 #include "chol.cuh"
+#include "chol_tiles.cuh"
 #include "ovb_internal.cuh"
 #include <math.h>
 #include <cstdio>
@@ -32,7 +33,7 @@
 #define CQ_KB 32         // rows per staged chunk in k_cq_gram
 #define CQ_CHOL_T 384
 #define CQ_CHOL_NA 5     // look-ahead warps of the Cholesky
-#define CQ_XP 12         // pitch of the panel buffer (conflict-free 8x4 fragments)
+#define CQ_XP CT_XP     // pitch of the panel buffer (chol_tiles.cuh)
 #define CQ_TRSM_T 640
 
 namespace {
@@ -301,243 +302,18 @@ struct CqCholSmem {
 
 namespace {
 
-// Factor the diagonal tile (row-major 8x8, lower) — all lanes of the calling warp compute the same thing in registers;
-// rows >= nbk of the tile are left untouched. strict: a pivot <= 0 (or NaN) raises *flag; else pivots are floored at
-// floor_d (semidefinite input) and a zero pivot empties its column.
-__device__ __forceinline__ void cq_diag8(double *tile, int nbk, double *invd, bool strict, double floor_d, int *flag) {
-  const int lane = threadIdx.x & 31;
-  double a[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-#pragma unroll
-    for (int j2 = 0; j2 < 4; j2++) {
-      if (2 * j2 <= i) {
-        const double2 v = *reinterpret_cast<const double2 *>(tile + i * 8 + 2 * j2);
-        a[i][2 * j2] = v.x;
-        a[i][2 * j2 + 1] = v.y;
-      }
-    }
-  }
-  double inv[8];
-  bool bad = false;
-  const double inv_floor = (floor_d > 0.0) ? fast_rsqrt(floor_d) : 0.0; // off the chain: known before the first pivot
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const double d0 = a[j][j];
-    const double y = fast_rsqrt(d0); // unconditional; the comparisons below run beside it and only select
-    const bool in = j < nbk;
-    double d, iv;
-    if (strict) {
-      const bool pos = d0 > 0.0;
-      bad = bad || (in && !pos);
-      d = d0;
-      iv = (in && pos) ? y : 0.0;
-    } else {
-      const bool above = d0 > floor_d; // NaN falls to the floor as well; it survives elsewhere in the row
-      d = above ? d0 : floor_d;
-      iv = in ? (above ? y : inv_floor) : 0.0; // floor 0 (all-zero system): the column empties
-    }
-    inv[j] = iv;
-    a[j][j] = d * iv;
-#pragma unroll
-    for (int i = j + 1; i < 8; i++)
-      a[i][j] *= iv;
-#pragma unroll
-    for (int i = j + 1; i < 8; i++)
-#pragma unroll
-      for (int c = j + 1; c <= i; c++)
-        a[i][c] -= a[i][j] * a[c][j];
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    if (lane == i && i < nbk) {
-#pragma unroll
-      for (int c = 0; c <= i; c++)
-        tile[i * 8 + c] = a[i][c];
-    }
-  }
-  if (lane == 8) {
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-      invd[j] = inv[j];
-    if (bad)
-      *flag = 1;
-  }
-}
-
-// rows i0, i0+stride, ... of panel k: x L_kk' = S[i][kb..kb+8); writes x in place and into the panel buffer (zero past nbk).
-// L_kk and the reciprocal pivots go to registers first so that the substitution chain never waits for shared memory.
-__device__ __forceinline__ void cq_panel_rows(double *T, double *Xp, const double *invd, int i0, int stride, int nrows, int k, int nbk) {
-  if (i0 >= nrows)
-    return;
-  const double *Lk = T + (size_t)(tri(k) + k) * 64;
-  double L[8][8], iv[8];
-#pragma unroll
-  for (int c = 0; c < 8; c++) {
-    iv[c] = (c < nbk) ? invd[8 * k + c] : 0.0;
-#pragma unroll
-    for (int t2 = 0; t2 < 4; t2++) {
-      if (2 * t2 < c) {
-        const double2 v = *reinterpret_cast<const double2 *>(Lk + c * 8 + 2 * t2);
-        L[c][2 * t2] = v.x;
-        L[c][2 * t2 + 1] = v.y;
-      }
-    }
-  }
-  for (int i = i0; i < nrows; i += stride) {
-    double *src = T + (size_t)(tri(i >> 3) + k) * 64 + (i & 7) * 8;
-    double v[8], x[8];
-    {
-      const double2 v01 = *reinterpret_cast<const double2 *>(src), v23 = *reinterpret_cast<const double2 *>(src + 2);
-      const double2 v45 = *reinterpret_cast<const double2 *>(src + 4), v67 = *reinterpret_cast<const double2 *>(src + 6);
-      v[0] = v01.x, v[1] = v01.y, v[2] = v23.x, v[3] = v23.y, v[4] = v45.x, v[5] = v45.y, v[6] = v67.x, v[7] = v67.y;
-    }
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-      double s = v[c];
-#pragma unroll
-      for (int t = 0; t < 8; t++)
-        if (t < c)
-          s -= x[t] * L[c][t];
-      x[c] = (c < nbk) ? s * iv[c] : 0.0;
-    }
-    if (nbk == 8) {
-      *reinterpret_cast<double2 *>(src) = make_double2(x[0], x[1]);
-      *reinterpret_cast<double2 *>(src + 2) = make_double2(x[2], x[3]);
-      *reinterpret_cast<double2 *>(src + 4) = make_double2(x[4], x[5]);
-      *reinterpret_cast<double2 *>(src + 6) = make_double2(x[6], x[7]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; c++)
-        if (c < nbk)
-          src[c] = x[c];
-    }
-    double *xp = Xp + (size_t)i * CQ_XP;
-    *reinterpret_cast<double2 *>(xp) = make_double2(x[0], x[1]);
-    *reinterpret_cast<double2 *>(xp + 2) = make_double2(x[2], x[3]);
-    *reinterpret_cast<double2 *>(xp + 4) = make_double2(x[4], x[5]);
-    *reinterpret_cast<double2 *>(xp + 6) = make_double2(x[6], x[7]);
-  }
-}
-
-struct CqTileOps {
-  double a0, a1, b0, b1;
-  double2 c;
-  double2 *cp;
-};
-// valid == false: the pair's second slot is empty; it is pointed at a dummy tile with zero operands so that both DMMAs of
-// the pair execute unconditionally (a branch around mma.sync costs convergence code on every use)
-__device__ __forceinline__ void cq_tile_load(CqTileOps &o, CqCholSmem &sm, const double *Xp, int bi, int bj, int lane, bool valid) {
-  const int g = lane >> 2, q = lane & 3;
-  const double *xa = valid ? Xp + (size_t)(8 * bi + g) * CQ_XP + q : sm.dummyX + q;
-  const double *xb = valid ? Xp + (size_t)(8 * bj + g) * CQ_XP + q : sm.dummyX + q;
-  o.cp = reinterpret_cast<double2 *>((valid ? sm.T + (size_t)(tri(bi) + bj) * 64 : sm.dummyT) + 2 * lane);
-  o.a0 = -xa[0];
-  o.a1 = -xa[4];
-  o.b0 = xb[0];
-  o.b1 = xb[4];
-  o.c = *o.cp;
-}
-__device__ __forceinline__ void cq_tile_mma_store(CqTileOps &o) {
-  dmma(o.c.x, o.c.y, o.a0, o.b0);
-  dmma(o.c.x, o.c.y, o.a1, o.b1);
-  *o.cp = o.c;
-}
-
-#ifdef CQ_PROBE
-#define CQ_PROBE_T(v) v = clock64()
-#else
-#define CQ_PROBE_T(v) do { } while (0)
-#endif
-
-// The factorisation proper, on a tile-packed lower triangle already in shared memory. n columns, nrows = n + extra rows.
-__device__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, bool strict, double floor_d) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // look-ahead group = warps 0..NA-1 (NA * 32 >= 152 rows: one panel row per thread at the widest step). The FP64/DMMA pipe
-  // is ONE unit shared by the four sub-partitions of an SM (tools/ubench/cholqr_bench.cu: a lone warp's DMMA chain slows
-  // down 3x as soon as other sub-partitions issue FP64 work), so no warp placement isolates the pivot chain.
-  constexpr int NW = CQ_CHOL_T / 32, NA = CQ_CHOL_NA, NBW = NW - NA;
-  const bool inA = wid < NA;
-  const int widA = wid, tidA = tid; // rank inside the look-ahead group
-  const int widB = wid - NA;        // rank among the other warps
-#ifdef CQ_PROBE
-  long long p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0;
-#endif
-  const int NB = (n + 7) >> 3, NRB = (nrows + 7) >> 3;
-  if (wid == 0)
-    cq_diag8(sm.T, min(8, n), sm.invd, strict, floor_d, &sm.flag);
-  __syncthreads();
-  cq_panel_rows(sm.T, sm.Xp[0], sm.invd, min(8, n) + tid, CQ_CHOL_T, nrows, 0, min(8, n));
-  __syncthreads();
-  for (int k = 0; k + 1 < NB; k++) {
-    const int par = k & 1;
-    const double *Xk = sm.Xp[par];
-    CQ_PROBE_T(p0);
-    if (inA) {
-      const int k1 = k + 1;
-      const int nbk1 = min(8, n - 8 * k1);
-      // block column k+1 (warp 0 takes the diagonal tile first), two tiles in flight
-      for (int bi = k1 + widA; bi < NRB; bi += 2 * NA) {
-        CqTileOps o0, o1;
-        cq_tile_load(o0, sm, Xk, bi, k1, lane, true);
-        cq_tile_load(o1, sm, Xk, bi + NA, k1, lane, bi + NA < NRB);
-        cq_tile_mma_store(o0);
-        cq_tile_mma_store(o1);
-      }
-      CQ_PROBE_T(p1);
-      bar_group(1, NA * 32);
-      CQ_PROBE_T(p2);
-      if (wid == 0)
-        cq_diag8(sm.T + (size_t)(tri(k1) + k1) * 64, nbk1, sm.invd + 8 * k1, strict, floor_d, &sm.flag);
-      CQ_PROBE_T(p3);
-      bar_group(1, NA * 32);
-      CQ_PROBE_T(p4);
-      cq_panel_rows(sm.T, sm.Xp[par ^ 1], sm.invd, 8 * k1 + nbk1 + tidA, NA * 32, nrows, k1, nbk1);
-      CQ_PROBE_T(p5);
-    } else {
-      // tiles (bi, bj) with k+2 <= bj <= bi < NRB, bj < NB, flattened row by row over the remaining warps; the flat index
-      // advances by the warp count, the (row, column) pair follows incrementally
-      const int R = NRB - (k + 2);
-      const int TB = (R * (R + 1)) >> 1;
-      int r = 0, c = widB;
-      while (c > r) {
-        c -= r + 1;
-        r++;
-      }
-      for (int t = widB; t < TB; t += 2 * NBW) {
-        const int bi0 = k + 2 + r, bj0 = k + 2 + c;
-        c += NBW;
-        while (c > r) {
-          c -= r + 1;
-          r++;
-        }
-        const int bi1 = k + 2 + r, bj1 = k + 2 + c;
-        const bool two = t + NBW < TB;
-        c += NBW;
-        while (c > r) {
-          c -= r + 1;
-          r++;
-        }
-        CqTileOps o0, o1;
-        cq_tile_load(o0, sm, Xk, bi0, bj0, lane, bj0 < NB);
-        cq_tile_load(o1, sm, Xk, bi1, bj1, lane, two && bj1 < NB);
-        cq_tile_mma_store(o0);
-        cq_tile_mma_store(o1);
-      }
-      CQ_PROBE_T(p1);
-    }
-    __syncthreads();
-    CQ_PROBE_T(p6);
-#ifdef CQ_PROBE
-    if ((k == 0 || k == 8 || k == 16) && (tid == 0 || tid == 32 || tid == NA * 32 || tid == CQ_CHOL_T - 32)) {
-      if (inA)
-        printf("chol k=%d tid=%d A: tiles %lld bar %lld diag %lld bar %lld panel %lld wait %lld | step %lld\n", k, tid, p1 - p0, p2 - p1, p3 - p2, p4 - p3,
-               p5 - p4, p6 - p5, p6 - p0);
-      else
-        printf("chol k=%d tid=%d B: tiles %lld wait %lld | step %lld\n", k, tid, p1 - p0, p6 - p1, p6 - p0);
-    }
-#endif
-  }
+// The factorisation proper lives in chol_tiles.cuh (shared with the per-feature gate); this kernel family runs it with
+// CQ_CHOL_T threads and CQ_CHOL_NA look-ahead warps (NA * 32 >= 152 rows: one panel row per thread at the widest step).
+__device__ __forceinline__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, bool strict, double floor_d) {
+  CtView v;
+  v.T = sm.T;
+  v.Xp0 = sm.Xp[0];
+  v.Xp1 = sm.Xp[1];
+  v.invd = sm.invd;
+  v.dummyT = sm.dummyT;
+  v.dummyX = sm.dummyX;
+  v.flag = &sm.flag;
+  ct_chol_tiles<CQ_CHOL_T, CQ_CHOL_NA>(v, n, nrows, strict, floor_d);
 }
 
 // stage the lower triangle of a row-major global matrix (rows < nrows, cols < n; rows >= n come from `rhs` when given)

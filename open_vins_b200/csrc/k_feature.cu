@@ -16,11 +16,20 @@
 //    residual carried as an extra row (chi² = |L^-1 r_o|²);
 //  * rows are written straight into the stacked staging matrix in canonical column order, coalesced.
 // Compiled with -fmad=false (see geom.cuh).
+#include <cstdio>
 #include "geom.cuh"
 #include "chol.cuh"
+#include "chol_tiles.cuh"
 
 #define FT_THREADS 256
 #define FT_WARPS (FT_THREADS / 32)
+#define FT_CHOL_NA 3 // look-ahead warps of the gate Cholesky (chol_tiles.cuh): 96 panel rows per trip
+#define FT_TU 2
+#ifdef FT_PROBE // per-phase cycle stamps of the longest track of a launch (thread 0 of CTA 0), printed at the end of the feature
+#define FT_STAMP(i) do { if (tid == 0 && blockIdx.x == 0) ft_t[i] = clock64(); } while (0)
+#else
+#define FT_STAMP(i) do { } while (0)
+#endif      // measurements whose covariance rows are in flight together in the T = H_x P pass
 
 // Per-measurement Jacobian blocks live in shared memory as structure-of-arrays:
 //   Bsh[I][b][16]  blocks [2][8] (row stride 8): 0 clone(6) 1 extrinsics(6) 2 intrinsics(8) 3 anchor clone(6) 4 anchor extrinsics(6);
@@ -34,12 +43,12 @@ struct MeasView {
   double *res;
   signed char *slot;
   unsigned char *lut;
-  int nblk, lutw;
-  __device__ __forceinline__ double *blk(int I, int b) const { return B + ((size_t)I * nblk + b) * 16; }
+  int nblk, lutw, bstride; // bstride = 16*nblk + 1 doubles per measurement: lanes walking measurements hit distinct banks
+  __device__ __forceinline__ double *blk(int I, int b) const { return B + (size_t)I * bstride + b * 16; }
   // value of Jacobian row (I, r) in column k of slot s (0 when the measurement does not touch the slot)
   __device__ __forceinline__ double x_at(int I, int r, int s, int k) const {
     const int b = lut[(size_t)I * lutw + s];
-    return (b == 255) ? 0.0 : B[((size_t)I * nblk + b) * 16 + 8 * r + k];
+    return (b == 255) ? 0.0 : B[(size_t)I * bstride + b * 16 + 8 * r + k];
   }
 };
 
@@ -65,6 +74,42 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, doub
     b += red[i * 3 + 1];
     c += red[i * 3 + 2];
   }
+}
+
+// block-wide sums of NV values; every thread gets the results. red: FT_WARPS*NV doubles of shared memory.
+template <int NV> __device__ __forceinline__ void block_sum_n(double (&v)[NV], double *red) {
+#pragma unroll
+  for (int e = 0; e < NV; e++)
+    v[e] = warp_sum(v[e]);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads(); // protect red from the previous use
+  if (l == 0) {
+#pragma unroll
+    for (int e = 0; e < NV; e++)
+      red[w * NV + e] = v[e];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < NV; e++) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < FT_WARPS; i++)
+      a += red[i * NV + e];
+    v[e] = a;
+  }
+}
+
+__device__ __forceinline__ void ft_cpa8(double *dst_smem, const double *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ft_cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void ft_cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The gate's factorisation as a real call: its register allocation (the 8x8 pivot block and the panel rows live in
+// registers) is then independent of what the feature kernel keeps live around it.
+__device__ __noinline__ void ft_gate_chol(double *ctbase, int NRB, int *flag, int n, int nrows) {
+  const CtView cv = ct_view_carve(ctbase, NRB, flag);
+  ct_chol_tiles<FT_THREADS, FT_CHOL_NA>(cv, n, nrows, true, 0.0);
 }
 
 // ---- d p_FinG / d lambda and the anchor terms: UpdaterHelper.cpp:32-190. Returns L (3x3 row-major),
@@ -201,13 +246,17 @@ __device__ __forceinline__ bool rep_is_relative(int rep) {
 // mode 2: SLAM update (update/UpdaterSLAM.cpp:310-447): the landmark is a state variable (block 5 = H_f, slot lm_slot),
 //         no nullspace projection (all 2M rows are kept), per-feature noise / gate multiplier, rows whitened by 1/sigma
 // The SLAM variant is a separate instantiation so that the MSCKF hot path carries none of its code or registers.
-template <bool SLAM>
+// BIG: tracks whose gate matrix does not fit shared memory (the launcher decides): S lives in a per-CTA slice of an
+// L2-resident scratch buffer and is factored by the scalar blocked Cholesky of chol.cuh after a two-sided projection.
+// Otherwise the gate runs on the tile-packed triangle of chol_tiles.cuh (DMMA) with the projection folded into the
+// right-hand sides (see "gate" below); Mc = measurements per chunk of the T = H_x P staging buffer.
+template <bool SLAM, bool BIG>
 __global__ void __launch_bounds__(FT_THREADS, 2)
     k_feature_system(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, DevFeat *__restrict__ feats, int sched_lo, int n_feats,
                      BlobView bv,
                      const double *__restrict__ P, int ldP, const double *__restrict__ chi2_table, double *__restrict__ Hs, int ldH,
                      unsigned char *__restrict__ feat_order, int mode, int maxM, int nblk, double *__restrict__ scratch,
-                     size_t scratch_per_cta, double *__restrict__ dump, int ld_dump, int dump_rows) {
+                     size_t scratch_per_cta, double *__restrict__ dump, int ld_dump, int dump_rows, int Mc) {
   OVB_PDL_ENTER();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ovb_opts &op = dop->o;
@@ -226,9 +275,10 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
   size_t o = 0;
   MeasView mv;
   mv.nblk = nblk;
+  mv.bstride = 16 * nblk + 1;
   mv.lutw = (n_slots + 3) & ~3;
   mv.B = (double *)(smem_raw + o);
-  o += sizeof(double) * 16 * (size_t)nblk * maxM;
+  o += sizeof(double) * (size_t)mv.bstride * maxM;
   mv.Hf = (double *)(smem_raw + o);
   o += sizeof(double) * 6 * (size_t)maxM;
   mv.res = (double *)(smem_raw + o);
@@ -237,10 +287,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
   o += sizeof(double) * 3 * 2 * (size_t)maxM;
   double *Z = (double *)(smem_raw + o); // [3][n_all+1]
   o += sizeof(double) * 3 * (size_t)(n_all + 1);
-  double *Tw = (double *)(smem_raw + o); // [FT_WARPS][2][n_all]
-  o += sizeof(double) * FT_WARPS * 2 * (size_t)n_all;
   double *red = (double *)(smem_raw + o);
-  o += sizeof(double) * (FT_WARPS * 3 + 24);
+  o += sizeof(double) * (FT_WARPS * 12 + 24);
   int *slot2l = (int *)(smem_raw + o); // [OVB_MAX_VARS] compact column start of a slot or -1
   o += sizeof(int) * OVB_MAX_VARS;
   int *fslot_off = (int *)(smem_raw + o); // frame tables, staged once per CTA
@@ -266,7 +314,14 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
   mv.lut = smem_raw + o;
   o += (size_t)maxM * mv.lutw;
   o = (o + 15) & ~(size_t)15;
-  double *S_sh = (double *)(smem_raw + o); // [(2M+1)][ldS] when it fits, else per-CTA global scratch
+  // BIG: Tw [FT_WARPS][2][n_all] (one measurement's T rows per warp).  else: TT [2*Mc][ldT] then the Cholesky working set
+  //      (T rows of a chunk), PS [2][Mc][6][ldT] (staged covariance rows), EX [15][ldT] when nblk > 3, then the Cholesky set
+  double *Tw = (double *)(smem_raw + o);
+  const int ldT = n_all | 1;
+  double *PS = Tw + (size_t)2 * Mc * ldT;
+  double *EX = PS + (size_t)12 * Mc * ldT;
+  double *ctbase = EX + (nblk > 3 ? (size_t)15 * ldT : 0);
+  ctbase += ((ctbase - Tw) & 1); // 16-byte aligned
 
   // ---- frame tables -> shared memory (the bookkeeping below would otherwise chase them through L2 serially)
   for (int s = tid; s < n_slots; s += FT_THREADS) {
@@ -282,6 +337,10 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
   // this launch works on entries [sched_lo, n_feats) of the longest-first schedule (one size class, see the launcher)
   for (int fi = sched_lo + blockIdx.x; fi < n_feats; fi += gridDim.x) {
     const int f = feats[fi].sched; // longest tracks first: the short ones fill the tail of the last wave
+#ifdef FT_PROBE
+    long long ft_t[12] = {0};
+#endif
+    FT_STAMP(0);
     DevFeat *F = &feats[f];
     const int m0 = F->m0, M = F->m1 - F->m0;
     const int rows = 2 * M;
@@ -335,6 +394,13 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
 
     for (int e = tid; e < M * mv.lutw; e += FT_THREADS)
       mv.lut[e] = 255;
+    if constexpr (!BIG) { // the gate's working set starts zeroed (panel buffers, the padding of the edge tiles, the dummy tile)
+      if (mode != 1) {
+        const int nd = (int)ct_view_doubles((rows + 1 + nproj + 7) >> 3);
+        for (int e = tid; e < nd; e += FT_THREADS)
+          ctbase[e] = 0.0;
+      }
+    }
     // measurement metadata -> shared memory, one coalesced pass
     for (int i = tid; i < M; i += FT_THREADS) {
       mcam[i] = bv.cam[m0 + i];
@@ -403,17 +469,12 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       }
       if (ord)
         ord[0] = (unsigned char)no;
-      // compact columns in canonical slot order
+      // compact columns in canonical slot order: the slot starts here, the per-column tables by all threads below
       int wf = 0;
       for (int s = 0; s < n_slots; s++) {
         if ((seen >> s) & 1ull) {
           slot2l[s] = wf;
-          const int w = fslot_size[s];
-          for (int k = 0; k < w; k++) {
-            lcol_slot[wf + k] = (short)s;
-            lcol_k[wf + k] = (short)k;
-          }
-          wf += w;
+          wf += fslot_size[s];
         } else
           slot2l[s] = -1;
       }
@@ -565,6 +626,52 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
     __syncthreads();
 
+    const int wf = ishare[0];
+    const int nchunk = (M + Mc - 1) / Mc;
+    for (int j = tid; j < n_all; j += FT_THREADS) { // compact column -> (slot, offset in slot)
+      const int sj = ccol_slot[j], l0 = slot2l[sj];
+      if (l0 >= 0) {
+        lcol_slot[l0 + ccol_k[j]] = (short)sj;
+        lcol_k[l0 + ccol_k[j]] = (short)ccol_k[j];
+      }
+    }
+    __syncthreads();
+    auto stage_rows = [&](int q) {
+      if (q < nchunk) {
+        const int I0 = q * Mc, I1 = min(M, I0 + Mc);
+        for (int c = tid; c < wf; c += FT_THREADS) {
+          const double *Pc = P + (fslot_off[lcol_slot[c]] + lcol_k[c]);
+          for (int I = I0; I < I1; I++) {
+            const double *Pr = Pc + (size_t)fslot_off[mcs[I]] * ldP;
+            double *dst = PS + ((size_t)((q & 1) * Mc + (I - I0)) * 6) * ldT + c;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              ft_cpa8(dst + (size_t)k * ldT, Pr + (size_t)k * ldP);
+          }
+        }
+      }
+      ft_cpa_commit(); // one group per call, empty or not: the wait below counts groups
+    };
+    if constexpr (!BIG) {
+      if (mode != 1) { // the first copies fly while the reflectors are built
+        if (nblk > 3) {
+          for (int c = tid; c < wf; c += FT_THREADS) {
+            const double *Pc = P + (fslot_off[lcol_slot[c]] + lcol_k[c]);
+#pragma unroll
+            for (int b = 3; b < 6; b++) {
+              const int sb = (b == 3) ? s_anchor : (b == 4 ? s_anchor_ext : (slam ? (int)F->lm_slot : -1));
+              if (b < nblk && sb >= 0) {
+                const int wb = (b == 5) ? lmw : 6;
+                for (int k = 0; k < wb; k++)
+                  ft_cpa8(EX + (size_t)((b - 3) * 6 + k) * ldT + c, Pc + (size_t)(fslot_off[sb] + k) * ldP);
+              }
+            }
+          }
+        }
+        stage_rows(0); // its group also carries the EX copies
+        stage_rows(1);
+      }
+    }
     if (mode == 1) {
       // dense dump: [Hf rows x 3][res rows][Hx rows x ld_dump], rows indexed 2*m0 + local
       double *dHf = dump, *dres = dump + (size_t)dump_rows * 3, *dHx = dump + (size_t)dump_rows * 4;
@@ -582,6 +689,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       continue;
     }
 
+    FT_STAMP(1);
     // ---- Householder QR of H_f (rows x 3): V (unit lower trapezoid) and tau; one thread per row
     double a[3] = {0, 0, 0};
     if (tid < rows) {
@@ -653,18 +761,21 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
     block_sum3(G10, G20, G21, red);
 
+    FT_STAMP(2);
     // ---- Z[k][j]: coefficients of Q'x = x - V z for every canonical column j and the residual (j = n_all)
     for (int j = tid; j <= n_all; j += FT_THREADS) {
       double w0 = 0, w1 = 0, w2 = 0;
       if (j < n_all) {
         const int s = ccol_slot[j], kk = ccol_k[j];
         if (slot2l[s] >= 0) {
+          // branch-free (a measurement that does not touch the slot adds zeros) so that the loads of several
+          // measurements are in flight together
+#pragma unroll 4
           for (int I = 0; I < M; I++) {
             const int b = mv.lut[(size_t)I * mv.lutw + s];
-            if (b == 255)
-              continue;
-            const double *Bb = mv.blk(I, b);
-            double x0 = Bb[kk], x1 = Bb[8 + kk];
+            const bool hit = (b != 255);
+            const double *Bb = mv.blk(I, hit ? b : 0);
+            const double x0 = hit ? Bb[kk] : 0.0, x1 = hit ? Bb[8 + kk] : 0.0;
             const double *v = V + 6 * I;
             w0 += v[0] * x0 + v[3] * x1;
             w1 += v[1] * x0 + v[4] * x1;
@@ -689,169 +800,364 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
     __syncthreads();
 
-    // ---- S = H_x P_marg H_x' + s² I from the sparse blocks (rows x rows), warp per measurement row pair
-    const int wf = ishare[0];
-    const int ldS = rows | 1; // odd leading dimension: conflict-free row and column sweeps
-    double *S = S_sh;
-    if (scratch != nullptr) // features too large for shared memory: per-CTA slice of an L2-resident scratch buffer
-      S = scratch + (size_t)blockIdx.x * scratch_per_cta;
-    double *Tmy = Tw + (size_t)wid * 2 * n_all;
-    // row pairs are dealt out so that every warp gets a similar share of the triangular J >= I sweep
-    for (int it = 0; it * FT_WARPS < M; it++) {
-      const int I = (it & 1) ? (it * FT_WARPS + (FT_WARPS - 1 - wid)) : (it * FT_WARPS + wid);
-      if (I >= M)
-        continue;
-      const signed char *slI = mv.slot + 8 * I;
-      const int s0 = slI[0], s1 = slI[1], s2 = slI[2];
-      const double *B0 = mv.blk(I, 0), *B1 = mv.blk(I, 1), *B2 = mv.blk(I, 2);
-      // T_I[r][c] = sum_b sum_k B_b[r][k] * P[off_b + k][state(c)]; all loads of a column are issued before their use
-      // (P is L2-resident: ~20 dependent-latency round trips per column otherwise)
-      for (int c = lane; c < wf; c += 32) {
-        const int pc = fslot_off[lcol_slot[c]] + lcol_k[c];
-        double pv[20];
-        const double *P0 = P + (size_t)fslot_off[s0] * ldP + pc;
-        const double *P1 = P + (size_t)fslot_off[s1 >= 0 ? s1 : s0] * ldP + pc;
-        const double *P2 = P + (size_t)fslot_off[s2 >= 0 ? s2 : s0] * ldP + pc;
-#pragma unroll
-        for (int k = 0; k < 6; k++)
-          pv[k] = __ldg(P0 + (size_t)k * ldP);
-        if (s1 >= 0) {
-#pragma unroll
+    const int nr = rows - r0;
+    bool spd = true;
+    double c2 = 0.0;
+    if constexpr (BIG) {
+      // ---- S = H_x P_marg H_x' + s² I from the sparse blocks (rows x rows), warp per measurement row pair
+      const int ldS = rows | 1; // odd leading dimension: conflict-free row and column sweeps
+      double *S = scratch + (size_t)blockIdx.x * scratch_per_cta; // per-CTA slice of an L2-resident scratch buffer
+      double *Tmy = Tw + (size_t)wid * 2 * n_all;
+      // row pairs are dealt out so that every warp gets a similar share of the triangular J >= I sweep
+      for (int it = 0; it * FT_WARPS < M; it++) {
+        const int I = (it & 1) ? (it * FT_WARPS + (FT_WARPS - 1 - wid)) : (it * FT_WARPS + wid);
+        if (I >= M)
+          continue;
+        const signed char *slI = mv.slot + 8 * I;
+        const int s0 = slI[0], s1 = slI[1], s2 = slI[2];
+        const double *B0 = mv.blk(I, 0), *B1 = mv.blk(I, 1), *B2 = mv.blk(I, 2);
+        // T_I[r][c] = sum_b sum_k B_b[r][k] * P[off_b + k][state(c)]; all loads of a column are issued before their use
+        // (P is L2-resident: ~20 dependent-latency round trips per column otherwise)
+        for (int c = lane; c < wf; c += 32) {
+          const int pc = fslot_off[lcol_slot[c]] + lcol_k[c];
+          double pv[20];
+          const double *P0 = P + (size_t)fslot_off[s0] * ldP + pc;
+          const double *P1 = P + (size_t)fslot_off[s1 >= 0 ? s1 : s0] * ldP + pc;
+          const double *P2 = P + (size_t)fslot_off[s2 >= 0 ? s2 : s0] * ldP + pc;
+  #pragma unroll
           for (int k = 0; k < 6; k++)
-            pv[6 + k] = __ldg(P1 + (size_t)k * ldP);
-        }
-        if (s2 >= 0) {
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-            pv[12 + k] = __ldg(P2 + (size_t)k * ldP);
-        }
-        double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-          t0 += B0[k] * pv[k];
-          t1 += B0[8 + k] * pv[k];
-        }
-        if (s1 >= 0) {
-#pragma unroll
-          for (int k = 0; k < 6; k++) {
-            t0 += B1[k] * pv[6 + k];
-            t1 += B1[8 + k] * pv[6 + k];
-          }
-        }
-        if (s2 >= 0) {
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            t0 += B2[k] * pv[12 + k];
-            t1 += B2[8 + k] * pv[12 + k];
-          }
-        }
-        if (nblk > 3) {
-#pragma unroll
-          for (int b = 3; b < 6; b++) {
-            if (b >= nblk)
-              break;
-            const int sb = slI[b];
-            if (sb < 0)
-              continue;
-            const double *B = mv.blk(I, b);
-            const double *Pb = P + (size_t)fslot_off[sb] * ldP + pc;
-            const int wb = (b == 5) ? lmw : blk_w(b);
-            double pw[6];
-#pragma unroll
+            pv[k] = __ldg(P0 + (size_t)k * ldP);
+          if (s1 >= 0) {
+  #pragma unroll
             for (int k = 0; k < 6; k++)
-              pw[k] = (k < wb) ? __ldg(Pb + (size_t)k * ldP) : 0.0;
-#pragma unroll
+              pv[6 + k] = __ldg(P1 + (size_t)k * ldP);
+          }
+          if (s2 >= 0) {
+  #pragma unroll
+            for (int k = 0; k < 8; k++)
+              pv[12 + k] = __ldg(P2 + (size_t)k * ldP);
+          }
+          double t0 = 0.0, t1 = 0.0;
+  #pragma unroll
+          for (int k = 0; k < 6; k++) {
+            t0 += B0[k] * pv[k];
+            t1 += B0[8 + k] * pv[k];
+          }
+          if (s1 >= 0) {
+  #pragma unroll
             for (int k = 0; k < 6; k++) {
-              if (k < wb) {
-                t0 += B[k] * pw[k];
-                t1 += B[8 + k] * pw[k];
+              t0 += B1[k] * pv[6 + k];
+              t1 += B1[8 + k] * pv[6 + k];
+            }
+          }
+          if (s2 >= 0) {
+  #pragma unroll
+            for (int k = 0; k < 8; k++) {
+              t0 += B2[k] * pv[12 + k];
+              t1 += B2[8 + k] * pv[12 + k];
+            }
+          }
+          if (nblk > 3) {
+  #pragma unroll
+            for (int b = 3; b < 6; b++) {
+              if (b >= nblk)
+                break;
+              const int sb = slI[b];
+              if (sb < 0)
+                continue;
+              const double *B = mv.blk(I, b);
+              const double *Pb = P + (size_t)fslot_off[sb] * ldP + pc;
+              const int wb = (b == 5) ? lmw : blk_w(b);
+              double pw[6];
+  #pragma unroll
+              for (int k = 0; k < 6; k++)
+                pw[k] = (k < wb) ? __ldg(Pb + (size_t)k * ldP) : 0.0;
+  #pragma unroll
+              for (int k = 0; k < 6; k++) {
+                if (k < wb) {
+                  t0 += B[k] * pw[k];
+                  t1 += B[8 + k] * pw[k];
+                }
               }
             }
           }
+          Tmy[c] = t0;
+          Tmy[n_all + c] = t1;
         }
-        Tmy[c] = t0;
-        Tmy[n_all + c] = t1;
-      }
-      __syncwarp();
-      for (int J = I + lane; J < M; J += 32) {
-        const signed char *slJ = mv.slot + 8 * J;
-        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-#pragma unroll
-        for (int b = 0; b < 6; b++) {
-          if (b >= nblk)
-            break;
-          int sb = slJ[b];
-          if (sb < 0)
-            continue;
-          const double *B = mv.blk(J, b);
-          int wb = (b == 5) ? lmw : blk_w(b);
-          int c0 = slot2l[sb];
-          for (int k = 0; k < wb; k++) {
-            double ta = Tmy[c0 + k], tb = Tmy[n_all + c0 + k];
-            s00 += ta * B[k];
-            s01 += ta * B[8 + k];
-            s10 += tb * B[k];
-            s11 += tb * B[8 + k];
+        __syncwarp();
+        for (int J = I + lane; J < M; J += 32) {
+          const signed char *slJ = mv.slot + 8 * J;
+          double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+  #pragma unroll
+          for (int b = 0; b < 6; b++) {
+            if (b >= nblk)
+              break;
+            int sb = slJ[b];
+            if (sb < 0)
+              continue;
+            const double *B = mv.blk(J, b);
+            int wb = (b == 5) ? lmw : blk_w(b);
+            int c0 = slot2l[sb];
+            for (int k = 0; k < wb; k++) {
+              double ta = Tmy[c0 + k], tb = Tmy[n_all + c0 + k];
+              s00 += ta * B[k];
+              s01 += ta * B[8 + k];
+              s10 += tb * B[k];
+              s11 += tb * B[8 + k];
+            }
           }
+          if (J == I) {
+            s00 += sig2;
+            s11 += sig2;
+            s10 = s01; // exact symmetry of the diagonal 2x2 block
+          }
+          S[(2 * I) * ldS + 2 * J] = s00;
+          S[(2 * I) * ldS + 2 * J + 1] = s01;
+          S[(2 * I + 1) * ldS + 2 * J] = s10;
+          S[(2 * I + 1) * ldS + 2 * J + 1] = s11;
+          S[(2 * J) * ldS + 2 * I] = s00;
+          S[(2 * J + 1) * ldS + 2 * I] = s01;
+          S[(2 * J) * ldS + 2 * I + 1] = s10;
+          S[(2 * J + 1) * ldS + 2 * I + 1] = s11;
         }
-        if (J == I) {
-          s00 += sig2;
-          s11 += sig2;
-          s10 = s01; // exact symmetry of the diagonal 2x2 block
-        }
-        S[(2 * I) * ldS + 2 * J] = s00;
-        S[(2 * I) * ldS + 2 * J + 1] = s01;
-        S[(2 * I + 1) * ldS + 2 * J] = s10;
-        S[(2 * I + 1) * ldS + 2 * J + 1] = s11;
-        S[(2 * J) * ldS + 2 * I] = s00;
-        S[(2 * J + 1) * ldS + 2 * I] = s01;
-        S[(2 * J) * ldS + 2 * I + 1] = s10;
-        S[(2 * J + 1) * ldS + 2 * I + 1] = s11;
-      }
-      __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- S <- Q' S Q (both sides), only rows/cols 3.. are used afterwards
-    for (int pass = 0; pass < 2 && nproj > 0; pass++) {
-      for (int j = tid; j < rows; j += FT_THREADS) {
-        // pass 0: vector = column j (stride ldS); pass 1: vector = row j (stride 1)
-        const int st = (pass == 0) ? ldS : 1;
-        double *x = (pass == 0) ? (S + j) : (S + (size_t)j * ldS);
-        double w0 = 0, w1 = 0, w2 = 0;
-        for (int i = 0; i < rows; i++) {
-          double xv = x[(size_t)i * st];
-          w0 += V[3 * i] * xv;
-          w1 += V[3 * i + 1] * xv;
-          w2 += V[3 * i + 2] * xv;
-        }
-        double z0 = tau[0] * w0;
-        double z1 = tau[1] * (w1 - G10 * z0);
-        double z2 = tau[2] * (w2 - G20 * z0 - G21 * z1);
-        for (int i = 0; i < rows; i++)
-          x[(size_t)i * st] -= (V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2;
+        __syncwarp();
       }
       __syncthreads();
-    }
-    // projected residual as the extra row `rows` of S: r_o[i] = res[i] - V[i,:] z(res)
-    {
-      double z0 = Z[n_all], z1 = Z[(n_all + 1) + n_all], z2 = Z[2 * (n_all + 1) + n_all];
-      for (int i = tid; i < rows; i += FT_THREADS) {
-        double rv = mv.res[i] - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2);
-        S[(size_t)rows * ldS + i] = rv;
+
+      // ---- S <- Q' S Q (both sides), only rows/cols 3.. are used afterwards
+      for (int pass = 0; pass < 2 && nproj > 0; pass++) {
+        for (int j = tid; j < rows; j += FT_THREADS) {
+          // pass 0: vector = column j (stride ldS); pass 1: vector = row j (stride 1)
+          const int st = (pass == 0) ? ldS : 1;
+          double *x = (pass == 0) ? (S + j) : (S + (size_t)j * ldS);
+          double w0 = 0, w1 = 0, w2 = 0;
+          for (int i = 0; i < rows; i++) {
+            double xv = x[(size_t)i * st];
+            w0 += V[3 * i] * xv;
+            w1 += V[3 * i + 1] * xv;
+            w2 += V[3 * i + 2] * xv;
+          }
+          double z0 = tau[0] * w0;
+          double z1 = tau[1] * (w1 - G10 * z0);
+          double z2 = tau[2] * (w2 - G20 * z0 - G21 * z1);
+          for (int i = 0; i < rows; i++)
+            x[(size_t)i * st] -= (V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2;
+        }
+        __syncthreads();
       }
+      // projected residual as the extra row `rows` of S: r_o[i] = res[i] - V[i,:] z(res)
+      {
+        double z0 = Z[n_all], z1 = Z[(n_all + 1) + n_all], z2 = Z[2 * (n_all + 1) + n_all];
+        for (int i = tid; i < rows; i += FT_THREADS) {
+          double rv = mv.res[i] - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2);
+          S[(size_t)rows * ldS + i] = rv;
+        }
+      }
+      __syncthreads();
+      // ---- chi² = |L^-1 r_o|² on the trailing (rows-3) block
+      spd = chol_lower_block<FT_THREADS, 2>(S + r0 * ldS + r0, ldS, nr, 1, &ishare[1], red + FT_WARPS * 3 + 4);
+      c2 = 0.0;
+      for (int i = tid; i < nr; i += FT_THREADS) {
+        double y = S[(size_t)rows * ldS + r0 + i];
+        c2 += y * y;
+      }
+      double dummy1 = 0, dummy2 = 0;
+      block_sum3(c2, dummy1, dummy2, red);
+    } else {
+      FT_STAMP(3);
+      // ---- gate on the tile-packed triangle. chi² = r_o' (Q2' S Q2)^-1 r_o with S = H_x P_marg H_x' + s² I is evaluated
+      // without projecting S: for Q = [Q1 Q2] orthogonal,
+      //   (Q2' S Q2)^-1 = Q2' S^-1 Q2 - Q2' S^-1 Q1 (Q1' S^-1 Q1)^-1 Q1' S^-1 Q2,  so with S = L L', a = L^-1 r, C = L^-1 Q1:
+      //   chi² = a'a - (C'a)' (C'C)^-1 (C'a)       (the generalised-least-squares residual of r against range(H_f))
+      // r and the nproj columns of Q1 ride through the factorisation as right-hand-side rows. Q1 = Q E comes straight from
+      // the reflectors (Q x = x - V z with the reverse recurrence), so a rank-deficient H_f behaves as in the projected form.
+      const int nrows_t = rows + 1 + nproj;
+      const int NRB = (nrows_t + 7) >> 3;
+      const CtView cv = ct_view_carve(ctbase, NRB, &ishare[1]);
+      {
+        double zq[3][3]; // zq[j][k]: coefficient k of Q e_j
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const double w0 = V[3 * j], w1 = V[3 * j + 1], w2 = V[3 * j + 2];
+          const double z2 = tau[2] * w2;
+          const double z1 = tau[1] * (w1 - G21 * z2);
+          const double z0 = tau[0] * (w0 - G10 * z1 - G20 * z2);
+          zq[j][0] = z0, zq[j][1] = z1, zq[j][2] = z2;
+        }
+        for (int i = tid; i < rows; i += FT_THREADS) {
+          cv.T[ct_idx(rows, i)] = mv.res[i];
+          const double v0 = V[3 * i], v1 = V[3 * i + 1], v2 = V[3 * i + 2];
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+            if (j < nproj)
+              cv.T[ct_idx(rows + 1 + j, i)] = ((i == j) ? 1.0 : 0.0) - ((v0 * zq[j][0] + v1 * zq[j][1]) + v2 * zq[j][2]);
+        }
+      }
+      FT_STAMP(4);
+      // ---- S in chunks of Mc measurements. T = H_x P, one thread per compact column c: the six covariance rows of each
+      // measurement's clone are fetched by cp.async into a two-stage ring (PS; a thread only ever reads what it copied, so a
+      // wait_group is all the synchronisation the ring needs) two chunks ahead of their use; the rows of the camera's
+      // calibration stay in registers from one camera change to the next; the blocks shared by the whole track (anchor
+      // clone / anchor extrinsics / landmark) were staged in EX when the feature started. Then the 2x2 blocks S[I][J],
+      // J <= I, one thread per pair.
+      {
+        double pe[6], pi[8];
+        int cur_cam = -1, s1 = -1, s2 = -1;
+        for (int q = 0; q < nchunk; q++) {
+          const int I0 = q * Mc, I1 = min(M, I0 + Mc);
+          ft_cpa_wait<1>(); // chunk q has landed (only chunk q+1 may still be in flight)
+          for (int c = tid; c < wf; c += FT_THREADS) {
+            const double *Pc = P + (fslot_off[lcol_slot[c]] + lcol_k[c]);
+            if (wf > FT_THREADS)
+              cur_cam = -1; // several columns per thread: the calibration registers belong to one column at a time
+            for (int I = I0; I < I1; I++) {
+              const int cam = mcam[I];
+              if (cam != cur_cam) { // measurements are grouped by camera: twice per stereo track
+                cur_cam = cam;
+                s1 = mv.slot[8 * I + 1];
+                s2 = mv.slot[8 * I + 2];
+                if (s1 >= 0) {
+                  const double *Pr = Pc + (size_t)fslot_off[s1] * ldP;
+#pragma unroll
+                  for (int k = 0; k < 6; k++)
+                    pe[k] = __ldg(Pr + (size_t)k * ldP);
+                }
+                if (s2 >= 0) {
+                  const double *Pr = Pc + (size_t)fslot_off[s2] * ldP;
+#pragma unroll
+                  for (int k = 0; k < 8; k++)
+                    pi[k] = __ldg(Pr + (size_t)k * ldP);
+                }
+              }
+              const double *B0 = mv.blk(I, 0);
+              const double *ps = PS + ((size_t)((q & 1) * Mc + (I - I0)) * 6) * ldT + c;
+              double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+              for (int k = 0; k < 6; k++) {
+                const double pk = ps[(size_t)k * ldT];
+                t0 = fma(B0[k], pk, t0);
+                t1 = fma(B0[8 + k], pk, t1);
+              }
+              if (s1 >= 0) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                  t0 = fma(B0[16 + k], pe[k], t0);
+                  t1 = fma(B0[24 + k], pe[k], t1);
+                }
+              }
+              if (s2 >= 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                  t0 = fma(B0[32 + k], pi[k], t0);
+                  t1 = fma(B0[40 + k], pi[k], t1);
+                }
+              }
+              if (nblk > 3) {
+                const signed char *slI = mv.slot + 8 * I;
+#pragma unroll
+                for (int b = 3; b < 6; b++) {
+                  if (b < nblk && slI[b] >= 0) { // else folded into block 0/1 (same slot) or absent
+                    const double *B = mv.blk(I, b);
+                    const double *ex = EX + (size_t)((b - 3) * 6) * ldT + c;
+                    const int wb = (b == 5) ? lmw : 6;
+                    for (int k = 0; k < wb; k++) {
+                      const double pk = ex[(size_t)k * ldT];
+                      t0 = fma(B[k], pk, t0);
+                      t1 = fma(B[8 + k], pk, t1);
+                    }
+                  }
+                }
+              }
+              Tw[(size_t)(2 * (I - I0)) * ldT + c] = t0;
+              Tw[(size_t)(2 * (I - I0) + 1) * ldT + c] = t1;
+            }
+          }
+          __syncthreads();
+          stage_rows(q + 2); // into the stage this thread has just finished reading
+          FT_STAMP(5);
+          {
+            const int npair = (I1 - I0) * I0 + (((I1 - I0) * (I1 - I0 + 1)) >> 1); // sum over I of (I + 1)
+            for (int pidx = tid; pidx < npair; pidx += FT_THREADS) {
+              int I = I0, rem = pidx;
+              while (rem > I) {
+                rem -= I + 1;
+                I++;
+              }
+              const int J = rem;
+              const double *T0 = Tw + (size_t)(2 * (I - I0)) * ldT, *T1 = T0 + ldT;
+              const signed char *slJ = mv.slot + 8 * J;
+              double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll
+              for (int b = 0; b < 6; b++) {
+                if (b >= nblk)
+                  break;
+                const int sb = slJ[b];
+                if (sb < 0)
+                  continue;
+                const double *B = mv.blk(J, b);
+                const int wb = (b == 5) ? lmw : blk_w(b);
+                const int c0 = slot2l[sb];
+                for (int k = 0; k < wb; k++) {
+                  const double ta = T0[c0 + k], tb = T1[c0 + k];
+                  s00 = fma(ta, B[k], s00);
+                  s01 = fma(ta, B[8 + k], s01);
+                  s10 = fma(tb, B[k], s10);
+                  s11 = fma(tb, B[8 + k], s11);
+                }
+              }
+              if (J == I) {
+                s00 += sig2;
+                s11 += sig2;
+              } else {
+                cv.T[ct_idx(2 * I, 2 * J + 1)] = s01;
+              }
+              cv.T[ct_idx(2 * I, 2 * J)] = s00;
+              cv.T[ct_idx(2 * I + 1, 2 * J)] = s10;
+              cv.T[ct_idx(2 * I + 1, 2 * J + 1)] = s11;
+            }
+          }
+          __syncthreads();
+        }
+        ft_cpa_wait<0>();
+      }
+      FT_STAMP(6);
+      ft_gate_chol(ctbase, NRB, &ishare[1], rows, nrows_t);
+      FT_STAMP(7);
+      // a'a, C'a, C'C over the solved right-hand-side rows
+      double q[10];
+#pragma unroll
+      for (int e = 0; e < 10; e++)
+        q[e] = 0.0;
+      for (int i = tid; i < rows; i += FT_THREADS) {
+        const double a = cv.T[ct_idx(rows, i)];
+        double cq[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          if (j < nproj)
+            cq[j] = cv.T[ct_idx(rows + 1 + j, i)];
+        q[0] = fma(a, a, q[0]);
+        q[1] = fma(cq[0], a, q[1]);
+        q[2] = fma(cq[1], a, q[2]);
+        q[3] = fma(cq[2], a, q[3]);
+        q[4] = fma(cq[0], cq[0], q[4]);
+        q[5] = fma(cq[1], cq[0], q[5]);
+        q[6] = fma(cq[1], cq[1], q[6]);
+        q[7] = fma(cq[2], cq[0], q[7]);
+        q[8] = fma(cq[2], cq[1], q[8]);
+        q[9] = fma(cq[2], cq[2], q[9]);
+      }
+      block_sum_n<10>(q, red);
+      {
+        // (C'C) y = C'a by a 3x3 Cholesky; unused columns are the identity
+        const double W00 = nproj > 0 ? q[4] : 1.0, W11 = nproj > 1 ? q[6] : 1.0, W22 = nproj > 2 ? q[9] : 1.0;
+        const double l00 = sqrt(W00), l10 = q[5] / l00, l20 = q[7] / l00;
+        const double l11 = sqrt(W11 - l10 * l10), l21 = (q[8] - l20 * l10) / l11;
+        const double l22 = sqrt(W22 - l20 * l20 - l21 * l21);
+        const double y0 = q[1] / l00, y1 = (q[2] - l10 * y0) / l11, y2 = (q[3] - l20 * y0 - l21 * y1) / l22;
+        c2 = q[0] - ((y0 * y0 + y1 * y1) + y2 * y2);
+      }
+      spd = (ishare[1] == 0);
     }
-    __syncthreads();
-    // ---- chi² = |L^-1 r_o|² on the trailing (rows-3) block
-    const int nr = rows - r0;
-    bool spd = chol_lower_block<FT_THREADS, 2>(S + r0 * ldS + r0, ldS, nr, 1, &ishare[1], red + FT_WARPS * 3 + 4);
-    double c2 = 0.0;
-    for (int i = tid; i < nr; i += FT_THREADS) {
-      double y = S[(size_t)rows * ldS + r0 + i];
-      c2 += y * y;
-    }
-    double dummy1 = 0, dummy2 = 0;
-    block_sum3(c2, dummy1, dummy2, red);
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double chi2 = spd ? c2 : qnan;
     double chi2_check = chi2_table[min(nr, OVB_CHI2_TABLE_LEN - 1)];
@@ -861,6 +1167,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       if (gated)
         F->status = OVB_FEAT_CHI2;
     }
+    FT_STAMP(8);
     // ---- write the projected rows into the stacked matrix, canonical columns, coalesced
     for (int jb = 0; jb <= n_all; jb += FT_THREADS) {
       int j = jb + tid;
@@ -882,25 +1189,36 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
         for (int i = r0; i < rows; i++)
           out[(size_t)(i - r0) * ldH] = 0.0;
       } else {
+#pragma unroll 4
         for (int i = r0; i < rows; i++) {
-          double xv = (j == n_all) ? mv.res[i] : mv.x_at(i >> 1, i & 1, s, kk);
+          const int I = i >> 1, r = i & 1;
+          const int b = (j == n_all) ? 255 : mv.lut[(size_t)I * mv.lutw + s];
+          const double *src = (j == n_all) ? (mv.res + i) : (mv.blk(I, b == 255 ? 0 : b) + 8 * r + kk);
+          const double xl = *src;
+          const double xv = (j < n_all && b == 255) ? 0.0 : xl;
           out[(size_t)(i - r0) * ldH] = (xv - ((V[3 * i] * z0 + V[3 * i + 1] * z1) + V[3 * i + 2] * z2)) * wgt;
         }
       }
     }
+#ifdef FT_PROBE
+    if (tid == 0 && blockIdx.x == 0 && fi == sched_lo && mode == 0)
+      printf("feat M=%d wf=%d Mc=%d: jac %lld hh %lld Z %lld rhs %lld Tphase(last chunk) %lld Sphase->chol %lld chol %lld chi2 %lld write %lld | total %lld\n", M, ishare[0], Mc,
+             ft_t[1] - ft_t[0], ft_t[2] - ft_t[1], ft_t[3] - ft_t[2], ft_t[4] - ft_t[3], ft_t[5] - ft_t[4], ft_t[6] - ft_t[5], ft_t[7] - ft_t[6],
+             ft_t[8] - ft_t[7], clock64() - ft_t[8], clock64() - ft_t[0]);
+#endif
   }
 }
 
-static size_t feature_smem_bytes(int maxM, int n_all, int n_slots, int nblk, bool S_in_smem) {
+// big: the old layout (per-warp T rows; S in global scratch). else: T chunk buffer of Mc measurements + the tile Cholesky set.
+static size_t feature_smem_bytes(int maxM, int n_all, int n_slots, int nblk, bool big, int Mc) {
   size_t o = 0;
   const size_t n_all8 = (size_t)((n_all + 7) & ~7);
-  o += sizeof(double) * 16 * (size_t)nblk * maxM;
+  o += sizeof(double) * (size_t)(16 * nblk + 1) * maxM;
   o += sizeof(double) * 6 * (size_t)maxM;
   o += sizeof(double) * 2 * (size_t)maxM;
   o += sizeof(double) * 3 * 2 * (size_t)maxM;
   o += sizeof(double) * 3 * (size_t)(n_all + 1);
-  o += sizeof(double) * FT_WARPS * 2 * (size_t)n_all;
-  o += sizeof(double) * (FT_WARPS * 3 + 24);
+  o += sizeof(double) * (FT_WARPS * 12 + 24);
   o += sizeof(int) * OVB_MAX_VARS * 2;
   o += sizeof(int) * 8;
   o += sizeof(short) * n_all8 * 2;
@@ -910,11 +1228,20 @@ static size_t feature_smem_bytes(int maxM, int n_all, int n_slots, int nblk, boo
   o += (size_t)((maxM + 7) & ~7) * 2;
   o += (size_t)maxM * (size_t)((n_slots + 3) & ~3);
   o = (o + 15) & ~(size_t)15;
-  if (S_in_smem) {
-    int rows = 2 * maxM;
-    o += sizeof(double) * (size_t)(rows + 1) * (rows | 1);
+  if (big) {
+    o += sizeof(double) * FT_WARPS * 2 * (size_t)n_all;
+  } else {
+    const size_t tt = (size_t)(14 * Mc + (nblk > 3 ? 15 : 0)) * (n_all | 1); // T chunk, the two-stage ring of covariance rows, shared blocks
+    o += sizeof(double) * (tt + (tt & 1));
+    o += sizeof(double) * ct_view_doubles((2 * maxM + 4 + 7) >> 3);
   }
   return o;
+}
+// measurements per chunk (T rows + two ring stages of six covariance rows each = 14 rows per measurement): about 48 KB
+static int feature_chunk(int maxM, int n_all) {
+  int Mc = (48 * 1024) / (14 * 8 * (n_all | 1));
+  Mc = Mc < 1 ? 1 : Mc;
+  return Mc > maxM ? maxM : Mc;
 }
 
 // feat_order buffer lives right after the DevFeat array in ctx->d_feat's allocation (see ovb_api.cu)
@@ -931,19 +1258,27 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
   const int rep = ctx->h_opts->rep;
   const int nblk = (mode == 2) ? 6 : ((rep == OVB_REP_GLOBAL_3D || rep == OVB_REP_GLOBAL_FULL_INVERSE_DEPTH) ? 3 : 5);
   const size_t smem_limit = 227 * 1024;
-  bool S_in_smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, true) <= smem_limit;
-  size_t smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, S_in_smem);
+  int Mc = feature_chunk(maxM, n_all);
+  bool big = feature_smem_bytes(maxM, n_all, n_slots, nblk, false, Mc) > smem_limit;
+  if (big && feature_smem_bytes(maxM, n_all, n_slots, nblk, false, 1) <= smem_limit) { // a thinner T buffer still fits
+    while (Mc > 1 && feature_smem_bytes(maxM, n_all, n_slots, nblk, false, Mc) > smem_limit)
+      Mc--;
+    big = false;
+  }
+  size_t smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, big, Mc);
   if (!ctx->attr_done[1]) { // function attributes are per device: one flag per context
-    cudaFuncSetAttribute(k_feature_system<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
-    cudaFuncSetAttribute(k_feature_system<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    cudaFuncSetAttribute(k_feature_system<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    cudaFuncSetAttribute(k_feature_system<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    cudaFuncSetAttribute(k_feature_system<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    cudaFuncSetAttribute(k_feature_system<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     ctx->attr_done[1] = 1;
   }
   int dump_rows = ctx->dump_rows; // rows of the current dump (set by ovb_feature_jacobians)
   // ---- size classes. Shared memory per CTA grows with the square of the track length, and one launch must size it for
-  // its longest track: a single launch runs 2 CTAs/SM for everybody and the short tracks wait for a second wave. Three
+  // its longest track: a single launch runs 1-2 CTAs/SM for everybody and the short tracks wait for a second wave. Three
   // launches (tracks > 32, 17..32, <= 16 measurements; the schedule is already sorted longest-first, so classes are
-  // contiguous ranges) on three streams let 3-5 short-track CTAs share an SM next to the long ones.
-  if (mode == 0 && S_in_smem && ctx->feat_classes && n_feats > ctx->sm_count) {
+  // contiguous ranges) on three streams let several short-track CTAs share an SM next to the long ones.
+  if (mode == 0 && !big && ctx->feat_classes && n_feats > ctx->sm_count) {
     const int thr[2] = {32, 16};
     int bound[4] = {0, n_feats, n_feats, n_feats};
     for (int i = 0, c = 0; i < n_feats && c < 2; i++) {
@@ -962,13 +1297,16 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
       const DevFeat &longest = ctx->h_feat[ctx->h_feat[lo].sched];
       int cM = longest.m1 - longest.m0;
       cM = cM < 2 ? 2 : (cM > maxM ? maxM : cM);
-      const size_t csmem = feature_smem_bytes(cM, n_all, n_slots, nblk, true);
+      int cMc = feature_chunk(cM, n_all);
+      while (cMc > 1 && feature_smem_bytes(cM, n_all, n_slots, nblk, false, cMc) > smem_limit)
+        cMc--;
+      const size_t csmem = feature_smem_bytes(cM, n_all, n_slots, nblk, false, cMc);
       if (c > 0)
         cudaStreamWaitEvent(side[c], ctx->ev_fork, 0);
       ctx->stream = side[c];
-      ovb_launch(ctx, k_feature_system<false>, dim3(hi - lo), dim3(FT_THREADS), csmem, ctx->d_frame, ctx->d_opts, ctx->d_feat, lo, hi, bv,
+      ovb_launch(ctx, k_feature_system<false, false>, dim3(hi - lo), dim3(FT_THREADS), csmem, ctx->d_frame, ctx->d_opts, ctx->d_feat, lo, hi, bv,
                  ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, cM, nblk, (double *)nullptr,
-                 ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
+                 ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows, cMc);
       ctx->stream = main_stream;
       ctx->n_launch++;
       if (c > 0) {
@@ -980,18 +1318,26 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
   }
   int grid = n_feats;
   double *scratch = nullptr;
-  if (!S_in_smem) {
+  if (big) {
     if (grid > ctx->scratch_ctas)
       grid = ctx->scratch_ctas;
     scratch = ctx->d_scratch;
   }
   ctx->n_launch++;
-  if (mode == 2)
-    ovb_launch(ctx, k_feature_system<true>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, 0, n_feats, bv,
-               ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,
-               ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
-  else
-    ovb_launch(ctx, k_feature_system<false>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, 0, n_feats, bv,
-               ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,
-               ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
+#define OVB_FS_LAUNCH(SL, BG)                                                                                                                       \
+  ovb_launch(ctx, k_feature_system<SL, BG>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, 0, n_feats, bv, \
+             ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,                    \
+             ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows, Mc)
+  if (mode == 2) {
+    if (big)
+      OVB_FS_LAUNCH(true, true);
+    else
+      OVB_FS_LAUNCH(true, false);
+  } else {
+    if (big)
+      OVB_FS_LAUNCH(false, true);
+    else
+      OVB_FS_LAUNCH(false, false);
+  }
+#undef OVB_FS_LAUNCH
 }
