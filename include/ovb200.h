@@ -78,18 +78,19 @@ typedef enum {
   OVB_COLS_CANONICAL = 1             /* ascending covariance offset; post-update state/P agree to rounding */
 } ovb_col_order;
 
-/* How UpdaterHelper::measurement_compress_inplace (update/UpdaterHelper.cpp:456-487) is carried out. Both give
- * R'R = H'H and R'z = H'r to round-off. */
+/* How UpdaterHelper::measurement_compress_inplace (update/UpdaterHelper.cpp:456-487) is carried out. All give
+ * R'R = H'H and R'z = H'r; ovb_opts_default selects OVB_COMPRESS_CHOLQR2. */
 typedef enum {
-  OVB_COMPRESS_HOUSEHOLDER_TSQR = 0, /* default. blocked Householder TSQR; R equals the reference's Givens R row for row
-                                        (diag >= 0); post-update P/x within 1e-9 of the reference in every tested setup */
-  OVB_COMPRESS_NORMAL_EQUATIONS = 1, /* opt-in fast mode: [R z] = chol([H r]'[H r]), one streaming pass, ~4x faster.
-                                        Squares the condition number: with weakly observable calibration states in the
-                                        update (online intrinsics/extrinsics) the posterior of those states is only good to
-                                        ~1e-6 relative, so it misses the 1e-9 parity bar there (tests/test_gpu_gram.py) */
-  OVB_COMPRESS_CHOLQR2 = 2           /* shifted CholeskyQR2 on the FP64 tensor-core path (csrc/k_cholqr.cu): two Gram +
+  OVB_COMPRESS_HOUSEHOLDER_TSQR = 0, /* blocked Householder TSQR; R equals the reference's Givens R row for row (diag >= 0);
+                                        post-update P/x within 1e-9 of the reference in every tested setup */
+  OVB_COMPRESS_NORMAL_EQUATIONS = 1, /* opt-in: [R z] = chol([H r]'[H r]), one streaming pass. Squares the condition number:
+                                        with weakly observable calibration states in the update (online intrinsics /
+                                        extrinsics) the posterior of those states is only good to ~1e-6 relative, so it
+                                        misses the 1e-9 parity bar there (tests/test_gpu_gram.py) */
+  OVB_COMPRESS_CHOLQR2 = 2           /* default. Shifted CholeskyQR2 on the FP64 tensor-core path (csrc/k_cholqr.cu): two Gram +
                                         Cholesky passes with a row-wise triangular solve in between. No condition-number
-                                        loss in R'R / R'z; systems wider than 159 columns use the blocked
+                                        loss in R'R / R'z, same 1e-9 bar as the Householder path, ~3x
+                                        faster at the BASELINE sizes; systems wider than 159 columns use the blocked
                                         variant (up to 512 columns), beyond that the Householder TSQR */
 } ovb_compress_mode;
 

@@ -61,7 +61,7 @@ def default_opts(**kw) -> ovb_opts:
                  min_dcost=1e-6, lam_mult=10.0, min_dist=0.10, max_dist=60.0, max_baseline=40.0,
                  max_cond_number=10000.0, sigma_pix=1.0, chi2_multipler=1.0, do_fej=1, feat_rep=REP_GLOBAL_3D,
                  do_calib_camera_pose=0, do_calib_camera_intrinsics=0, col_order=COLS_REFERENCE_FIRST_SEEN,
-                 compress=COMPRESS_HOUSEHOLDER_TSQR)
+                 compress=COMPRESS_CHOLQR2)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise AttributeError(k)

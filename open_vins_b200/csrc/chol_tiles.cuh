@@ -28,12 +28,15 @@ __device__ __forceinline__ size_t ct_idx(int i, int j) { return (size_t)(ct_tri(
 //   T      ct_tri(NRB)*64      the triangle (zero past the edges)
 //   Xp0/1  NRB*8*CT_XP each    double-buffered panel (rows of the current block column as DMMA operands); must start zeroed
 //   invd   NRB*8               reciprocal pivots
+//   Linv   2*64                inverse of the current / next diagonal block (row-major 8x8, lower), for the helpers' panels
 //   dummyT 64, dummyX 2*CT_XP  zero tile / zero operand rows: target of the masked-out half of a tile pair
 struct CtView {
-  double *T, *Xp0, *Xp1, *invd, *dummyT, *dummyX;
+  double *T, *Xp0, *Xp1, *invd, *Linv0, *Linv1, *dummyT, *dummyX;
   int *flag;
 };
-__host__ __device__ inline size_t ct_view_doubles(int NRB) { return (size_t)((NRB * (NRB + 1)) / 2) * 64 + 2 * (size_t)NRB * 8 * CT_XP + (size_t)NRB * 8 + 64 + 2 * CT_XP; }
+__host__ __device__ inline size_t ct_view_doubles(int NRB) {
+  return (size_t)((NRB * (NRB + 1)) / 2) * 64 + 2 * (size_t)NRB * 8 * CT_XP + (size_t)NRB * 8 + 128 + 64 + 2 * CT_XP;
+}
 // carve a view out of `base` (16-byte aligned); flag_word: one int of shared memory
 __device__ __forceinline__ CtView ct_view_carve(double *base, int NRB, int *flag_word) {
   CtView v;
@@ -41,7 +44,9 @@ __device__ __forceinline__ CtView ct_view_carve(double *base, int NRB, int *flag
   v.Xp0 = v.T + (size_t)((NRB * (NRB + 1)) / 2) * 64;
   v.Xp1 = v.Xp0 + (size_t)NRB * 8 * CT_XP;
   v.invd = v.Xp1 + (size_t)NRB * 8 * CT_XP;
-  v.dummyT = v.invd + (size_t)NRB * 8;
+  v.Linv0 = v.invd + (size_t)NRB * 8;
+  v.Linv1 = v.Linv0 + 64;
+  v.dummyT = v.Linv1 + 64;
   v.dummyX = v.dummyT + 64;
   v.flag = flag_word;
   return v;
@@ -113,6 +118,44 @@ __device__ __forceinline__ void ct_diag8_frag(double &d0, double &d1, int nbk, d
     invd[lane] = myinv;
   if (bad && lane == 0)
     *flag = 1;
+}
+
+// L^-1 of a factored diagonal tile (zero past the columns whose reciprocal pivot is zero): lane c (and its copies in the
+// other quarters of the warp) carries column c through the forward substitution L m = e_c. The whole warp calls.
+__device__ __forceinline__ void ct_linv8(const double *Lt, const double *invd, double *Linv) {
+  const int lane = threadIdx.x & 31, cc = lane & 7;
+  double mc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    double s0 = (j == cc) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+    for (int t = 0; t < j; t++) {
+      if (t & 1)
+        s1 = fma(-Lt[j * 8 + t], mc[t], s1);
+      else
+        s0 = fma(-Lt[j * 8 + t], mc[t], s0);
+    }
+    mc[j] = (s0 + s1) * invd[j];
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      Linv[i * 8 + cc] = (i >= cc) ? mc[i] : 0.0;
+  }
+}
+
+// Panel tile (i, k): X = T(i,k) L_kk^-T as one 8x8x8 product on the tensor path, written back over the tile and into the
+// operand buffer (rows 8i.. of Xb). The whole warp calls.
+__device__ __forceinline__ void ct_panel_tile(const CtView &sm, int i, int k, const double *Linv, double *Xb) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  double *t = sm.T + (size_t)(ct_tri(i) + k) * 64;
+  const double a0 = t[g * 8 + q], a1 = t[g * 8 + q + 4];
+  const double b0 = Linv[g * 8 + q], b1 = Linv[g * 8 + q + 4]; // B[k][n] = Linv[n][k]
+  double2 d = make_double2(0.0, 0.0);
+  ct_dmma(d.x, d.y, a0, b0);
+  ct_dmma(d.x, d.y, a1, b1);
+  *reinterpret_cast<double2 *>(t + 2 * lane) = d;
+  *reinterpret_cast<double2 *>(Xb + (size_t)(8 * i + g) * CT_XP + 2 * q) = d;
 }
 
 // rows i0, i0+stride, ... of panel k: x L_kk' = S[i][kb..kb+8) by substitution, one thread per row (backward stable row by
@@ -239,7 +282,8 @@ __device__ __forceinline__ void ct_trail_row(const CtView &sm, const double *Xk,
 // cycles, and with helpers next to it warp 0's pivots ran 2-2.5x slower (tools/ubench/diag8_bench.cu: 854 cycles alone,
 // 1900-2400 in the first version of this kernel); the other warps of sub-partition 0 only keep the barriers company.
 // One __syncthreads per step; named barrier 1 joins the helpers after their panel rows, named barrier 2 hands block
-// column k+1 to warp 0 (it has never been seen to wait there: the helpers' first two moves are shorter than eight pivots).
+// column k+1 to warp 0 (it has never been seen to wait there: the helpers' first two moves are shorter than eight pivots),
+// named barrier 3 hands each factored diagonal block to the inverting warp.
 template <int THREADS, int NA_UNUSED>
 __device__ __forceinline__ void ct_chol_tiles(const CtView &sm, int n, int nrows, bool strict, double floor_d) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -247,8 +291,13 @@ __device__ __forceinline__ void ct_chol_tiles(const CtView &sm, int n, int nrows
   static_assert(NH >= 1, "need at least one helper warp");
   const bool helper = (wid & 3) != 0;
   const int hr = wid - 1 - (wid >> 2); // rank among the helpers
+  // With eight warps or more, warp 4 (idle, on warp 0's sub-partition) inverts each diagonal block as soon as warp 0 has
+  // stored it (named barrier 3), and the helpers' panel tiles become one 8x8x8 DMMA product each instead of a 36-step
+  // substitution per row. The explicit inverse makes the panel error proportional to cond(L_kk) (<= ~3e5 in the first
+  // CholeskyQR pass, whose factor only preconditions the second; O(1..1e3) elsewhere) instead of backward stable.
+  constexpr bool LINV = NW >= 8;
 #ifdef CQ_PROBE
-  long long p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0;
+  long long p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, acc[6] = {0, 0, 0, 0, 0, 0};
 #endif
   const int NB = (n + 7) >> 3, NRB = (nrows + 7) >> 3;
   if (wid == 0) {
@@ -256,7 +305,12 @@ __device__ __forceinline__ void ct_chol_tiles(const CtView &sm, int n, int nrows
     ct_diag8_frag(c.x, c.y, min(8, n), sm.invd, strict, floor_d, sm.flag);
     *reinterpret_cast<double2 *>(sm.T + 2 * lane) = c;
     __syncwarp();
+    if (LINV)
+      asm volatile("bar.arrive 3, 64;" ::: "memory");
     ct_panel_rows(sm.T, sm.Xp0, sm.invd, lane < 8 ? 8 + lane : nrows, 1 << 30, nrows, 0, min(8, n)); // the eight rows of block 1 only
+  } else if (LINV && wid == 4) {
+    asm volatile("bar.sync 3, 64;" ::: "memory");
+    ct_linv8(sm.T, sm.invd, sm.Linv0);
   }
   __syncthreads();
   for (int k = 0; k < NB; k++) {
@@ -264,6 +318,9 @@ __device__ __forceinline__ void ct_chol_tiles(const CtView &sm, int n, int nrows
     double *Xk = par ? sm.Xp1 : sm.Xp0, *Xn = par ? sm.Xp0 : sm.Xp1;
     const bool more = k + 1 < NB;
     CT_PROBE_T(p0);
+#ifdef CQ_PROBE
+    p1 = p2 = p3 = p4 = p0;
+#endif
     if (wid == 0) {
       if (more) {
         const int k1 = k + 1, nbk1 = min(8, n - 8 * k1);
@@ -274,14 +331,27 @@ __device__ __forceinline__ void ct_chol_tiles(const CtView &sm, int n, int nrows
         ct_diag8_frag(o.c.x, o.c.y, nbk1, sm.invd + 8 * k1, strict, floor_d, sm.flag);
         *o.cp = o.c;
         __syncwarp();
+        if (LINV)
+          asm volatile("bar.arrive 3, 64;" ::: "memory");
         CT_PROBE_T(p2);
         asm volatile("bar.sync 2, %0;" ::"r"((NH + 1) * 32) : "memory");
         CT_PROBE_T(p3);
         ct_panel_rows(sm.T, Xn, sm.invd, lane < 8 ? 8 * (k + 2) + lane : nrows, 1 << 30, nrows, k1, nbk1); // block k+2 only
         CT_PROBE_T(p4);
       }
+    } else if (LINV && wid == 4) {
+      if (more) {
+        asm volatile("bar.sync 3, 64;" ::: "memory");
+        ct_linv8(sm.T + (size_t)(ct_tri(k + 1) + k + 1) * 64, sm.invd + 8 * (k + 1), par ? sm.Linv0 : sm.Linv1);
+      }
     } else if (helper) {
-      ct_panel_rows(sm.T, Xk, sm.invd, 8 * (k + 2) + hr * 32 + lane, NH * 32, nrows, k, min(8, n - 8 * k));
+      if (LINV) {
+        const double *Lk = par ? sm.Linv1 : sm.Linv0;
+        for (int i = k + 2 + hr; i < NRB; i += NH)
+          ct_panel_tile(sm, i, k, Lk, Xk);
+      } else {
+        ct_panel_rows(sm.T, Xk, sm.invd, 8 * (k + 2) + hr * 32 + lane, NH * 32, nrows, k, min(8, n - 8 * k));
+      }
       if (NH > 1)
         ct_bar_group(1, NH * 32);
       else
@@ -310,12 +380,19 @@ __device__ __forceinline__ void ct_chol_tiles(const CtView &sm, int n, int nrows
     __syncthreads();
     CT_PROBE_T(p5);
 #ifdef CQ_PROBE
-    if ((k == 0 || k == 8 || k == 16) && (tid == 0 || tid == 32 || tid == THREADS - 32)) {
-      if (wid == 0)
-        printf("chol k=%d W0: diagupd %lld diag8 %lld wait %lld panel %lld tail %lld | step %lld\n", k, p1 - p0, p2 - p1, p3 - p2, p4 - p3, p5 - p4, p5 - p0);
-      else
-        printf("chol k=%d tid=%d H: panel %lld col %lld trailing %lld wait %lld | step %lld\n", k, tid, p1 - p0, p2 - p1, p3 - p2, p5 - p3, p5 - p0);
+    if (wid == 0) {
+      acc[0] += p1 - p0, acc[1] += p2 - p1, acc[2] += p3 - p2, acc[3] += p4 - p3, acc[4] += p5 - p4;
+    } else {
+      acc[0] += p1 - p0, acc[1] += p2 - p1, acc[2] += p3 - p2, acc[3] += p5 - p3;
     }
+    acc[5] += p5 - p0;
 #endif
   }
+#ifdef CQ_PROBE // sums over the block steps, one line per role
+  if (tid == 0)
+    printf("chol n=%d W0 (cycles over %d steps): diag update %lld pivots %lld wait %lld rows below %lld step tail %lld | %lld\n", n, NB, acc[0], acc[1], acc[2], acc[3],
+           acc[4], acc[5]);
+  if (tid == 32 || tid == THREADS - 32)
+    printf("chol n=%d helper warp %d: panel rows %lld column k+1 %lld trailing %lld wait %lld | %lld\n", n, wid, acc[0], acc[1], acc[2], acc[3], acc[5]);
+#endif
 }

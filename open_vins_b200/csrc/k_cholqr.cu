@@ -288,6 +288,7 @@ struct CqCholSmem {
   double T[(CQ_MAXRB * (CQ_MAXRB + 1) / 2) * 64];
   double Xp[2][CQ_MAXRB * 8 * CQ_XP];
   double invd[CQ_MAXRB * 8];
+  double Linv[2][64];       // inverse of the current / next diagonal block
   double red[32];
   double dummyT[64];        // target of the masked-out tile of a pair (operands zero: it stays zero)
   double dummyX[2 * CQ_XP]; // zero operand rows for it
@@ -310,6 +311,8 @@ __device__ __forceinline__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, 
   v.Xp0 = sm.Xp[0];
   v.Xp1 = sm.Xp[1];
   v.invd = sm.invd;
+  v.Linv0 = sm.Linv[0];
+  v.Linv1 = sm.Linv[1];
   v.dummyT = sm.dummyT;
   v.dummyX = sm.dummyX;
   v.flag = &sm.flag;

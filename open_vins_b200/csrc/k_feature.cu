@@ -99,12 +99,6 @@ template <int NV> __device__ __forceinline__ void block_sum_n(double (&v)[NV], d
   }
 }
 
-__device__ __forceinline__ void ft_cpa8(double *dst_smem, const double *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void ft_cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void ft_cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // The gate's factorisation as a real call: its register allocation (the 8x8 pivot block and the panel rows live in
 // registers) is then independent of what the feature kernel keeps live around it.
 __device__ __noinline__ void ft_gate_chol(double *ctbase, int NRB, int *flag, int n, int nrows) {
@@ -249,14 +243,14 @@ __device__ __forceinline__ bool rep_is_relative(int rep) {
 // BIG: tracks whose gate matrix does not fit shared memory (the launcher decides): S lives in a per-CTA slice of an
 // L2-resident scratch buffer and is factored by the scalar blocked Cholesky of chol.cuh after a two-sided projection.
 // Otherwise the gate runs on the tile-packed triangle of chol_tiles.cuh (DMMA) with the projection folded into the
-// right-hand sides (see "gate" below); Mc = measurements per chunk of the T = H_x P staging buffer.
+// right-hand sides (see "gate" below).
 template <bool SLAM, bool BIG>
 __global__ void __launch_bounds__(FT_THREADS, 2)
     k_feature_system(const DevFrame *__restrict__ fr, const DevOpts *__restrict__ dop, DevFeat *__restrict__ feats, int sched_lo, int n_feats,
                      BlobView bv,
                      const double *__restrict__ P, int ldP, const double *__restrict__ chi2_table, double *__restrict__ Hs, int ldH,
                      unsigned char *__restrict__ feat_order, int mode, int maxM, int nblk, double *__restrict__ scratch,
-                     size_t scratch_per_cta, double *__restrict__ dump, int ld_dump, int dump_rows, int Mc) {
+                     size_t scratch_per_cta, double *__restrict__ dump, int ld_dump, int dump_rows) {
   OVB_PDL_ENTER();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ovb_opts &op = dop->o;
@@ -314,14 +308,9 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
   mv.lut = smem_raw + o;
   o += (size_t)maxM * mv.lutw;
   o = (o + 15) & ~(size_t)15;
-  // BIG: Tw [FT_WARPS][2][n_all] (one measurement's T rows per warp).  else: TT [2*Mc][ldT] then the Cholesky working set
-  //      (T rows of a chunk), PS [2][Mc][6][ldT] (staged covariance rows), EX [15][ldT] when nblk > 3, then the Cholesky set
+  // Tw [FT_WARPS][2][n_all]: one measurement's two rows of T = H_x P per warp; then (not BIG) the gate's Cholesky working set
   double *Tw = (double *)(smem_raw + o);
-  const int ldT = n_all | 1;
-  double *PS = Tw + (size_t)2 * Mc * ldT;
-  double *EX = PS + (size_t)12 * Mc * ldT;
-  double *ctbase = EX + (nblk > 3 ? (size_t)15 * ldT : 0);
-  ctbase += ((ctbase - Tw) & 1); // 16-byte aligned
+  double *ctbase = Tw + (size_t)FT_WARPS * 2 * n_all; // 16-byte aligned: an even number of doubles after a 16-byte boundary
 
   // ---- frame tables -> shared memory (the bookkeeping below would otherwise chase them through L2 serially)
   for (int s = tid; s < n_slots; s += FT_THREADS) {
@@ -627,7 +616,6 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     __syncthreads();
 
     const int wf = ishare[0];
-    const int nchunk = (M + Mc - 1) / Mc;
     for (int j = tid; j < n_all; j += FT_THREADS) { // compact column -> (slot, offset in slot)
       const int sj = ccol_slot[j], l0 = slot2l[sj];
       if (l0 >= 0) {
@@ -636,42 +624,6 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       }
     }
     __syncthreads();
-    auto stage_rows = [&](int q) {
-      if (q < nchunk) {
-        const int I0 = q * Mc, I1 = min(M, I0 + Mc);
-        for (int c = tid; c < wf; c += FT_THREADS) {
-          const double *Pc = P + (fslot_off[lcol_slot[c]] + lcol_k[c]);
-          for (int I = I0; I < I1; I++) {
-            const double *Pr = Pc + (size_t)fslot_off[mcs[I]] * ldP;
-            double *dst = PS + ((size_t)((q & 1) * Mc + (I - I0)) * 6) * ldT + c;
-#pragma unroll
-            for (int k = 0; k < 6; k++)
-              ft_cpa8(dst + (size_t)k * ldT, Pr + (size_t)k * ldP);
-          }
-        }
-      }
-      ft_cpa_commit(); // one group per call, empty or not: the wait below counts groups
-    };
-    if constexpr (!BIG) {
-      if (mode != 1) { // the first copies fly while the reflectors are built
-        if (nblk > 3) {
-          for (int c = tid; c < wf; c += FT_THREADS) {
-            const double *Pc = P + (fslot_off[lcol_slot[c]] + lcol_k[c]);
-#pragma unroll
-            for (int b = 3; b < 6; b++) {
-              const int sb = (b == 3) ? s_anchor : (b == 4 ? s_anchor_ext : (slam ? (int)F->lm_slot : -1));
-              if (b < nblk && sb >= 0) {
-                const int wb = (b == 5) ? lmw : 6;
-                for (int k = 0; k < wb; k++)
-                  ft_cpa8(EX + (size_t)((b - 3) * 6 + k) * ldT + c, Pc + (size_t)(fslot_off[sb] + k) * ldP);
-              }
-            }
-          }
-        }
-        stage_rows(0); // its group also carries the EX copies
-        stage_rows(1);
-      }
-    }
     if (mode == 1) {
       // dense dump: [Hf rows x 3][res rows][Hx rows x ld_dump], rows indexed 2*m0 + local
       double *dHf = dump, *dres = dump + (size_t)dump_rows * 3, *dHx = dump + (size_t)dump_rows * 4;
@@ -803,114 +755,134 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     const int nr = rows - r0;
     bool spd = true;
     double c2 = 0.0;
-    if constexpr (BIG) {
-      // ---- S = H_x P_marg H_x' + s² I from the sparse blocks (rows x rows), warp per measurement row pair
-      const int ldS = rows | 1; // odd leading dimension: conflict-free row and column sweeps
-      double *S = scratch + (size_t)blockIdx.x * scratch_per_cta; // per-CTA slice of an L2-resident scratch buffer
-      double *Tmy = Tw + (size_t)wid * 2 * n_all;
-      // row pairs are dealt out so that every warp gets a similar share of the triangular J >= I sweep
-      for (int it = 0; it * FT_WARPS < M; it++) {
-        const int I = (it & 1) ? (it * FT_WARPS + (FT_WARPS - 1 - wid)) : (it * FT_WARPS + wid);
-        if (I >= M)
-          continue;
-        const signed char *slI = mv.slot + 8 * I;
-        const int s0 = slI[0], s1 = slI[1], s2 = slI[2];
-        const double *B0 = mv.blk(I, 0), *B1 = mv.blk(I, 1), *B2 = mv.blk(I, 2);
-        // T_I[r][c] = sum_b sum_k B_b[r][k] * P[off_b + k][state(c)]; all loads of a column are issued before their use
-        // (P is L2-resident: ~20 dependent-latency round trips per column otherwise)
-        for (int c = lane; c < wf; c += 32) {
-          const int pc = fslot_off[lcol_slot[c]] + lcol_k[c];
-          double pv[20];
-          const double *P0 = P + (size_t)fslot_off[s0] * ldP + pc;
-          const double *P1 = P + (size_t)fslot_off[s1 >= 0 ? s1 : s0] * ldP + pc;
-          const double *P2 = P + (size_t)fslot_off[s2 >= 0 ? s2 : s0] * ldP + pc;
-  #pragma unroll
+    FT_STAMP(3);
+    // ---- S = H_x P_marg H_x' + s² I from the sparse blocks (rows x rows), warp per measurement row pair
+    // BIG: full symmetric S in a per-CTA slice of an L2-resident scratch buffer (odd leading dimension: conflict-free row and
+    // column sweeps); else the lower triangle goes straight into the tile-packed layout of the gate's Cholesky
+    const int ldS = rows | 1;
+    double *S = BIG ? scratch + (size_t)blockIdx.x * scratch_per_cta : nullptr;
+    const int NRB = (rows + 1 + nproj + 7) >> 3;
+    const CtView cv = ct_view_carve(ctbase, NRB, &ishare[1]);
+    double *Tmy = Tw + (size_t)wid * 2 * n_all;
+    // row pairs are dealt out so that every warp gets a similar share of the triangular J >= I sweep
+    for (int it = 0; it * FT_WARPS < M; it++) {
+      const int I = (it & 1) ? (it * FT_WARPS + (FT_WARPS - 1 - wid)) : (it * FT_WARPS + wid);
+      if (I >= M)
+        continue;
+      const signed char *slI = mv.slot + 8 * I;
+      const int s0 = slI[0], s1 = slI[1], s2 = slI[2];
+      const double *B0 = mv.blk(I, 0), *B1 = mv.blk(I, 1), *B2 = mv.blk(I, 2);
+      // T_I[r][c] = sum_b sum_k B_b[r][k] * P[off_b + k][state(c)]; all loads of a column are issued before their use
+      // (P is L2-resident: ~20 dependent-latency round trips per column otherwise)
+      for (int c = lane; c < wf; c += 32) {
+        const int pc = fslot_off[lcol_slot[c]] + lcol_k[c];
+        double pv[20];
+        const double *P0 = P + (size_t)fslot_off[s0] * ldP + pc;
+        const double *P1 = P + (size_t)fslot_off[s1 >= 0 ? s1 : s0] * ldP + pc;
+        const double *P2 = P + (size_t)fslot_off[s2 >= 0 ? s2 : s0] * ldP + pc;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          pv[k] = __ldg(P0 + (size_t)k * ldP);
+        if (s1 >= 0) {
+#pragma unroll
           for (int k = 0; k < 6; k++)
-            pv[k] = __ldg(P0 + (size_t)k * ldP);
-          if (s1 >= 0) {
-  #pragma unroll
-            for (int k = 0; k < 6; k++)
-              pv[6 + k] = __ldg(P1 + (size_t)k * ldP);
-          }
-          if (s2 >= 0) {
-  #pragma unroll
-            for (int k = 0; k < 8; k++)
-              pv[12 + k] = __ldg(P2 + (size_t)k * ldP);
-          }
-          double t0 = 0.0, t1 = 0.0;
-  #pragma unroll
+            pv[6 + k] = __ldg(P1 + (size_t)k * ldP);
+        }
+        if (s2 >= 0) {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            pv[12 + k] = __ldg(P2 + (size_t)k * ldP);
+        }
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          t0 = fma(B0[k], pv[k], t0);
+          t1 = fma(B0[8 + k], pv[k], t1);
+        }
+        if (s1 >= 0) {
+#pragma unroll
           for (int k = 0; k < 6; k++) {
-            t0 += B0[k] * pv[k];
-            t1 += B0[8 + k] * pv[k];
+            t0 = fma(B1[k], pv[6 + k], t0);
+            t1 = fma(B1[8 + k], pv[6 + k], t1);
           }
-          if (s1 >= 0) {
-  #pragma unroll
+        }
+        if (s2 >= 0) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            t0 = fma(B2[k], pv[12 + k], t0);
+            t1 = fma(B2[8 + k], pv[12 + k], t1);
+          }
+        }
+        if (nblk > 3) {
+#pragma unroll
+          for (int b = 3; b < 6; b++) {
+            if (b >= nblk)
+              break;
+            const int sb = slI[b];
+            if (sb < 0)
+              continue;
+            const double *B = mv.blk(I, b);
+            const double *Pb = P + (size_t)fslot_off[sb] * ldP + pc;
+            const int wb = (b == 5) ? lmw : blk_w(b);
+            double pw[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              pw[k] = (k < wb) ? __ldg(Pb + (size_t)k * ldP) : 0.0;
+#pragma unroll
             for (int k = 0; k < 6; k++) {
-              t0 += B1[k] * pv[6 + k];
-              t1 += B1[8 + k] * pv[6 + k];
-            }
-          }
-          if (s2 >= 0) {
-  #pragma unroll
-            for (int k = 0; k < 8; k++) {
-              t0 += B2[k] * pv[12 + k];
-              t1 += B2[8 + k] * pv[12 + k];
-            }
-          }
-          if (nblk > 3) {
-  #pragma unroll
-            for (int b = 3; b < 6; b++) {
-              if (b >= nblk)
-                break;
-              const int sb = slI[b];
-              if (sb < 0)
-                continue;
-              const double *B = mv.blk(I, b);
-              const double *Pb = P + (size_t)fslot_off[sb] * ldP + pc;
-              const int wb = (b == 5) ? lmw : blk_w(b);
-              double pw[6];
-  #pragma unroll
-              for (int k = 0; k < 6; k++)
-                pw[k] = (k < wb) ? __ldg(Pb + (size_t)k * ldP) : 0.0;
-  #pragma unroll
-              for (int k = 0; k < 6; k++) {
-                if (k < wb) {
-                  t0 += B[k] * pw[k];
-                  t1 += B[8 + k] * pw[k];
-                }
+              if (k < wb) {
+                t0 = fma(B[k], pw[k], t0);
+                t1 = fma(B[8 + k], pw[k], t1);
               }
             }
           }
-          Tmy[c] = t0;
-          Tmy[n_all + c] = t1;
         }
-        __syncwarp();
-        for (int J = I + lane; J < M; J += 32) {
-          const signed char *slJ = mv.slot + 8 * J;
-          double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-  #pragma unroll
-          for (int b = 0; b < 6; b++) {
-            if (b >= nblk)
-              break;
-            int sb = slJ[b];
-            if (sb < 0)
-              continue;
-            const double *B = mv.blk(J, b);
-            int wb = (b == 5) ? lmw : blk_w(b);
-            int c0 = slot2l[sb];
-            for (int k = 0; k < wb; k++) {
-              double ta = Tmy[c0 + k], tb = Tmy[n_all + c0 + k];
-              s00 += ta * B[k];
-              s01 += ta * B[8 + k];
-              s10 += tb * B[k];
-              s11 += tb * B[8 + k];
-            }
+        Tmy[c] = t0;
+        Tmy[n_all + c] = t1;
+      }
+      __syncwarp();
+      for (int J = I + lane; J < M; J += 32) {
+        const signed char *slJ = mv.slot + 8 * J;
+        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+        // block widths are compile-time (6 6 8 6 6, landmark 1 or 3): the loads of a block are issued together
+#define FT_S_BLOCK(BI, W)                                                                       \
+  if ((BI) < nblk) {                                                                            \
+    const int sb = slJ[BI];                                                                     \
+    if (sb >= 0) {                                                                              \
+      const double *B = mv.blk(J, BI);                                                          \
+      const double *ta_ = Tmy + slot2l[sb], *tb_ = ta_ + n_all;                                 \
+      _Pragma("unroll") for (int k = 0; k < (W); k++) {                                         \
+        const double ta = ta_[k], tb = tb_[k];                                                  \
+        s00 = fma(ta, B[k], s00);                                                               \
+        s01 = fma(ta, B[8 + k], s01);                                                           \
+        s10 = fma(tb, B[k], s10);                                                               \
+        s11 = fma(tb, B[8 + k], s11);                                                           \
+      }                                                                                         \
+    }                                                                                           \
+  }
+        FT_S_BLOCK(0, 6)
+        FT_S_BLOCK(1, 6)
+        FT_S_BLOCK(2, 8)
+        FT_S_BLOCK(3, 6)
+        FT_S_BLOCK(4, 6)
+#undef FT_S_BLOCK
+        if (nblk > 5 && slJ[5] >= 0) {
+          const double *B = mv.blk(J, 5);
+          const double *ta_ = Tmy + slot2l[slJ[5]], *tb_ = ta_ + n_all;
+          for (int k = 0; k < lmw; k++) {
+            const double ta = ta_[k], tb = tb_[k];
+            s00 = fma(ta, B[k], s00);
+            s01 = fma(ta, B[8 + k], s01);
+            s10 = fma(tb, B[k], s10);
+            s11 = fma(tb, B[8 + k], s11);
           }
-          if (J == I) {
-            s00 += sig2;
-            s11 += sig2;
-            s10 = s01; // exact symmetry of the diagonal 2x2 block
-          }
+        }
+        if (J == I) {
+          s00 += sig2;
+          s11 += sig2;
+          s10 = s01; // exact symmetry of the diagonal 2x2 block
+        }
+        if constexpr (BIG) {
           S[(2 * I) * ldS + 2 * J] = s00;
           S[(2 * I) * ldS + 2 * J + 1] = s01;
           S[(2 * I + 1) * ldS + 2 * J] = s10;
@@ -919,11 +891,20 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
           S[(2 * J + 1) * ldS + 2 * I] = s01;
           S[(2 * J) * ldS + 2 * I + 1] = s10;
           S[(2 * J + 1) * ldS + 2 * I + 1] = s11;
+        } else { // s_ab = S[2I+a][2J+b] = S[2J+b][2I+a], J >= I: the lower triangle
+          cv.T[ct_idx(2 * J, 2 * I)] = s00;
+          cv.T[ct_idx(2 * J + 1, 2 * I)] = s01;
+          if (J != I)
+            cv.T[ct_idx(2 * J, 2 * I + 1)] = s10;
+          cv.T[ct_idx(2 * J + 1, 2 * I + 1)] = s11;
         }
-        __syncwarp();
       }
-      __syncthreads();
+      __syncwarp();
+    }
+    __syncthreads();
 
+    FT_STAMP(4);
+    if constexpr (BIG) {
       // ---- S <- Q' S Q (both sides), only rows/cols 3.. are used afterwards
       for (int pass = 0; pass < 2 && nproj > 0; pass++) {
         for (int j = tid; j < rows; j += FT_THREADS) {
@@ -964,7 +945,6 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       double dummy1 = 0, dummy2 = 0;
       block_sum3(c2, dummy1, dummy2, red);
     } else {
-      FT_STAMP(3);
       // ---- gate on the tile-packed triangle. chi² = r_o' (Q2' S Q2)^-1 r_o with S = H_x P_marg H_x' + s² I is evaluated
       // without projecting S: for Q = [Q1 Q2] orthogonal,
       //   (Q2' S Q2)^-1 = Q2' S^-1 Q2 - Q2' S^-1 Q1 (Q1' S^-1 Q1)^-1 Q1' S^-1 Q2,  so with S = L L', a = L^-1 r, C = L^-1 Q1:
@@ -972,8 +952,6 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
       // r and the nproj columns of Q1 ride through the factorisation as right-hand-side rows. Q1 = Q E comes straight from
       // the reflectors (Q x = x - V z with the reverse recurrence), so a rank-deficient H_f behaves as in the projected form.
       const int nrows_t = rows + 1 + nproj;
-      const int NRB = (nrows_t + 7) >> 3;
-      const CtView cv = ct_view_carve(ctbase, NRB, &ishare[1]);
       {
         double zq[3][3]; // zq[j][k]: coefficient k of Q e_j
 #pragma unroll
@@ -992,133 +970,6 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
             if (j < nproj)
               cv.T[ct_idx(rows + 1 + j, i)] = ((i == j) ? 1.0 : 0.0) - ((v0 * zq[j][0] + v1 * zq[j][1]) + v2 * zq[j][2]);
         }
-      }
-      FT_STAMP(4);
-      // ---- S in chunks of Mc measurements. T = H_x P, one thread per compact column c: the six covariance rows of each
-      // measurement's clone are fetched by cp.async into a two-stage ring (PS; a thread only ever reads what it copied, so a
-      // wait_group is all the synchronisation the ring needs) two chunks ahead of their use; the rows of the camera's
-      // calibration stay in registers from one camera change to the next; the blocks shared by the whole track (anchor
-      // clone / anchor extrinsics / landmark) were staged in EX when the feature started. Then the 2x2 blocks S[I][J],
-      // J <= I, one thread per pair.
-      {
-        double pe[6], pi[8];
-        int cur_cam = -1, s1 = -1, s2 = -1;
-        for (int q = 0; q < nchunk; q++) {
-          const int I0 = q * Mc, I1 = min(M, I0 + Mc);
-          ft_cpa_wait<1>(); // chunk q has landed (only chunk q+1 may still be in flight)
-          for (int c = tid; c < wf; c += FT_THREADS) {
-            const double *Pc = P + (fslot_off[lcol_slot[c]] + lcol_k[c]);
-            if (wf > FT_THREADS)
-              cur_cam = -1; // several columns per thread: the calibration registers belong to one column at a time
-            for (int I = I0; I < I1; I++) {
-              const int cam = mcam[I];
-              if (cam != cur_cam) { // measurements are grouped by camera: twice per stereo track
-                cur_cam = cam;
-                s1 = mv.slot[8 * I + 1];
-                s2 = mv.slot[8 * I + 2];
-                if (s1 >= 0) {
-                  const double *Pr = Pc + (size_t)fslot_off[s1] * ldP;
-#pragma unroll
-                  for (int k = 0; k < 6; k++)
-                    pe[k] = __ldg(Pr + (size_t)k * ldP);
-                }
-                if (s2 >= 0) {
-                  const double *Pr = Pc + (size_t)fslot_off[s2] * ldP;
-#pragma unroll
-                  for (int k = 0; k < 8; k++)
-                    pi[k] = __ldg(Pr + (size_t)k * ldP);
-                }
-              }
-              const double *B0 = mv.blk(I, 0);
-              const double *ps = PS + ((size_t)((q & 1) * Mc + (I - I0)) * 6) * ldT + c;
-              double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-              for (int k = 0; k < 6; k++) {
-                const double pk = ps[(size_t)k * ldT];
-                t0 = fma(B0[k], pk, t0);
-                t1 = fma(B0[8 + k], pk, t1);
-              }
-              if (s1 >= 0) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) {
-                  t0 = fma(B0[16 + k], pe[k], t0);
-                  t1 = fma(B0[24 + k], pe[k], t1);
-                }
-              }
-              if (s2 >= 0) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                  t0 = fma(B0[32 + k], pi[k], t0);
-                  t1 = fma(B0[40 + k], pi[k], t1);
-                }
-              }
-              if (nblk > 3) {
-                const signed char *slI = mv.slot + 8 * I;
-#pragma unroll
-                for (int b = 3; b < 6; b++) {
-                  if (b < nblk && slI[b] >= 0) { // else folded into block 0/1 (same slot) or absent
-                    const double *B = mv.blk(I, b);
-                    const double *ex = EX + (size_t)((b - 3) * 6) * ldT + c;
-                    const int wb = (b == 5) ? lmw : 6;
-                    for (int k = 0; k < wb; k++) {
-                      const double pk = ex[(size_t)k * ldT];
-                      t0 = fma(B[k], pk, t0);
-                      t1 = fma(B[8 + k], pk, t1);
-                    }
-                  }
-                }
-              }
-              Tw[(size_t)(2 * (I - I0)) * ldT + c] = t0;
-              Tw[(size_t)(2 * (I - I0) + 1) * ldT + c] = t1;
-            }
-          }
-          __syncthreads();
-          stage_rows(q + 2); // into the stage this thread has just finished reading
-          FT_STAMP(5);
-          {
-            const int npair = (I1 - I0) * I0 + (((I1 - I0) * (I1 - I0 + 1)) >> 1); // sum over I of (I + 1)
-            for (int pidx = tid; pidx < npair; pidx += FT_THREADS) {
-              int I = I0, rem = pidx;
-              while (rem > I) {
-                rem -= I + 1;
-                I++;
-              }
-              const int J = rem;
-              const double *T0 = Tw + (size_t)(2 * (I - I0)) * ldT, *T1 = T0 + ldT;
-              const signed char *slJ = mv.slot + 8 * J;
-              double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-#pragma unroll
-              for (int b = 0; b < 6; b++) {
-                if (b >= nblk)
-                  break;
-                const int sb = slJ[b];
-                if (sb < 0)
-                  continue;
-                const double *B = mv.blk(J, b);
-                const int wb = (b == 5) ? lmw : blk_w(b);
-                const int c0 = slot2l[sb];
-                for (int k = 0; k < wb; k++) {
-                  const double ta = T0[c0 + k], tb = T1[c0 + k];
-                  s00 = fma(ta, B[k], s00);
-                  s01 = fma(ta, B[8 + k], s01);
-                  s10 = fma(tb, B[k], s10);
-                  s11 = fma(tb, B[8 + k], s11);
-                }
-              }
-              if (J == I) {
-                s00 += sig2;
-                s11 += sig2;
-              } else {
-                cv.T[ct_idx(2 * I, 2 * J + 1)] = s01;
-              }
-              cv.T[ct_idx(2 * I, 2 * J)] = s00;
-              cv.T[ct_idx(2 * I + 1, 2 * J)] = s10;
-              cv.T[ct_idx(2 * I + 1, 2 * J + 1)] = s11;
-            }
-          }
-          __syncthreads();
-        }
-        ft_cpa_wait<0>();
       }
       FT_STAMP(6);
       ft_gate_chol(ctbase, NRB, &ishare[1], rows, nrows_t);
@@ -1202,15 +1053,15 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
     }
 #ifdef FT_PROBE
     if (tid == 0 && blockIdx.x == 0 && fi == sched_lo && mode == 0)
-      printf("feat M=%d wf=%d Mc=%d: jac %lld hh %lld Z %lld rhs %lld Tphase(last chunk) %lld Sphase->chol %lld chol %lld chi2 %lld write %lld | total %lld\n", M, ishare[0], Mc,
-             ft_t[1] - ft_t[0], ft_t[2] - ft_t[1], ft_t[3] - ft_t[2], ft_t[4] - ft_t[3], ft_t[5] - ft_t[4], ft_t[6] - ft_t[5], ft_t[7] - ft_t[6],
-             ft_t[8] - ft_t[7], clock64() - ft_t[8], clock64() - ft_t[0]);
+      printf("feat M=%d wf=%d: jac %lld hh %lld Z %lld | S sweep %lld | rhs rows %lld chol %lld chi2 %lld write %lld | total %lld\n", M, ishare[0],
+             ft_t[1] - ft_t[0], ft_t[2] - ft_t[1], ft_t[3] - ft_t[2], ft_t[4] - ft_t[3], ft_t[6] - ft_t[4], ft_t[7] - ft_t[6], ft_t[8] - ft_t[7],
+             clock64() - ft_t[8], clock64() - ft_t[0]);
 #endif
   }
 }
 
-// big: the old layout (per-warp T rows; S in global scratch). else: T chunk buffer of Mc measurements + the tile Cholesky set.
-static size_t feature_smem_bytes(int maxM, int n_all, int n_slots, int nblk, bool big, int Mc) {
+// big: S lives in global scratch; else the gate's tile Cholesky working set follows the per-warp T rows
+static size_t feature_smem_bytes(int maxM, int n_all, int n_slots, int nblk, bool big) {
   size_t o = 0;
   const size_t n_all8 = (size_t)((n_all + 7) & ~7);
   o += sizeof(double) * (size_t)(16 * nblk + 1) * maxM;
@@ -1228,20 +1079,10 @@ static size_t feature_smem_bytes(int maxM, int n_all, int n_slots, int nblk, boo
   o += (size_t)((maxM + 7) & ~7) * 2;
   o += (size_t)maxM * (size_t)((n_slots + 3) & ~3);
   o = (o + 15) & ~(size_t)15;
-  if (big) {
-    o += sizeof(double) * FT_WARPS * 2 * (size_t)n_all;
-  } else {
-    const size_t tt = (size_t)(14 * Mc + (nblk > 3 ? 15 : 0)) * (n_all | 1); // T chunk, the two-stage ring of covariance rows, shared blocks
-    o += sizeof(double) * (tt + (tt & 1));
+  o += sizeof(double) * FT_WARPS * 2 * (size_t)n_all;
+  if (!big)
     o += sizeof(double) * ct_view_doubles((2 * maxM + 4 + 7) >> 3);
-  }
   return o;
-}
-// measurements per chunk (T rows + two ring stages of six covariance rows each = 14 rows per measurement): about 48 KB
-static int feature_chunk(int maxM, int n_all) {
-  int Mc = (48 * 1024) / (14 * 8 * (n_all | 1));
-  Mc = Mc < 1 ? 1 : Mc;
-  return Mc > maxM ? maxM : Mc;
 }
 
 // feat_order buffer lives right after the DevFeat array in ctx->d_feat's allocation (see ovb_api.cu)
@@ -1258,14 +1099,8 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
   const int rep = ctx->h_opts->rep;
   const int nblk = (mode == 2) ? 6 : ((rep == OVB_REP_GLOBAL_3D || rep == OVB_REP_GLOBAL_FULL_INVERSE_DEPTH) ? 3 : 5);
   const size_t smem_limit = 227 * 1024;
-  int Mc = feature_chunk(maxM, n_all);
-  bool big = feature_smem_bytes(maxM, n_all, n_slots, nblk, false, Mc) > smem_limit;
-  if (big && feature_smem_bytes(maxM, n_all, n_slots, nblk, false, 1) <= smem_limit) { // a thinner T buffer still fits
-    while (Mc > 1 && feature_smem_bytes(maxM, n_all, n_slots, nblk, false, Mc) > smem_limit)
-      Mc--;
-    big = false;
-  }
-  size_t smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, big, Mc);
+  const bool big = feature_smem_bytes(maxM, n_all, n_slots, nblk, false) > smem_limit;
+  size_t smem = feature_smem_bytes(maxM, n_all, n_slots, nblk, big);
   if (!ctx->attr_done[1]) { // function attributes are per device: one flag per context
     cudaFuncSetAttribute(k_feature_system<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     cudaFuncSetAttribute(k_feature_system<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
@@ -1297,16 +1132,13 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
       const DevFeat &longest = ctx->h_feat[ctx->h_feat[lo].sched];
       int cM = longest.m1 - longest.m0;
       cM = cM < 2 ? 2 : (cM > maxM ? maxM : cM);
-      int cMc = feature_chunk(cM, n_all);
-      while (cMc > 1 && feature_smem_bytes(cM, n_all, n_slots, nblk, false, cMc) > smem_limit)
-        cMc--;
-      const size_t csmem = feature_smem_bytes(cM, n_all, n_slots, nblk, false, cMc);
+      const size_t csmem = feature_smem_bytes(cM, n_all, n_slots, nblk, false);
       if (c > 0)
         cudaStreamWaitEvent(side[c], ctx->ev_fork, 0);
       ctx->stream = side[c];
       ovb_launch(ctx, k_feature_system<false, false>, dim3(hi - lo), dim3(FT_THREADS), csmem, ctx->d_frame, ctx->d_opts, ctx->d_feat, lo, hi, bv,
                  ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, cM, nblk, (double *)nullptr,
-                 ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows, cMc);
+                 ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows);
       ctx->stream = main_stream;
       ctx->n_launch++;
       if (c > 0) {
@@ -1327,7 +1159,7 @@ void launch_feature_system(ovb_ctx *ctx, int n_feats, BlobView bv, int ldH, int 
 #define OVB_FS_LAUNCH(SL, BG)                                                                                                                       \
   ovb_launch(ctx, k_feature_system<SL, BG>, dim3(grid), dim3(FT_THREADS), (size_t)(smem), ctx->d_frame, ctx->d_opts, ctx->d_feat, 0, n_feats, bv, \
              ctx->P[ctx->cur], ctx->ldP, ctx->d_chi2_table, ctx->d_Hs, ldH, ovb_feat_order_ptr(ctx), mode, maxM, nblk, scratch,                    \
-             ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows, Mc)
+             ctx->scratch_per_cta, ctx->d_dump, OVB_MAX_COLS, dump_rows)
   if (mode == 2) {
     if (big)
       OVB_FS_LAUNCH(true, true);

@@ -52,7 +52,7 @@ void ovb_opts_default(ovb_opts *o) {
   o->do_calib_camera_pose = 0;
   o->do_calib_camera_intrinsics = 0;
   o->col_order = OVB_COLS_CANONICAL;
-  o->compress = OVB_COMPRESS_HOUSEHOLDER_TSQR;
+  o->compress = OVB_COMPRESS_CHOLQR2;
 }
 
 const char *ovb_last_error(const ovb_ctx *ctx) { return ctx ? ctx->err : "null context"; }
