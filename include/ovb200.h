@@ -351,6 +351,9 @@ ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_block
 /* out[0] kernels launched by the last update pipeline, out[1] of which TSQR level kernels,
  * out[2]/out[3] bytes copied host->device / device->host by the last ovb_msckf_update. */
 ovb_status ovb_last_counters(const ovb_ctx *ctx, int64_t out[4]);
+/* Host wall clock (microseconds) of the last ovb_msckf_update: [0] marshalling into the pinned arena + H2D enqueue,
+ * [1] kernel and D2H enqueue, [2] wait for the stream, [3] unpacking the results. */
+ovb_status ovb_last_host_us(const ovb_ctx *ctx, double out[4]);
 /* Per-kernel timing (measurement support): ovb_set_profile(ctx,1) brackets every kernel of the update pipeline that is
  * launched on the context stream with CUDA events (programmatic dependent launch is off meanwhile); ovb_profile_read
  * returns the kernels of the last update in launch order: NUL-separated mangled names and durations in microseconds. */

@@ -213,9 +213,10 @@ class FeatOut:
         self.chi2 = np.full(n_feats, np.nan)
 
     def struct(self) -> ovb_feat_out:
-        return ovb_feat_out(_ptr(self.status, c_int_p), _ptr(self.p_FinA, c_double_p), _ptr(self.p_FinG, c_double_p),
-                            _ptr(self.anchor_cam, c_int_p), _ptr(self.anchor_clone, c_int_p),
-                            _ptr(self.chi2, c_double_p))
+        if getattr(self, "_st", None) is None:  # the arrays are written in place by the library: the pointers stay valid
+            self._st = ovb_feat_out(_ptr(self.status, c_int_p), _ptr(self.p_FinA, c_double_p), _ptr(self.p_FinG, c_double_p),
+                                    _ptr(self.anchor_cam, c_int_p), _ptr(self.anchor_clone, c_int_p), _ptr(self.chi2, c_double_p))
+        return self._st
 
     def copy(self) -> "FeatOut":
         o = FeatOut(len(self.status))
@@ -277,6 +278,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ovb_chi2_quantile95.restype = C.c_double
     lib.ovb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 6)]
     lib.ovb_last_counters.argtypes = [vp, C.POINTER(C.c_int64 * 4)]
+    lib.ovb_last_host_us.argtypes = [vp, C.POINTER(C.c_double * 4)]
     lib.ovb_set_stream.argtypes = [vp, C.c_void_p]
     lib.ovb_msckf_shard_compress.argtypes = [vp, C.POINTER(ovb_frame), C.POINTER(ovb_feat_batch), C.POINTER(ovb_opts), C.c_void_p,
                                              C.c_int, c_int_p, c_int_p]
@@ -297,7 +299,7 @@ EXPORTED_SYMBOLS = [
     "ovb_create", "ovb_destroy", "ovb_last_error", "ovb_abi_version", "ovb_opts_default", "ovb_cov_set", "ovb_cov_get",
     "ovb_cov_dim", "ovb_cov_get_marginal", "ovb_cov_clone", "ovb_cov_marginalize", "ovb_cov_propagate", "ovb_cov_initialize",
     "ovb_msckf_update", "ovb_slam_update", "ovb_slam_delayed_init", "ovb_slam_anchor_change", "ovb_ekf_update", "ovb_triangulate", "ovb_feature_jacobians", "ovb_compress", "ovb_compress_gram", "ovb_compress_cholqr2",
-    "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters", "ovb_set_profile", "ovb_profile_read",
+    "ovb_chi2_quantile95", "ovb_last_stage_ms", "ovb_set_replay", "ovb_msckf_replay", "ovb_last_counters", "ovb_last_host_us", "ovb_set_profile", "ovb_profile_read",
     "ovb_set_stream", "ovb_msckf_shard_compress", "ovb_msckf_shard_compress_range", "ovb_shard_partition", "ovb_msckf_shard_finish",
 ]
 
@@ -542,6 +544,12 @@ class Engine:
         a = (C.c_int64 * 4)()
         self._check(self.lib.ovb_last_counters(self.h, C.byref(a)))
         return dict(launches=int(a[0]), tsqr_level_launches=int(a[1]), h2d_bytes=int(a[2]), d2h_bytes=int(a[3]))
+
+    def last_host_us(self):
+        """Host wall clock of the last msckf_update in microseconds."""
+        a = (C.c_double * 4)()
+        self._check(self.lib.ovb_last_host_us(self.h, C.byref(a)))
+        return dict(marshal_h2d_enqueue=float(a[0]), kernel_enqueue=float(a[1]), wait=float(a[2]), unpack=float(a[3]))
 
     def set_profile(self, enabled=True):
         self._check(self.lib.ovb_set_profile(self.h, int(bool(enabled))))

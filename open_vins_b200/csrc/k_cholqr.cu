@@ -31,7 +31,9 @@
 #define CQ_MAXRB 22      // row blocks of the Cholesky (n + extra right-hand-side rows <= 176)
 #define CQ_GRAM_T 512    // threads of k_cq_gram (16 warps, one 32x32 output tile each)
 #define CQ_KB 32         // rows per staged chunk in k_cq_gram
+#ifndef CQ_CHOL_T
 #define CQ_CHOL_T 384
+#endif
 #define CQ_CHOL_NA 5     // look-ahead warps of the Cholesky
 #define CQ_XP CT_XP     // pitch of the panel buffer (chol_tiles.cuh)
 #define CQ_TRSM_T 640

@@ -39,12 +39,31 @@ void launch_cam_poses(ovb_ctx *ctx) {
 // `count` (warp uniform) of them are real. A butterfly sum would differ in the last bits, and the LM loop's float32 casts
 // turn such a difference into 1e-8-level jumps of p_FinG now and then (hard part 8). All lanes end
 // with the same sums.
-template <int NV> __device__ __forceinline__ void seq_add(double (&s)[NV], const double (&c)[NV], int count) {
-  for (int l = 0; l < count; l++) {
+#define TRI_MAX_WARPS 8
+#define TRI_PITCH 33 // doubles per component row in the staging buffer (odd: lanes reading different rows hit distinct banks)
+// Lane k (< NV) adds component k of lanes 0..count-1 onto s[k] in that order, reading the terms from the warp's staging
+// buffer — the same operation sequence as the reference's loop, ~2 instructions per term for the warp instead of the
+// 3 NV a shuffle-per-term version issues (864 instructions per 32 measurements at NV = 9; the kernel is one dependent
+// instruction chain per feature, so its duration follows its instruction count).
+template <int NV> __device__ __forceinline__ void seq_add(double (&s)[NV], const double (&c)[NV], int count, double *wbuf) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < NV; k++)
-      s[k] += __shfl_sync(0xffffffffu, c[k], l);
+  for (int k = 0; k < NV; k++)
+    wbuf[k * TRI_PITCH + lane] = c[k];
+  __syncwarp();
+  double a = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV; k++)
+    a = (lane == k) ? s[k] : a;
+  if (lane < NV) {
+    const double *row = wbuf + lane * TRI_PITCH;
+    for (int l = 0; l < count; l++)
+      a += row[l];
   }
+#pragma unroll
+  for (int k = 0; k < NV; k++)
+    s[k] = __shfl_sync(0xffffffffu, a, k);
+  __syncwarp(); // the buffer is rewritten by the next call
 }
 
 struct Rel {
@@ -65,7 +84,7 @@ __device__ __forceinline__ Rel rel_pose(const DevCamPoses *fr, int cam, int cl, 
 
 // feat/FeatureInitializer.cpp:377-423 — returns the cost, identical in all lanes
 __device__ __forceinline__ double lm_cost(const DevCamPoses *fr, const BlobView &bv, int m0, int m1, int lane, const dm3 &R_GtoA, dv3 p_AinG,
-                                          double alpha, double beta, double rho) {
+                                          double alpha, double beta, double rho, double *wbuf) {
   double err[1] = {0.0};
   for (int base = m0; base < m1; base += 32) {
     const int i = base + lane;
@@ -80,7 +99,7 @@ __device__ __forceinline__ double lm_cost(const DevCamPoses *fr, const BlobView 
       float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)));
       c[0] = (double)nrm * (double)nrm; // exact: product of two promoted floats
     }
-    seq_add<1>(err, c, min(32, m1 - base));
+    seq_add<1>(err, c, min(32, m1 - base), wbuf);
   }
   return err[0];
 }
@@ -88,6 +107,8 @@ __device__ __forceinline__ double lm_cost(const DevCamPoses *fr, const BlobView 
 __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restrict__ fr, const DevOpts *__restrict__ dop,
                                                      DevFeat *__restrict__ feats, int n_feats, BlobView bv) {
   OVB_PDL_ENTER();
+  __shared__ double tri_stage[TRI_MAX_WARPS][9 * TRI_PITCH];
+  double *wbuf = tri_stage[threadIdx.x >> 5];
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= n_feats)
@@ -146,7 +167,7 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
           c[0] = Ai.m[0], c[1] = Ai.m[1], c[2] = Ai.m[2], c[3] = Ai.m[4], c[4] = Ai.m[5], c[5] = Ai.m[8];
           c[6] = Aip.x, c[7] = Aip.y, c[8] = Aip.z;
         }
-        seq_add<9>(Ab, c, min(32, m1 - base));
+        seq_add<9>(Ab, c, min(32, m1 - base), wbuf);
       }
       // the mirrored entries of A follow the same operation sequence as their twins
       double A[9] = {Ab[0], Ab[1], Ab[2], Ab[1], Ab[3], Ab[4], Ab[2], Ab[4], Ab[5]};
@@ -178,7 +199,7 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
           c[0] = dot3(Bb, Bb);
           c[1] = dot3(Bb, mv3(Bp, r.t));
         }
-        seq_add<2>(Ab1, c, min(32, m1 - base));
+        seq_add<2>(Ab1, c, min(32, m1 - base), wbuf);
       }
       const double A1 = Ab1[0], b1 = Ab1[1];
       double depth = b1 / A1;
@@ -203,7 +224,7 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
       bool recompute = true;
       double Hs[6] = {0, 0, 0, 0, 0, 0}; // 00 01 02 11 12 22
       double g[3] = {0, 0, 0};
-      double cost_old = lm_cost(fr, bv, m0, m1, lane, R_GtoA, p_AinG, alpha, beta, rho);
+      double cost_old = lm_cost(fr, bv, m0, m1, lane, R_GtoA, p_AinG, alpha, beta, rho, wbuf);
       while (runs < op.max_runs && lam < op.max_lamda && eps > op.min_dx) {
         if (recompute) {
 #pragma unroll
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
               for (int a = 0; a < 3; a++)
                 c[6 + a] = H0[a] * rd0 + H1[a] * rd1;
             }
-            seq_add<9>(Hg, c, min(32, m1 - base));
+            seq_add<9>(Hg, c, min(32, m1 - base), wbuf);
           }
 #pragma unroll
           for (int k = 0; k < 6; k++)
@@ -250,7 +271,7 @@ __global__ void __launch_bounds__(256) k_triangulate(const DevCamPoses *__restri
         }
         double Hl[9] = {Hs[0] * (1.0 + lam), Hs[1], Hs[2], Hs[1], Hs[3] * (1.0 + lam), Hs[4], Hs[2], Hs[4], Hs[5] * (1.0 + lam)};
         dv3 dx = colpiv_solve3(Hl, mk3(g[0], g[1], g[2]));
-        double cost = lm_cost(fr, bv, m0, m1, lane, R_GtoA, p_AinG, alpha + dx.x, beta + dx.y, rho + dx.z);
+        double cost = lm_cost(fr, bv, m0, m1, lane, R_GtoA, p_AinG, alpha + dx.x, beta + dx.y, rho + dx.z, wbuf);
         if (cost <= cost_old && (cost_old - cost) / cost_old < op.min_dcost) {
           alpha += dx.x;
           beta += dx.y;

@@ -1,6 +1,7 @@
 // ovb_api.cu — the C ABI of include/ovb200.h: context, host-side marshalling into one pinned arena, stream orchestration.
 // No arithmetic of the path happens on the host: it packs the inputs, launches the kernels of k_*.cu and copies results back.
 #include "ovb_internal.cuh"
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -947,6 +948,14 @@ ovb_status ovb_profile_read(ovb_ctx *ctx, char *names, int name_cap, float *us, 
   return OVB_OK;
 }
 
+ovb_status ovb_last_host_us(const ovb_ctx *ctx, double out[4]) {
+  if (!ctx || !out)
+    return OVB_ERR_ARG;
+  for (int i = 0; i < 4; i++)
+    out[i] = ctx->host_us[i];
+  return OVB_OK;
+}
+
 ovb_status ovb_last_counters(const ovb_ctx *ctx, int64_t out[4]) {
   if (!ctx || !out)
     return OVB_ERR_ARG;
@@ -1032,10 +1041,12 @@ ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat
   if (!feats || feats->n_feats <= 0) // UpdaterMSCKF.cpp:61-62
     return OVB_OK;
   cudaEventRecord(ctx->ev[0], ctx->stream);
+  const auto h0 = std::chrono::steady_clock::now();
   Packed pk;
   ovb_status st = pack_inputs(ctx, frame, feats, opts, nullptr, &pk);
   if (st != OVB_OK)
     return st;
+  const auto h1 = std::chrono::steady_clock::now();
   const int F = pk.n_feats;
   if (ctx->replay_enabled) {
     // keep the prior so that ovb_msckf_replay can re-run this exact update on device-resident inputs
@@ -1057,10 +1068,19 @@ ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat
                                       ctx->stream)); // info + dx in one copy
   ctx->last_d2h_bytes = sizeof(DevFeat) * (size_t)F + ctx->info_bytes + sizeof(double) * (size_t)N;
   cudaEventRecord(ctx->ev[6], ctx->stream);
+  const auto h2 = std::chrono::steady_clock::now();
   OVB_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const auto h3 = std::chrono::steady_clock::now();
   unpack_feats(ctx, F, out);
   for (int i = 0; i < N; i++)
     dx[i] = ctx->h_dx[i];
+  {
+    const auto h4 = std::chrono::steady_clock::now();
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    ctx->host_us[0] = us(h0, h1), ctx->host_us[1] = us(h1, h2), ctx->host_us[2] = us(h2, h3), ctx->host_us[3] = us(h3, h4);
+  }
   for (int s = 0; s < 5; s++)
     cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
   cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[0], ctx->ev[6]);

@@ -146,6 +146,7 @@ struct ovb_ctx {
   int gram_cluster;  // k_cq_gram: clusters of 4 slabs pre-reduce in distributed shared memory (OVB_GRAM_CLUSTER=0 disables: A/B timing only)
   int ekf_chol_dmma; // EKF Cholesky on the DMMA kernel of k_cholqr.cu (OVB_EKF_CHOL_DMMA=0 disables: A/B timing only)
   float stage_ms[6];
+  double host_us[4]; // host wall clock of the last ovb_msckf_update: marshalling + H2D enqueue, kernel enqueue, wait, result unpack
   // replay of the last update on device-resident inputs (bench: `value` leg; see ovb_msckf_replay)
   int replay_enabled, last_pk_valid;
   int last_n_feats, last_max_M, last_m_total, last_ldH, last_n_all, last_col_order;
