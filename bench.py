@@ -17,6 +17,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -142,19 +143,27 @@ def unpin(old):
             pass
 
 
-def cpu_updates(w: Workload, n_updates: int, warm: int = 1):
-    """n_updates of the oracle (CPU restatement of the reference's Eigen arithmetic) on the workload, one pinned thread.
-    Returns (updates/s from the median, last result, per-stage seconds of the last update, times)."""
+def cpu_updates(w: Workload, n_updates: int | None = None, warm: int = 1, budget_s: float = 20.0):
+    """Updates of the oracle (CPU restatement of the reference's Eigen arithmetic) on the workload, one pinned thread.
+    n_updates None: as many as fit in about budget_s seconds of CPU work (at least one; the first run doubles as the warm-up
+    when a single update already takes seconds). Returns (updates/s from the median, last result, times)."""
     from oracle import ovo_py
     ovo_py.build()
     old = pin_to_one_core()
     try:
         times, r = [], None
-        for i in range(warm + n_updates):
+        t = time.perf_counter()
+        r = ovo_py.msckf_update(w.frame, w.feats, w.opts, w.P, dumps=False)
+        t_first = time.perf_counter() - t
+        if n_updates is None:
+            n_updates = max(1, min(60, int(budget_s / max(t_first, 1e-3))))
+        if t_first > 2.0 or warm == 0:
+            times.append(t_first)  # seconds-long updates: cache warm-up is noise, every run counts
+            n_updates -= 1
+        for i in range(n_updates):
             t = time.perf_counter()
             r = ovo_py.msckf_update(w.frame, w.feats, w.opts, w.P, dumps=False)
-            if i >= warm:
-                times.append(time.perf_counter() - t)
+            times.append(time.perf_counter() - t)
     finally:
         unpin(old)
     return 1.0 / float(np.median(times)), r, times
@@ -217,7 +226,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "msckf_updates_per_sec", "value": ups, "unit": "updates/s", "n_gpus": args.gpus, "steps": budget_steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / budget_steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": w.data, "feats_per_sec": ups * w.n_feats,
-        "config": {"workload": w.name},
+        "config": {"workload": w.name, "features_in": int(w.n_feats), "features_used": int(r["stats"].n_feats_used), "rows_stacked": int(r["stats"].rows_stacked),
+                   "cols_stacked": int(r["stats"].cols_stacked), "state_dim": int(w.P.shape[0])},
         "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": 1, "kind": "port",
                          "sample": f"{budget_steps} full updates of the {w.n_feats}-feature batch, one pinned thread (the reference update is single-threaded)"},
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -257,7 +267,8 @@ def short_name(mangled: str) -> str:
               "k_ekf_trsm", "k_tsqr_level", "k_tsqr_assemble", "k_gram"):
         if k in mangled:
             return k
-    return mangled[:40]
+    m = re.search(r"k_[a-z0-9_]+", mangled)  # any other kernel of the library: the identifier inside the mangled name
+    return m.group(0) if m else mangled[:40]
 
 
 def kernel_table(eng, w: Workload, repeats=5):
@@ -579,8 +590,8 @@ def main():
         eng3.close()
     if rank == 0 and line is not None:
         if not args.no_cpu_baseline and w.mode == "msckf":
-            n_cpu = 3 if F >= 2000 else (12 if F >= 300 else 60)
-            ups, rr, times = cpu_updates(w, n_cpu)
+            ups, rr, times = cpu_updates(w)
+            n_cpu = len(times)
             if world == 1 or replicated:
                 assert np.array_equal(rr["out"].status, r["out"].status), "GPU and CPU gate decisions differ on the bench workload"
             line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": 1, "kind": "port",

@@ -799,20 +799,24 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
           t0 = fma(B0[k], pv[k], t0);
           t1 = fma(B0[8 + k], pv[k], t1);
         }
+        // one accumulator pair per block: three 6..8-deep chains side by side instead of one 20-deep chain
+        double u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
         if (s1 >= 0) {
 #pragma unroll
           for (int k = 0; k < 6; k++) {
-            t0 = fma(B1[k], pv[6 + k], t0);
-            t1 = fma(B1[8 + k], pv[6 + k], t1);
+            u0 = fma(B1[k], pv[6 + k], u0);
+            u1 = fma(B1[8 + k], pv[6 + k], u1);
           }
         }
         if (s2 >= 0) {
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            t0 = fma(B2[k], pv[12 + k], t0);
-            t1 = fma(B2[8 + k], pv[12 + k], t1);
+            v0 = fma(B2[k], pv[12 + k], v0);
+            v1 = fma(B2[8 + k], pv[12 + k], v1);
           }
         }
+        t0 += u0 + v0;
+        t1 += u1 + v1;
         if (nblk > 3) {
 #pragma unroll
           for (int b = 3; b < 6; b++) {
