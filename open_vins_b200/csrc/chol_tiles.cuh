@@ -284,7 +284,7 @@ __device__ __forceinline__ void ct_trail_row(const CtView &sm, const double *Xk,
 // One __syncthreads per step; named barrier 1 joins the helpers after their panel rows, named barrier 2 hands block
 // column k+1 to warp 0 (it has never been seen to wait there: the helpers' first two moves are shorter than eight pivots),
 // named barrier 3 hands each factored diagonal block to the inverting warp.
-template <int THREADS, int NA_UNUSED>
+template <int THREADS>
 __device__ __forceinline__ void ct_chol_tiles(const CtView &sm, int n, int nrows, bool strict, double floor_d) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NW = THREADS / 32, NH = NW - (NW + 3) / 4;

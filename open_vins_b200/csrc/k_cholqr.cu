@@ -4,7 +4,7 @@
 // 3mn² flops with stride-m accesses) for stacked systems of up to CQ_MAXN columns (residual included).
 //
 //   pass 1   G1 = [H r]'[H r]                      k_cq_gram (DMMA, row slabs over all SMs) + k_cq_reduce (fixed order)
-//            R1'R1 = G1 + s1 I                      k_cq_chol (one CTA, matrix tile-packed in shared memory, DMMA trailing update)
+//            R1'R1 = G1 + s1 I                      k_cq_chol_gram (one CTA, tile-packed in shared memory: chol_tiles.cuh)
 //            Q1 = [H r] R1^-1   (in place)          k_cq_trsm (row groups in registers, right-looking, DMMA)
 //   pass 2   G2 = Q1'Q1,  R2'R2 = G2 + s2 I         the same two kernels
 //            [R z] = rows 0..n-1 of R2 R1           k_cq_trmm
@@ -34,7 +34,6 @@
 #ifndef CQ_CHOL_T
 #define CQ_CHOL_T 384
 #endif
-#define CQ_CHOL_NA 5     // look-ahead warps of the Cholesky
 #define CQ_XP CT_XP     // pitch of the panel buffer (chol_tiles.cuh)
 #define CQ_TRSM_T 640
 
@@ -306,7 +305,7 @@ struct CqCholSmem {
 namespace {
 
 // The factorisation proper lives in chol_tiles.cuh (shared with the per-feature gate); this kernel family runs it with
-// CQ_CHOL_T threads and CQ_CHOL_NA look-ahead warps (NA * 32 >= 152 rows: one panel row per thread at the widest step).
+// CQ_CHOL_T threads (256 / 512 / 640 were measured: 40.9 / 37.7 / 38.9 us against 36.8 us at 384, n = 155).
 __device__ __forceinline__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, bool strict, double floor_d) {
   CtView v;
   v.T = sm.T;
@@ -318,7 +317,7 @@ __device__ __forceinline__ void cq_chol_tiles(CqCholSmem &sm, int n, int nrows, 
   v.dummyT = sm.dummyT;
   v.dummyX = sm.dummyX;
   v.flag = &sm.flag;
-  ct_chol_tiles<CQ_CHOL_T, CQ_CHOL_NA>(v, n, nrows, strict, floor_d);
+  ct_chol_tiles<CQ_CHOL_T>(v, n, nrows, strict, floor_d);
 }
 
 // stage the lower triangle of a row-major global matrix (rows < nrows, cols < n; rows >= n come from `rhs` when given)
@@ -541,16 +540,30 @@ __global__ void __launch_bounds__(CQ_TRSM_T) k_cq_trsm(double *__restrict__ A, i
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
   const int NB = (nt + 7) >> 3;
   constexpr int NBP = NH1 + NH2; // padded block count: tiles past NB are zero, their reciprocal pivots 1
-  for (int e = 2 * tid; e < tri(NB) * 64; e += 2 * CQ_TRSM_T)
-    cpa16(s_u32(Lt + e), Lpk + e, 16u);
-  for (int e = 2 * tid; e < NB * 8; e += 2 * CQ_TRSM_T)
-    cpa16(s_u32(Ri + e), Lpk + CQ_PK_INV + e, 16u);
-  cpa_commit();
+  // the packed factor (up to 106 KB, contiguous) arrives as two bulk copies (TMA engine, SASS UBLKCP) signalled on an
+  // mbarrier: one instruction issues them, nobody spends issue slots or registers on the transfer
+  __shared__ __align__(8) unsigned long long l_bar;
+  const unsigned bar = s_u32(&l_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned bytesL = (unsigned)(tri(NB) * 64 * sizeof(double)), bytesR = (unsigned)(NB * 8 * sizeof(double));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytesL + bytesR) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(Lt)), "l"(Lpk), "r"(bytesL), "r"(bar)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(Ri)), "l"(Lpk + CQ_PK_INV), "r"(bytesR),
+                 "r"(bar)
+                 : "memory");
+  }
   for (int e = tri(NB) * 64 + tid; e < tri(NBP) * 64; e += CQ_TRSM_T)
     Lt[e] = 0.0;
   for (int e = NB * 8 + tid; e < NBP * 8; e += CQ_TRSM_T)
     Ri[e] = 1.0;
-  cpa_wait<0>();
+  asm volatile("{\n\t.reg .pred p;\n\tCQ_LWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra CQ_LDONE;\n\tbra CQ_LWAIT;\n\tCQ_LDONE:\n\t}" ::"r"(bar)
+               : "memory");
   __syncthreads();
   double *xs = Xs + (size_t)wid * (CQ_TRSM_NH * 2 * 32);
   const int ngroups = (m + 7) >> 3;

@@ -254,6 +254,9 @@ __global__ void __launch_bounds__(256) k_ekf_downdate(double *__restrict__ P, in
 // ---- one-shot variants for K <= EK1_KMAX (the whole inner dimension staged at once: a CTA pays ONE L2 round trip instead
 // of one per 32-wide K tile; at config-2 sizes these products are latency-, not flop-bound). Same contract as k_ekf_gemm.
 #define EK1_KMAX 160
+__device__ __forceinline__ void ek_cpa8(double *dst_smem, const double *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 __global__ void __launch_bounds__(256) k_ekf_gemm1(int mode, const double *__restrict__ P, int ldP, const double *__restrict__ H, int ldH,
                                                    const double *__restrict__ Min, int ldM, const DevUpdateInfo *__restrict__ info, int X, int Y,
                                                    int K, double *__restrict__ Cout, int ldC, double sigma2, const double *__restrict__ Rdiag) {
@@ -272,13 +275,28 @@ __global__ void __launch_bounds__(256) k_ekf_gemm1(int mode, const double *__res
   const int ldG = (mode == 0) ? ldP : ldM;
   const int g0 = (mode == 0) ? x0 : y0, gmax = (mode == 0) ? X : Y;
   const int h0 = (mode == 0) ? y0 : x0, hmax = (mode == 0) ? Y : X;
+  // the column map first (the gathered rows' addresses depend on it), then every element of both operands as an 8-byte
+  // cp.async: one L2 round trip for the whole staging instead of a dependent index -> element pair per loop trip
+  __shared__ int cs_s[EK1_KMAX];
+  for (int j = tid; j < K; j += 256)
+    cs_s[j] = cs[j];
+  __syncthreads();
   for (int e = tid; e < K * 32; e += 256) {
     const int j = e >> 5, a = e & 31;
-    Gs[j * 33 + a] = (g0 + a < gmax) ? Gsrc[(size_t)cs[j] * ldG + g0 + a] : 0.0;
+    if (g0 + a < gmax)
+      ek_cpa8(&Gs[j * 33 + a], &Gsrc[(size_t)cs_s[j] * ldG + g0 + a]);
+    else
+      Gs[j * 33 + a] = 0.0;
   }
   for (int i = ty; i < 32; i += 8)
-    for (int j = tx; j < K; j += 32)
-      Hs[i * pk + j] = (h0 + i < hmax) ? H[(size_t)(h0 + i) * ldH + j] : 0.0;
+    for (int j = tx; j < K; j += 32) {
+      if (h0 + i < hmax)
+        ek_cpa8(&Hs[i * pk + j], &H[(size_t)(h0 + i) * ldH + j]);
+      else
+        Hs[i * pk + j] = 0.0;
+    }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   double acc[4] = {0, 0, 0, 0};
   if (mode == 0) {
@@ -334,11 +352,19 @@ __global__ void __launch_bounds__(256) k_ekf_downdate1(double *__restrict__ P, i
   double *As = d1, *Bs = d1 + (size_t)32 * pk, *ws = Bs + (size_t)32 * pk;
   for (int i = ty; i < 32; i += 8)
     for (int k = tx; k < r; k += 32) {
-      As[i * pk + k] = (a0 + i < N) ? Yin[(size_t)(a0 + i) * ldY + k] : 0.0;
-      Bs[i * pk + k] = (b0 + i < N) ? Yin[(size_t)(b0 + i) * ldY + k] : 0.0;
+      if (a0 + i < N)
+        ek_cpa8(&As[i * pk + k], &Yin[(size_t)(a0 + i) * ldY + k]);
+      else
+        As[i * pk + k] = 0.0;
+      if (b0 + i < N)
+        ek_cpa8(&Bs[i * pk + k], &Yin[(size_t)(b0 + i) * ldY + k]);
+      else
+        Bs[i * pk + k] = 0.0;
     }
   for (int k = tid; k < r; k += 256)
-    ws[k] = w[k];
+    ek_cpa8(&ws[k], &w[k]);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   double acc[4] = {0, 0, 0, 0};
   for (int k = 0; k < r; k++) {

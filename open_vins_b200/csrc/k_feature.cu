@@ -11,9 +11,12 @@
 //    3(2M-1) sequential Givens rotations: Q2'[H_x r] = rows 3.. of (X - V Z). It spans the same subspace; the
 //    projected block differs from the reference's by an orthogonal transform of its rows, which leaves H_o'H_o,
 //    H_o'r_o, chi² and everything downstream unchanged;
-//  * the gate uses S_o = Q2'(H_x P H_x' + s²I)Q2 with H_x P H_x' accumulated from the sparse blocks
-//    (≈6x fewer flops than the dense (2M-3) x w_f products) and a blocked in-place Cholesky with the projected
-//    residual carried as an extra row (chi² = |L^-1 r_o|²);
+//  * the gate needs chi² = r_o'(Q2' S Q2)^-1 r_o with S = H_x P H_x' + s²I. S is accumulated from the sparse blocks
+//    (≈6x fewer flops than the dense (2M-3) x w_f products) straight into a tile-packed triangle and factored ONCE,
+//    unprojected, by the DMMA tile Cholesky of chol_tiles.cuh; the projection is folded into four right-hand-side rows
+//    (r and the columns of Q1): chi² = a'a - (C'a)'(C'C)^-1(C'a), a = L^-1 r, C = L^-1 Q1 (see "gate" in the kernel).
+//    Tracks too long for a shared-memory triangle (template parameter BIG) keep the explicit two-sided projection and the
+//    scalar blocked Cholesky of chol.cuh on an L2-resident scratch slice;
 //  * rows are written straight into the stacked staging matrix in canonical column order, coalesced.
 // Compiled with -fmad=false (see geom.cuh).
 #include <cstdio>
@@ -23,7 +26,6 @@
 
 #define FT_THREADS 256
 #define FT_WARPS (FT_THREADS / 32)
-#define FT_CHOL_NA 3 // look-ahead warps of the gate Cholesky (chol_tiles.cuh): 96 panel rows per trip
 #define FT_TU 2
 #ifdef FT_PROBE // per-phase cycle stamps of the longest track of a launch (thread 0 of CTA 0), printed at the end of the feature
 #define FT_STAMP(i) do { if (tid == 0 && blockIdx.x == 0) ft_t[i] = clock64(); } while (0)
@@ -103,7 +105,7 @@ template <int NV> __device__ __forceinline__ void block_sum_n(double (&v)[NV], d
 // registers) is then independent of what the feature kernel keeps live around it.
 __device__ __noinline__ void ft_gate_chol(double *ctbase, int NRB, int *flag, int n, int nrows) {
   const CtView cv = ct_view_carve(ctbase, NRB, flag);
-  ct_chol_tiles<FT_THREADS, FT_CHOL_NA>(cv, n, nrows, true, 0.0);
+  ct_chol_tiles<FT_THREADS>(cv, n, nrows, true, 0.0);
 }
 
 // ---- d p_FinG / d lambda and the anchor terms: UpdaterHelper.cpp:32-190. Returns L (3x3 row-major),
