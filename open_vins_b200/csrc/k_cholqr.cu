@@ -238,8 +238,10 @@ __global__ void __launch_bounds__(CQ_GRAM_T) k_cq_gram(const double *__restrict_
 #define CQ_RED_T 1024
 #define CQ_RED_CH 8
 #define CQ_RED_GX (16 * CQ_RED_CH)
+// tiled != 0: G receives the lower triangle in the tile-packed layout of chol_tiles.cuh (diagonal tiles whole), which the
+// Cholesky kernel then takes in with one bulk copy; else row-major, both triangles.
 __global__ void __launch_bounds__(CQ_RED_T) k_cq_reduce(const double *__restrict__ Gpart, int nslab, int nblk, int BW, int nblk_side, int nt,
-                                                       double *__restrict__ G, int ldG) {
+                                                       double *__restrict__ G, int ldG, int tiled) {
   OVB_PDL_ENTER();
   __shared__ double red[8][128];
   int ci, cj, offI, offJ;
@@ -267,8 +269,14 @@ __global__ void __launch_bounds__(CQ_RED_T) k_cq_reduce(const double *__restrict
     const int i = ci + (e >> 5), j = cj + (e & 31);
     if (i < nt && j < nt && i <= j) {
       const double s = ((red[0][el] + red[1][el]) + (red[2][el] + red[3][el])) + ((red[4][el] + red[5][el]) + (red[6][el] + red[7][el]));
-      G[(size_t)i * ldG + j] = s;
-      G[(size_t)j * ldG + i] = s;
+      if (tiled) {
+        G[ct_idx(j, i)] = s;
+        if ((i >> 3) == (j >> 3))
+          G[(size_t)(tri(j >> 3) + (j >> 3)) * 64 + (i & 7) * 8 + (j & 7)] = s; // upper half of a diagonal tile
+      } else {
+        G[(size_t)i * ldG + j] = s;
+        G[(size_t)j * ldG + i] = s;
+      }
     }
   }
 }
@@ -277,14 +285,8 @@ __global__ void __launch_bounds__(CQ_RED_T) k_cq_reduce(const double *__restrict
 // Single-CTA Cholesky of an n x n SPD matrix (n <= CQ_MAXN) with `extra` right-hand-side rows appended as rows n.. .
 // The lower triangle lives in shared memory as packed 8x8 tiles (tile (bi,bj), bj <= bi, at (bi(bi+1)/2 + bj)*64,
 // row-major inside): a tile IS the DMMA accumulator fragment (lane reads its two doubles at 2*lane: conflict free), and
-// the whole 160 x 160 triangle is 107 KB. Right-looking, 8-wide block steps:
-//   trailing update  S[bi][bj] -= X[bi] X[bj]'  : two DMMAs per tile, operands from the panel buffer Xp (pitch 12),
-//                    two tiles in flight per warp
-//   look-ahead       warps 0..4 update block column k+1 first, warp 0 factors its diagonal tile — every lane holds the
-//                    whole 8x8 triangle in registers and runs the same 8-pivot chain (no shuffles, no divergence;
-//                    MUFU.RSQ64H-seeded reciprocal square roots) — then the five warps solve panel k+1, all while warps
-//                    5..15 finish the rest of trailing update k. One CTA barrier per block step.
-// Measured chain per block step (tools/ubench/cholqr_bench.cu): DMMA 26 cycles dependent, DFMA 8, rsqrt ~80.
+// the whole 160 x 160 triangle is 107 KB. The factorisation itself — warp 0 on the pivot chain, helper warps on the
+// panels and the trailing update — is ct_chol_tiles (chol_tiles.cuh).
 struct CqCholSmem {
   double T[(CQ_MAXRB * (CQ_MAXRB + 1) / 2) * 64];
   double Xp[2][CQ_MAXRB * 8 * CQ_XP];
@@ -354,7 +356,7 @@ __device__ __forceinline__ double cq_el(const double *T, int i, int j) { return 
 } // namespace
 
 // Gram mode: L L' = G + shift_rel * max(diag G) * I; writes L (= R') in the packed layout above to Lpk. ldG even.
-__global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_gram(const double *__restrict__ G, int ldG, int n, double shift_rel, double *__restrict__ Lpk) {
+__global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_gram(const double *__restrict__ G, int ldG, int n, double shift_rel, double *__restrict__ Lpk, int tiled) {
   OVB_PDL_ENTER();
   extern __shared__ __align__(16) unsigned char cq_raw[];
   CqCholSmem &sm = *reinterpret_cast<CqCholSmem *>(cq_raw);
@@ -362,7 +364,44 @@ __global__ void __launch_bounds__(CQ_CHOL_T) k_cq_chol_gram(const double *__rest
 #ifdef CQ_PROBE
   const long long q0 = clock64();
 #endif
-  cq_load_tiles(sm, G, (size_t)ldG, n, n, nullptr, 0);
+  if (tiled) {
+    // G is already tile-packed (k_cq_reduce): one bulk copy (TMA engine) on an mbarrier instead of a scatter of 16-byte cp.asyncs
+    __shared__ __align__(8) unsigned long long g_bar;
+    const unsigned bar = s_u32(&g_bar);
+    const int NB = (n + 7) >> 3;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)(tri(NB) * 64 * sizeof(double));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(sm.T)), "l"(G), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+    for (int e = tid; e < 2 * CQ_MAXRB * 8 * CQ_XP; e += CQ_CHOL_T)
+      (&sm.Xp[0][0])[e] = 0.0;
+    if (tid < 64)
+      sm.dummyT[tid] = 0.0;
+    if (tid < 2 * CQ_XP)
+      sm.dummyX[tid] = 0.0;
+    if (tid == 0)
+      sm.flag = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tCQ_GWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra CQ_GDONE;\n\tbra CQ_GWAIT;\n\tCQ_GDONE:\n\t}" ::"r"(bar)
+                 : "memory");
+    // rows past n of the last block row are whatever an earlier, wider system left in G: the factorisation multiplies the
+    // padding by zeros, so it has to BE zero
+    const int r0 = n - 8 * (NB - 1);
+    if (r0 < 8) {
+      double *last = sm.T + (size_t)tri(NB - 1) * 64;
+      for (int e = tid; e < NB * 64; e += CQ_CHOL_T)
+        if (((e >> 3) & 7) >= r0)
+          last[e] = 0.0;
+    }
+  } else {
+    cq_load_tiles(sm, G, (size_t)ldG, n, n, nullptr, 0);
+  }
   __syncthreads();
   // largest diagonal entry -> shift
   double mx = 0.0;
@@ -873,6 +912,7 @@ static bool cq_ensure_G(ovb_ctx *ctx) {
     ctx->d_G = nullptr;
     if (cudaMalloc(&ctx->d_G, sizeof(double) * need_G) != cudaSuccess)
       return false;
+    cudaMemsetAsync(ctx->d_G, 0, sizeof(double) * need_G, ctx->stream); // the tile-packed Gram matrix keeps finite padding
     ctx->G_cap = need_G;
   }
   return true;
@@ -1030,7 +1070,7 @@ static int cq_compress_wide(ovb_ctx *ctx, double *A, int m, int n, int ldA, doub
   for (int pass = 0; pass < 2; pass++) {
     double *G = pass == 0 ? G1 : G2;
     cq_launch_gram(ctx, nblk, nslab, gram_smem, (const double *)A, ldA, m, nt, slab_rows, BW, nblk_side, ctx->d_Gpart, 1);
-    ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, nslab, nblk, BW, nblk_side, nt, G, (int)CQ_WMAX);
+    ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, nslab, nblk, BW, nblk_side, nt, G, (int)CQ_WMAX, 0);
     ovb_launch(ctx, k_cq_shift, dim3(1), dim3(256), (size_t)0, G, (int)CQ_WMAX, nt, pass == 0 ? 1e-11 : 1e-13, floor_dev + pass);
     cq_chol_blocked(ctx, G, CQ_WMAX, nt, 0, pass == 0 ? Lpk1 : Lpk2, floor_dev + pass, (DevUpdateInfo *)nullptr);
     if (pass == 0)
@@ -1087,9 +1127,9 @@ int launch_compress_cholqr2(ovb_ctx *ctx, double *A, int m, int n, int ldA, doub
     trsm_ctas = ctx->sm_count;
   for (int pass = 0; pass < 2; pass++) {
     cq_launch_gram(ctx, nblk, nslab_pad, gram_smem, (const double *)A, ldA, m, nt, slab_rows, BW, nblk_side, ctx->d_Gpart, cs);
-    ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, npart, nblk, BW, nblk_side, nt, G, ldW);
+    ovb_launch(ctx, k_cq_reduce, dim3(CQ_RED_GX, nblk), dim3(CQ_RED_T), (size_t)0, (const double *)ctx->d_Gpart, npart, nblk, BW, nblk_side, nt, G, ldW, 1);
     ovb_launch(ctx, k_cq_chol_gram, dim3(1), dim3(CQ_CHOL_T), sizeof(CqCholSmem), (const double *)G, ldW, nt, pass == 0 ? 1e-11 : 1e-13,
-               pass == 0 ? L1 : L2);
+               pass == 0 ? L1 : L2, 1);
     if (pass == 0)
       cq_launch_trsm(ctx, trsm_ctas, A, ldA, m, nt, (const double *)L1);
   }

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "open_vins_b200", "libovb200.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
-WATCH = ["DMMA", "DFMA", "DMUL", "DADD", "MUFU.RSQ64H", "MUFU.RCP64H", "LDGSTS", "SHFL", "BAR", "LDS", "STS", "UTMALDG", "UTCHMMA", "UTCQMMA", "UTCIMMA", "LDTM", "STTM"]
+WATCH = ["DMMA", "DFMA", "DMUL", "DADD", "MUFU.RSQ64H", "MUFU.RCP64H", "LDGSTS", "UBLKCP", "SYNCS", "SHFL", "BAR", "LDS", "STS", "UTMALDG", "UTCHMMA", "UTCQMMA", "UTCIMMA", "LDTM", "STTM"]
 counts = collections.OrderedDict()
 fn = None
 for line in out.splitlines():
@@ -31,7 +31,7 @@ demangle = subprocess.run(["c++filt"], input="\n".join(counts.keys()), capture_o
 with open(os.path.join(ROOT, "profiles", "sass_r02.txt"), "w") as f:
     f.write("# SASS opcode counts per kernel of open_vins_b200/libovb200.so (cuobjdump -sass, sm_100a), round 2; regenerate: python tools/sass_listing.py\n")
     f.write("# DMMA = mma.sync.m8n8k4.f64 (FP64 tensor-core path); LDGSTS = cp.async; MUFU.RSQ64H = rsqrt.approx.f64 pivot seed.\n")
-    f.write("# tcgen05 / TMA opcodes (UTC*MMA, UTMALDG, LDTM, STTM): none in any kernel — tcgen05.mma has no FP64 kind, and every operand tile here is\n")
+    f.write("# UBLKCP = cp.async.bulk (TMA engine, 1-D) + SYNCS = mbarrier ops: the packed Cholesky factor of k_cq_trsm. tcgen05 / tensor-map TMA opcodes\n# (UTC*MMA, UTMALDG, LDTM, STTM): none — tcgen05.mma has no FP64 kind, and every other operand tile here is\n")
     f.write("# either register-resident or a few KB staged by cp.async (DESIGN.md §4).\n")
     for (fn, c), dm in zip(counts.items(), demangle):
         name = dm.split("(")[0]

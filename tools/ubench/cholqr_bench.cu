@@ -124,9 +124,9 @@ int main() {
     cudaEventRecord(e[0]);
     k_cq_gram<<<dim3(1, nslab), CQ_GRAM_T, gram_smem>>>(A, ld, m, nt, slab_rows, BW, 1, Gpart, 1);
     cudaEventRecord(e[1]);
-    k_cq_reduce<<<dim3(CQ_RED_GX, 1), CQ_RED_T>>>(Gpart, nslab, 1, BW, 1, nt, G, ldW);
+    k_cq_reduce<<<dim3(CQ_RED_GX, 1), CQ_RED_T>>>(Gpart, nslab, 1, BW, 1, nt, G, ldW, 1);
     cudaEventRecord(e[2]);
-    k_cq_chol_gram<<<1, CQ_CHOL_T, sizeof(CqCholSmem)>>>(G, ldW, nt, 1e-11, Rpk);
+    k_cq_chol_gram<<<1, CQ_CHOL_T, sizeof(CqCholSmem)>>>(G, ldW, nt, 1e-11, Rpk, 1);
     cudaEventRecord(e[3]);
     k_cq_trsm<10, 10><<<sms, CQ_TRSM_T, trsm_smem>>>(A, ld, m, nt, Rpk);
     cudaEventRecord(e[4]);
