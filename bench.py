@@ -365,11 +365,12 @@ def bench_update(args, w: Workload, local_rank=0, dist=None, rank=0, world=1):
     t_e2e = 0.0
     host_us = np.zeros(4)
     out_buf = capi.FeatOut(F)  # result arrays owned by the caller, reused across calls like a host filter would
+    dx_buf = np.zeros(w.P.shape[0])
     for _ in range(K):
         eng.cov_set(w.P)
         torch.cuda.synchronize()
         t = time.perf_counter()
-        st, out, dx, stats = eng.msckf_update(w.frame, w.feats, w.opts, out_buf)
+        st, out, dx, stats = eng.msckf_update(w.frame, w.feats, w.opts, out_buf, dx_buf)
         t_e2e += time.perf_counter() - t
         h = eng.last_host_us()
         host_us += [h["marshal_h2d_enqueue"], h["kernel_enqueue"], h["wait"], h["unpack"]]

@@ -426,9 +426,11 @@ class Engine:
         return st, bool(acc[0]), dx_new, dx[:self.cov_dim()]
 
     # ---- hot path
-    def msckf_update(self, frame: FrameArrays, feats: FeatArrays, opts: ovb_opts, out: FeatOut | None = None):
+    def msckf_update(self, frame: FrameArrays, feats: FeatArrays, opts: ovb_opts, out: FeatOut | None = None, dx: np.ndarray | None = None):
+        """out / dx: caller-owned result buffers to reuse across calls (a host filter keeps them); allocated here when omitted."""
         out = out or FeatOut(feats.n_feats)
-        dx = np.zeros(self.cov_dim())
+        if dx is None:
+            dx = np.zeros(self.cov_dim())
         stats = ovb_stats()
         fs, bs, os_ = frame.struct(), feats.struct(), out.struct()
         st = self.lib.ovb_msckf_update(self.h, C.byref(fs), C.byref(bs), C.byref(opts), C.byref(os_),

@@ -1081,8 +1081,7 @@ ovb_status ovb_msckf_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat
     };
     ctx->host_us[0] = us(h0, h1), ctx->host_us[1] = us(h1, h2), ctx->host_us[2] = us(h2, h3), ctx->host_us[3] = us(h3, h4);
   }
-  for (int s = 0; s < 5; s++)
-    cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
+  ctx->stage_pending = 1; // the five stage times are read from the events when ovb_last_stage_ms asks for them
   cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[0], ctx->ev[6]);
   const DevUpdateInfo *inf = ctx->h_info;
   if (stats) {
@@ -1156,8 +1155,7 @@ ovb_status ovb_slam_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_
   }
   for (int i = 0; i < N; i++)
     dx[i] = ctx->h_dx[i];
-  for (int s = 0; s < 5; s++)
-    cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
+  ctx->stage_pending = 1; // the five stage times are read from the events when ovb_last_stage_ms asks for them
   cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[0], ctx->ev[6]);
   const DevUpdateInfo *inf = ctx->h_info;
   if (stats) {
@@ -1189,6 +1187,11 @@ ovb_status ovb_slam_update(ovb_ctx *ctx, const ovb_frame *frame, const ovb_feat_
 ovb_status ovb_last_stage_ms(const ovb_ctx *ctx, float ms[6]) {
   if (!ctx || !ms)
     return OVB_ERR_ARG;
+  if (ctx->stage_pending) {
+    for (int s = 0; s < 5; s++)
+      cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
+    ctx->stage_pending = 0;
+  }
   for (int i = 0; i < 6; i++)
     ms[i] = ctx->stage_ms[i];
   return OVB_OK;
@@ -1327,6 +1330,7 @@ ovb_status ovb_msckf_shard_finish(ovb_ctx *ctx, double *stacked_dev, int n_block
   unpack_feats(ctx, F, out);
   for (int i = 0; i < N; i++)
     dx[i] = ctx->h_dx[i];
+  ctx->stage_pending = 0;
   cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev[0], ctx->ev[6]);
   cudaEventElapsedTime(&ctx->stage_ms[3], ctx->ev[0], ctx->ev[4]);
   cudaEventElapsedTime(&ctx->stage_ms[4], ctx->ev[4], ctx->ev[5]);

@@ -145,7 +145,8 @@ struct ovb_ctx {
   int tsqr_cluster; // upper TSQR levels as one thread-block cluster (OVB_TSQR_CLUSTER=0 disables: A/B timing only)
   int gram_cluster;  // k_cq_gram: clusters of 4 slabs pre-reduce in distributed shared memory (OVB_GRAM_CLUSTER=0 disables: A/B timing only)
   int ekf_chol_dmma; // EKF Cholesky on the DMMA kernel of k_cholqr.cu (OVB_EKF_CHOL_DMMA=0 disables: A/B timing only)
-  float stage_ms[6];
+  mutable float stage_ms[6];
+  mutable int stage_pending; // stage_ms[0..4] of the last update not read back from the events yet (done on demand: each read costs ~1.5 us of host time)
   double host_us[4]; // host wall clock of the last ovb_msckf_update: marshalling + H2D enqueue, kernel enqueue, wait, result unpack
   // replay of the last update on device-resident inputs (bench: `value` leg; see ovb_msckf_replay)
   int replay_enabled, last_pk_valid;
