@@ -1,4 +1,4 @@
-# refresh of the round-2 artefacts on the final build (everything except the default bench line and the parity suite, which tools/gpu/run27.sh produced)
+# refresh of the round-2 artefacts on the final build (everything except the default bench line and the parity suite, which tools/gpu/suite_and_bench.sh produced)
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke_r02.txt
 timeout 400 python bench.py --impl reference --steps 60 > gpurun_out/bench_r02_reference.json 2> gpurun_out/bench_r02_reference.err; tail -c 300 gpurun_out/bench_r02_reference.err
