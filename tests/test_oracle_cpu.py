@@ -339,3 +339,39 @@ def test_whole_update_is_consistent(oracle, cfg):
     assert np.all(np.diag(r["P"]) <= np.diag(case.P) + 1e-18) and np.linalg.eigvalsh(r["P"]).min() > -1e-12
     # rejected features are reported with the reference's reasons
     assert set(np.unique(r["out"].status)).issubset({0, 2, 3, 5, 6, 8})
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_camera_model_against_opencv(oracle, model):
+    """Third-party pin of CamRadtan / CamEqui (ov_core/src/cam/CamRadtan.h:89-185, CamEqui.h:91-199): OpenCV's own projection
+    functions — the library the reference links and whose conventions its camera classes restate — give the distorted pixel and
+    its analytic Jacobians with respect to the normalised point and to (fx, fy, cx, cy, d1..d4). cv2.projectPoints is the
+    plumb-bob model (k1, k2, p1, p2), cv2.fisheye.projectPoints the equidistant one (k1..k4)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    intr = np.array(sim._INTR[0] if model == 0 else sim._INTR_EQUI, dtype=np.float64)
+    K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
+    D = intr[4:8].copy()
+    uv, dzn, dzeta = np.zeros(2), np.zeros(4), np.zeros(16)
+    zero3 = np.zeros(3)
+    for _ in range(40):
+        x, y = rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4)
+        X = np.array([[[x, y, 1.0]]])
+        if model == 0:
+            img, jac = cv2.projectPoints(X, zero3, zero3, K, D)
+            # columns: rvec(3) tvec(3) f(2) c(2) dist(k1 k2 p1 p2 ...)
+            d_point = jac[:, 3:5]  # d uv / d (X, Y) at Z = 1 = d uv / d (xn, yn)
+            d_intr = np.hstack([jac[:, 6:8], jac[:, 8:10], jac[:, 10:14]])
+        else:
+            img, jac = cv2.fisheye.projectPoints(X, zero3, zero3, K, D)
+            # columns: f(2) c(2) k(4) rvec(3) tvec(3) alpha(1)
+            d_point = jac[:, 11:13]
+            d_intr = jac[:, 0:8]
+        ref = np.asarray(img, dtype=np.float64).ravel()
+        oracle.lib().ovo_distort_d(C.c_int(model), intr.ctypes.data_as(capi.c_double_p), C.c_double(x), C.c_double(y),
+                                   uv.ctypes.data_as(capi.c_double_p))
+        assert np.all(np.abs(uv - ref) <= 4e-5)  # distort_d rounds the pixel to float32 (cam/CamBase.h:130-135)
+        oracle.lib().ovo_distort_jacobian(C.c_int(model), intr.ctypes.data_as(capi.c_double_p), C.c_double(x), C.c_double(y),
+                                          dzn.ctypes.data_as(capi.c_double_p), dzeta.ctypes.data_as(capi.c_double_p))
+        assert np.allclose(dzn.reshape(2, 2), d_point, rtol=1e-9, atol=1e-9)
+        assert np.allclose(dzeta.reshape(2, 8), d_intr, rtol=1e-9, atol=1e-9)
