@@ -52,6 +52,47 @@ int main(int argc, char **argv) {
     }
     return 0;
   }
+  if (cmd == "propmean" && argc >= 4) {
+    // K steps of the mean propagation (predict_mean_*, state/Propagator.cpp:482-681) with constant raw IMU readings, identity
+    // intrinsics, zero biases: prints R_GtoI (row-major), p_IinG, v_IinG for comparison with an ODE solver
+    const std::string m = argv[2];
+    const int K = std::atoi(argv[3]);
+    VioOptions vo;
+    vo.integration_method = m == "discrete" ? INTEGRATION_DISCRETE : (m == "analytical" ? INTEGRATION_ANALYTICAL : INTEGRATION_RK4);
+    struct NullCov2 : CovBackend {
+      int dim() override { return 0; }
+      void set(const std::vector<double> &, int) override {}
+      std::vector<double> get() override { return {}; }
+      std::vector<double> get_marginal(const std::vector<int> &, const std::vector<int> &) override { return {}; }
+      void clone(int, int, const double *, int) override {}
+      void marginalize(int, int) override {}
+      void propagate(int, int, const std::vector<int> &, const std::vector<int> &, const std::vector<double> &, const std::vector<double> &) override {}
+      int msckf_update(const ovb_frame *, const ovb_feat_batch *, const ovb_opts *, ovb_feat_out *, double *, ovb_stats *) override { return 0; }
+    };
+    VioManager sys(vo, sp, std::make_shared<NullCov2>());
+    VioState st = sys.state;
+    st.q = st.q_fej = quatnorm({0.1, -0.2, 0.3, 0.9});
+    st.p = st.p_fej = {1, 2, 3};
+    st.v = st.v_fej = {0.5, -0.3, 0.2};
+    st.bg = {0, 0, 0};
+    st.ba = {0, 0, 0};
+    ImuData d0, d1;
+    d0.wm = d1.wm = {0.3, -0.2, 0.5};
+    d0.am = d1.am = {0.5, 9.6, 1.0};
+    Propagator prop(9.81);
+    const double dt = 0.0025;
+    const Mat3 R0 = quat_2_Rot(st.q);
+    std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", R0[0], R0[1], R0[2], R0[3], R0[4], R0[5], R0[6], R0[7], R0[8]);
+    for (int k = 0; k < K; k++) {
+      d0.timestamp = k * dt, d1.timestamp = (k + 1) * dt;
+      std::vector<double> F, Qd;
+      prop.predict_and_compute(st, d0, d1, F, Qd);
+    }
+    const Mat3 R = quat_2_Rot(st.q);
+    std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7],
+                R[8], st.p[0], st.p[1], st.p[2], st.v[0], st.v[1], st.v[2]);
+    return 0;
+  }
   if (cmd == "propfd" && argc >= 3) {
     const std::string m = argv[2];
     VioOptions vo;

@@ -98,3 +98,31 @@ def test_simulation_is_repeatable_and_consistent(exes, tmp_path):
 def test_stereo_calib_off_runs(exes):
     r = simrun.run(exe=exes["oracle"], traj=TRAJ, cams=2, clones=8, msckf=20, pts=100, frames=60, calib=0)
     assert r["state_dim"] == 15 + 6 * 8 and r["ate_pos_m"] < 0.2
+
+
+@pytest.mark.parametrize("method,tol_p,tol_v,tol_R", [("analytical", 1e-10, 1e-10, 1e-11), ("rk4", 1e-8, 1e-8, 1e-10), ("discrete", 2e-2, 2e-2, 1e-11)])
+def test_mean_propagation_against_ode_solver(exes, method, tol_p, tol_v, tol_R):
+    """Third-party pin of predict_mean_{analytic,rk4,discrete} (state/Propagator.cpp:482-681): one second of IMU kinematics with
+    constant body-frame readings, against scipy's adaptive ODE solver on  R' = R [w]x,  v' = R a - g e_z,  p' = v  (R = R_ItoG).
+    The analytical integrator is exact for constant readings, RK4 fourth order; the discrete one holds the attitude over each
+    step for the velocity / position update (first order: its bound is that error, not a tolerance on the others)."""
+    from scipy.integrate import solve_ivp
+    K, dt = 400, 0.0025
+    first, last = _probe(exes, "propmean", method, K)
+    R0 = first.reshape(3, 3).T  # the probe prints R_GtoI
+    w, a, g = np.array([0.3, -0.2, 0.5]), np.array([0.5, 9.6, 1.0]), np.array([0.0, 0.0, 9.81])
+
+    def skew(x):
+        return np.array([[0, -x[2], x[1]], [x[2], 0, -x[0]], [-x[1], x[0], 0]])
+
+    def rhs(t, y):
+        R = y[:9].reshape(3, 3)
+        return np.concatenate([(R @ skew(w)).ravel(), y[12:15], R @ a - g])
+    y0 = np.concatenate([R0.ravel(), [1, 2, 3], [0.5, -0.3, 0.2]])
+    sol = solve_ivp(rhs, [0, K * dt], y0, method="DOP853", rtol=1e-13, atol=1e-14)
+    yT = sol.y[:, -1]
+    R_ref, p_ref, v_ref = yT[:9].reshape(3, 3), yT[9:12], yT[12:15]
+    R_got, p_got, v_got = last[:9].reshape(3, 3).T, last[9:12], last[12:15]
+    assert np.abs(R_got - R_ref).max() <= tol_R
+    assert np.abs(p_got - p_ref).max() <= tol_p
+    assert np.abs(v_got - v_ref).max() <= tol_v
