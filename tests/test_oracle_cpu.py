@@ -375,3 +375,43 @@ def test_camera_model_against_opencv(oracle, model):
                                           dzn.ctypes.data_as(capi.c_double_p), dzeta.ctypes.data_as(capi.c_double_p))
         assert np.allclose(dzn.reshape(2, 2), d_point, rtol=1e-9, atol=1e-9)
         assert np.allclose(dzeta.reshape(2, 8), d_intr, rtol=1e-9, atol=1e-9)
+
+
+def test_gauss_newton_against_scipy_least_squares(oracle):
+    """Third-party pin of single_gaussnewton (feat/FeatureInitializer.cpp:197-335): the refined point minimises the
+    reprojection error in the anchor frame over (alpha, beta, rho); scipy.optimize.least_squares on the same cost (double
+    precision, no float casts) lands on the same minimiser up to the reference's own stopping rule (min_dx = 1e-6 on the
+    inverse-depth parameters) and float32 residuals."""
+    from scipy.optimize import least_squares
+    case = _case(n_feats=60, n_cams=2, n_clones=12, seed=9, outlier_frac=0.0, degenerate_frac=0.0)
+    out, _ = oracle.triangulate(case.frame, case.feats, capi.default_opts(refine_features=1))
+    ok = np.nonzero(out.status == capi.FEAT_OK)[0]
+    assert len(ok) > 40
+    fr, fb = case.frame, case.feats
+    worst = 0.0
+    for f in ok[:25]:
+        acam, acl = int(out.anchor_cam[f]), int(out.anchor_clone[f])
+        R_GtoA = fr.cam_R[acam].reshape(3, 3) @ fr.clone_R[acl].reshape(3, 3)
+        p_AinG = fr.clone_p[acl] - R_GtoA.T @ fr.cam_p[acam]
+        rows = range(fb.meas_off[f], fb.meas_off[f + 1])
+        poses = []
+        for i in rows:
+            cam, cl = int(fb.cam[i]), int(fb.clone[i])
+            R_GtoC = fr.cam_R[cam].reshape(3, 3) @ fr.clone_R[cl].reshape(3, 3)
+            p_CinG = fr.clone_p[cl] - R_GtoC.T @ fr.cam_p[cam]
+            poses.append((R_GtoC @ R_GtoA.T, R_GtoA @ (p_CinG - p_AinG), fb.uvn[i].astype(np.float64)))
+
+        def resid(x):
+            a, b, rho = x
+            r = []
+            for R_AtoC, p_CinA, z in poses:
+                h = R_AtoC @ (np.array([a, b, 1.0]) - rho * p_CinA)
+                r += [z[0] - h[0] / h[2], z[1] - h[1] / h[2]]
+            return np.array(r)
+        pA = out.p_FinA[f]
+        x0 = np.array([pA[0] / pA[2], pA[1] / pA[2], 1.0 / pA[2]])
+        sol = least_squares(resid, x0, method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14)
+        # the oracle's point is (numerically) a stationary point already: scipy moves it by less than the LM stopping tolerance
+        worst = max(worst, float(np.abs(sol.x - x0).max()))
+        assert np.sum(resid(x0) ** 2) <= np.sum(sol.fun ** 2) * (1 + 1e-6) + 1e-12
+    assert worst <= 5e-6  # measured 2.1e-7
