@@ -3,6 +3,8 @@
 //   sim_probe distort xn yn            -> u v
 //   sim_probe spline TRAJ t            -> R(9) p(3) w(3) v(3) alpha(3) a(3) start_time
 //   sim_probe propfd METHOD            -> max |F_analytic - F_numeric| over the 15+24 state, and |F| for scale
+//   sim_probe propmean METHOD K        -> R_GtoI before / R_GtoI p v after K steps of mean propagation with constant readings
+//   sim_probe simproj TRAJ             -> noise-free simulator frames: state, calibration, map points and their pixels
 #include "../../include/ovb200_vio.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -49,6 +51,56 @@ int main(int argc, char **argv) {
       for (const Vec3 *q : {&p, &w, &v, &al, &a})
         for (double x : *q) std::printf(" %.17g", x);
       std::printf(" %.17g\n", s.get_start_time());
+    }
+    return 0;
+  }
+  if (cmd == "simproj" && argc >= 3) {
+    // first camera frames of a noise-free simulator: ground-truth IMU state, extrinsics, intrinsics and, per camera, the
+    // map points with their simulated pixels — for a projection with OpenCV on the Python side
+    const std::string traj = argv[2];
+    auto data = traj.substr(traj.size() - 4) == ".bin" ? load_trajectory_bin(traj) : load_simulated_trajectory(traj);
+    sp.sigma_pix = 0.0;
+    sp.num_pts = 60;
+    Simulator sim(sp, data);
+    int frames = 0;
+    bool pending = false;
+    double tc_pending = 0;
+    std::vector<int> camids_p;
+    std::vector<std::vector<SimFeat>> feats_p;
+    while (sim.ok() && frames < 3) {
+      double t;
+      Vec3 wm, am;
+      sim.get_next_imu(t, wm, am);
+      std::array<double, 17> st;
+      // the true-bias history (which get_state interpolates) trails the camera time by an IMU sample: ask again after the next one
+      if (pending && sim.get_state(tc_pending + sp.calib_camimu_dt, st)) {
+        pending = false;
+        frames++;
+        for (size_t c = 0; c < camids_p.size(); c++) {
+          const int cam = camids_p[c];
+          std::printf("FRAME %d %zu", cam, feats_p[c].size());
+          for (int k = 1; k < 8; k++) std::printf(" %.17g", st[(size_t)k]); // q_GtoI (JPL xyzw), p_IinG
+          const Vec4 &qe = sp.camera_extrinsics[(size_t)cam].first;
+          const Vec3 &pe = sp.camera_extrinsics[(size_t)cam].second;
+          std::printf(" %.17g %.17g %.17g %.17g %.17g %.17g %.17g", qe[0], qe[1], qe[2], qe[3], pe[0], pe[1], pe[2]);
+          for (int k = 0; k < 8; k++) std::printf(" %.17g", sp.camera_intrinsics[(size_t)cam].d[k]);
+          std::printf("\n");
+          for (const SimFeat &f : feats_p[c]) {
+            const size_t id = sp.use_stereo ? f.id : f.id - (size_t)cam * sim.featmap.size();
+            const Vec3 &P = sim.featmap.at(id);
+            std::printf("%.17g %.17g %.17g %.9g %.9g\n", P[0], P[1], P[2], (double)f.u, (double)f.v);
+          }
+        }
+      }
+      double tc;
+      std::vector<int> camids;
+      std::vector<std::vector<SimFeat>> feats;
+      if (!pending && sim.get_next_cam(tc, camids, feats)) {
+        pending = true;
+        tc_pending = tc;
+        camids_p = camids;
+        feats_p = feats;
+      }
     }
     return 0;
   }

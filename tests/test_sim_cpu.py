@@ -126,3 +126,39 @@ def test_mean_propagation_against_ode_solver(exes, method, tol_p, tol_v, tol_R):
     assert np.abs(R_got - R_ref).max() <= tol_R
     assert np.abs(p_got - p_ref).max() <= tol_p
     assert np.abs(v_got - v_ref).max() <= tol_v
+
+
+def test_simulated_pixels_against_opencv_projection(exes):
+    """Third-party pin of the simulator's measurement geometry (Simulator::project_pointcloud, sim/Simulator.cpp:455-499) and of
+    the conventions it rests on: the ground-truth JPL quaternion q_GtoI and the extrinsics (q_ItoC, p_IinC) are turned into
+    OpenCV's world-to-camera pose with scipy's (Hamilton) quaternions — R_JPL(q) = R_Hamilton(q)' — and the map points go
+    through cv2.projectPoints with the camera's plumb-bob intrinsics. The simulator's noise-free float32 pixels agree to
+    float32 rounding."""
+    cv2 = pytest.importorskip("cv2")
+    from scipy.spatial.transform import Rotation
+    out = subprocess.run([exes["probe"], "simproj", TRAJ], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    i, frames, worst = 0, 0, 0.0
+    while i < len(out):
+        head = out[i].split()
+        assert head[0] == "FRAME"
+        n = int(head[2])
+        v = np.array([float(x) for x in head[3:]])
+        q_GtoI, p_IinG, q_ItoC, p_IinC, intr = v[0:4], v[4:7], v[7:11], v[11:14], v[14:22]
+        pts = np.array([[float(x) for x in line.split()] for line in out[i + 1:i + 1 + n]])
+        i += 1 + n
+        if n == 0:
+            continue
+        R_GtoI = Rotation.from_quat(q_GtoI).as_matrix().T
+        R_ItoC = Rotation.from_quat(q_ItoC).as_matrix().T
+        R_GtoC = R_ItoC @ R_GtoI
+        t = R_ItoC @ (-R_GtoI @ p_IinG) + p_IinC
+        K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
+        img, _ = cv2.projectPoints(pts[:, :3].reshape(-1, 1, 3), cv2.Rodrigues(R_GtoC)[0], t, K, intr[4:8])
+        err = np.abs(img.reshape(-1, 2) - pts[:, 3:5]).max()
+        worst = max(worst, float(err))
+        frames += 1
+        # every simulated point is in front of the camera, inside the image
+        pc = (R_GtoC @ pts[:, :3].T).T + t
+        assert np.all(pc[:, 2] > 0.1) and np.all((pts[:, 3] >= 0) & (pts[:, 3] <= 752) & (pts[:, 4] >= 0) & (pts[:, 4] <= 480))
+    assert frames >= 4
+    assert worst <= 5e-4  # pixels (measured 5.6e-5): float32 normalised coordinates times a 458 px focal length
