@@ -415,3 +415,33 @@ def test_gauss_newton_against_scipy_least_squares(oracle):
         worst = max(worst, float(np.abs(sol.x - x0).max()))
         assert np.sum(resid(x0) ** 2) <= np.sum(sol.fun ** 2) * (1 + 1e-6) + 1e-12
     assert worst <= 5e-6  # measured 2.1e-7
+
+
+def test_residual_and_feature_jacobian_against_opencv(oracle):
+    """Third-party pin of the measurement model in get_feature_jacobian_full (update/UpdaterHelper.cpp:313-393): for every
+    measurement, the residual is the tracked pixel minus OpenCV's projection of p_FinG through the clone / extrinsic pose, and
+    H_f (GLOBAL_3D) is OpenCV's Jacobian with respect to the camera-frame point times R_GtoC."""
+    cv2 = pytest.importorskip("cv2")
+    case = _case(n_feats=12, n_cams=2, n_clones=8, seed=21, outlier_frac=0.0, degenerate_frac=0.0)
+    opts = capi.default_opts(feat_rep=capi.REP_GLOBAL_3D, do_fej=0)
+    fr, fb = case.frame, case.feats
+    tri, _ = oracle.triangulate(fr, fb, opts)
+    cols = np.concatenate([np.arange(o, o + 6) for o in fr.clone_off])
+    Hf, Hx, res, row_off = oracle.feature_jacobians(fr, fb, opts, tri, 0, cols)
+    checked = 0
+    for f in np.nonzero(tri.status == capi.FEAT_OK)[0]:
+        r0 = int(row_off[f])
+        for k, i in enumerate(range(fb.meas_off[f], fb.meas_off[f + 1])):
+            cam, cl = int(fb.cam[i]), int(fb.clone[i])
+            R_GtoC = fr.cam_R[cam].reshape(3, 3) @ fr.clone_R[cl].reshape(3, 3)
+            t = fr.cam_R[cam].reshape(3, 3) @ (-fr.clone_R[cl].reshape(3, 3) @ fr.clone_p[cl]) + fr.cam_p[cam]
+            intr = fr.cam_intr[cam]
+            K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
+            img, jac = cv2.projectPoints(tri.p_FinG[f].reshape(1, 1, 3), cv2.Rodrigues(R_GtoC)[0], t, K, intr[4:8])
+            ref_res = fb.uv[i].astype(np.float64) - img.ravel()
+            assert np.all(np.abs(res[r0 + 2 * k:r0 + 2 * k + 2] - ref_res) <= 6e-5)  # distort_d rounds the pixel to float32
+            ref_Hf = jac[:, 3:6] @ R_GtoC
+            got = Hf[r0 + 2 * k:r0 + 2 * k + 2]
+            assert np.allclose(got, ref_Hf, rtol=1e-9, atol=1e-9 * np.abs(ref_Hf).max())
+            checked += 1
+    assert checked > 60
