@@ -445,3 +445,40 @@ def test_residual_and_feature_jacobian_against_opencv(oracle):
             assert np.allclose(got, ref_Hf, rtol=1e-9, atol=1e-9 * np.abs(ref_Hf).max())
             checked += 1
     assert checked > 60
+
+
+@pytest.mark.parametrize("calib", [False, True])
+def test_msckf_gate_against_scipy_nullspace(oracle, calib):
+    """Third-party pin of nullspace_project_inplace + the chi² gate (update/UpdaterHelper.cpp:426-454, UpdaterMSCKF.cpp:209-234):
+    chi² does not depend on the basis of the left nullspace of H_f, so scipy.linalg.null_space (LAPACK SVD) in place of the
+    reference's Givens sweep, numpy's solve in place of its LLT, and the pre-nullspace Jacobians must reproduce the value the
+    oracle reports for every feature that reaches the gate; and the gate decision follows scipy's 0.95 quantile."""
+    from scipy.linalg import null_space
+    from scipy.stats import chi2 as chi2_dist
+    case = _case(n_feats=40, n_cams=2, n_clones=9, seed=31, calib_ext=calib, calib_intr=calib)
+    opts = capi.default_opts(do_calib_camera_pose=int(calib), do_calib_camera_intrinsics=int(calib))
+    r = oracle.msckf_update(case.frame, case.feats, opts, case.P)
+    out = r["out"]
+    N = case.P.shape[0]
+    cols = np.arange(N)
+    pre = capi.FeatOut(case.feats.n_feats)
+    for k in ("status", "p_FinA", "p_FinG", "anchor_cam", "anchor_clone"):
+        getattr(pre, k)[...] = getattr(out, k)
+    reached = np.isin(out.status, (capi.FEAT_OK, capi.FEAT_CHI2))
+    pre.status[reached] = capi.FEAT_OK  # rebuild the Jacobians of everything that was triangulated, gated or not
+    Hf, Hx, res, row_off = oracle.feature_jacobians(case.frame, case.feats, opts, pre, 0, cols)
+    s2 = float(opts.sigma_pix) ** 2
+    n = 0
+    for f in np.nonzero(reached)[0]:
+        a, b = int(row_off[f]), int(row_off[f + 1])
+        if b - a < 4:
+            continue
+        Nl = null_space(Hf[a:b].T)  # (2M) x (2M-3)
+        Ho, ro = Nl.T @ Hx[a:b], Nl.T @ res[a:b]
+        S = Ho @ case.P @ Ho.T + s2 * np.eye(Ho.shape[0])
+        chi2 = float(ro @ np.linalg.solve(S, ro))
+        assert abs(chi2 - out.chi2[f]) <= 1e-9 * chi2
+        accept = chi2 <= float(opts.chi2_multipler) * chi2_dist.ppf(0.95, Ho.shape[0])
+        assert (out.status[f] == capi.FEAT_OK) == accept
+        n += 1
+    assert n > 20
