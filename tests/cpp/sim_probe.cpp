@@ -4,8 +4,10 @@
 //   sim_probe spline TRAJ t            -> R(9) p(3) w(3) v(3) alpha(3) a(3) start_time
 //   sim_probe propfd METHOD            -> max |F_analytic - F_numeric| over the 15+24 state, and |F| for scale
 //   sim_probe propmean METHOD K        -> R_GtoI before / R_GtoI p v after K steps of mean propagation with constant readings
+//   sim_probe propq METHOD             -> n dt sigma_w sigma_a sigma_wb sigma_ab / diag(Q_d)[0..15) of one IMU step
 //   sim_probe simproj TRAJ             -> noise-free simulator frames: state, calibration, map points and their pixels
 #include "../../include/ovb200_vio.hpp"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -102,6 +104,39 @@ int main(int argc, char **argv) {
         feats_p = feats;
       }
     }
+    return 0;
+  }
+  if (cmd == "propq" && argc >= 3) {
+    // diagonal of the discrete process noise Q_d of ONE IMU step (identity intrinsics, zero biases), and dt
+    const std::string m = argv[2];
+    VioOptions vo;
+    vo.integration_method = m == "discrete" ? INTEGRATION_DISCRETE : (m == "analytical" ? INTEGRATION_ANALYTICAL : INTEGRATION_RK4);
+    struct NullCov3 : CovBackend {
+      int dim() override { return 0; }
+      void set(const std::vector<double> &, int) override {}
+      std::vector<double> get() override { return {}; }
+      std::vector<double> get_marginal(const std::vector<int> &, const std::vector<int> &) override { return {}; }
+      void clone(int, int, const double *, int) override {}
+      void marginalize(int, int) override {}
+      void propagate(int, int, const std::vector<int> &, const std::vector<int> &, const std::vector<double> &, const std::vector<double> &) override {}
+      int msckf_update(const ovb_frame *, const ovb_feat_batch *, const ovb_opts *, ovb_feat_out *, double *, ovb_stats *) override { return 0; }
+    };
+    VioManager sys(vo, sp, std::make_shared<NullCov3>());
+    VioState st = sys.state;
+    st.q = st.q_fej = quatnorm({0.1, -0.2, 0.3, 0.9});
+    st.p = st.p_fej = {1, 2, 3};
+    st.v = st.v_fej = {0.5, -0.3, 0.2};
+    ImuData d0, d1;
+    d0.timestamp = 0, d1.timestamp = 0.0025;
+    d0.wm = d1.wm = {0.3, -0.2, 0.5};
+    d0.am = d1.am = {0.5, 9.6, 1.0};
+    Propagator prop(9.81);
+    std::vector<double> F, Qd;
+    prop.predict_and_compute(st, d0, d1, F, Qd);
+    const int n = (int)std::lround(std::sqrt((double)Qd.size()));
+    std::printf("%d %.17g %.17g %.17g %.17g %.17g\n", n, d1.timestamp - d0.timestamp, vo.sigma_w, vo.sigma_a, vo.sigma_wb, vo.sigma_ab);
+    for (int i = 0; i < 15; i++) std::printf("%.17g ", Qd[(size_t)i * n + i]);
+    std::printf("\n");
     return 0;
   }
   if (cmd == "propmean" && argc >= 4) {

@@ -162,3 +162,20 @@ def test_simulated_pixels_against_opencv_projection(exes):
         assert np.all(pc[:, 2] > 0.1) and np.all((pts[:, 3] >= 0) & (pts[:, 3] <= 752) & (pts[:, 4] >= 0) & (pts[:, 4] <= 480))
     assert frames >= 4
     assert worst <= 5e-4  # pixels (measured 5.6e-5): float32 normalised coordinates times a 458 px focal length
+
+
+@pytest.mark.parametrize("method", ["discrete", "rk4", "analytical"])
+def test_process_noise_scaling(exes, method):
+    """Textbook pin of the discrete process noise (state/Propagator.cpp:510-530, 900-1016): over one IMU step of length dt the
+    orientation / velocity errors integrate white noise of density sigma_w / sigma_a (variance sigma^2 dt) and the biases are
+    random walks of density sigma_wb / sigma_ab (variance sigma^2 dt) — to first order in dt whatever the integrator; the
+    position variance is third order (sigma_a^2 dt^3 / 3 up to the integrator's constant)."""
+    head, diag = _probe(exes, "propq", method)
+    n, dt, sw, sa, swb, sab = head
+    assert int(n) == 39
+    th, p, v, bg, ba = diag[0:3], diag[3:6], diag[6:9], diag[9:12], diag[12:15]
+    assert np.allclose(th, sw**2 * dt, rtol=5e-3)
+    assert np.allclose(v, sa**2 * dt, rtol=5e-3)
+    assert np.allclose(bg, swb**2 * dt, rtol=1e-9) and np.allclose(ba, sab**2 * dt, rtol=1e-9)
+    assert np.all(p > 0) and np.all(p < sa**2 * dt**3)  # between dt^3/4 and dt^3/3 times sigma_a^2 for every integrator
+    assert np.all(p > 0.2 * sa**2 * dt**3)
